@@ -1,0 +1,134 @@
+"""Multi-GPU sharding: one process per GPU, torch.distributed for the plumbing.
+
+The front-end shards without any data-path exchange:
+  * sequence (configs 2/3): contiguous blocks of frame pairs per rank, balanced by descriptor-pair
+    work; a rank also runs the stereo stage of its right halo frame;
+  * loop closure (config 4): the lower-triangular (keyframe, earlier keyframe) candidate list is
+    cut into blocks balanced by Nq*Nt;
+  * dense sweep (config 5): the TRAIN set is cut into slices, queries are replicated, every rank
+    emits per-query top-2 keys with GLOBAL train indices.
+The only collective is one all-gather of the per-shard result tables (NCCL over NVLink on GPUs,
+gloo in the CPU tests); the top-2 tables are then min-merged (exact, keys are totally ordered).
+The partitioning / merge logic below is pure host code and backend-agnostic.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from torchrun's environment; returns (rank, world, local_rank)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local_rank)
+    return rank, world, local_rank
+
+
+def balanced_ranges(work, world):
+    """Cut len(work) consecutive units into `world` contiguous ranges of near-equal total work.
+    Returns an int64 array of world+1 boundaries."""
+    work = np.asarray(work, dtype=np.float64)
+    n = len(work)
+    bounds = np.zeros(world + 1, dtype=np.int64)
+    if n == 0:
+        return bounds
+    csum = np.concatenate([[0.0], np.cumsum(work)])
+    total = csum[-1]
+    for r in range(1, world):
+        target = total * r / world
+        b = int(np.searchsorted(csum, target, side="left"))
+        if b > 0 and b <= n and target - csum[b - 1] < csum[b] - target:
+            b -= 1  # the boundary whose prefix sum is nearest to the target
+        # keep boundaries monotone and leave at least zero units per rank
+        bounds[r] = min(max(b, bounds[r - 1]), n)
+    bounds[world] = n
+    return bounds
+
+
+def frame_pair_shards(n_l, n_r, world):
+    """Shard frames by stereo work Nl*Nr.  Returns boundaries b: rank r owns frames
+    [b[r], b[r+1]) and the frame pairs (f, f+1) for f in that range (f+1 < n_frames)."""
+    n_l, n_r = np.asarray(n_l, dtype=np.int64), np.asarray(n_r, dtype=np.int64)
+    return balanced_ranges(n_l * n_r, world)
+
+
+def candidate_pairs(n_keyframes):
+    """All (keyframe i, earlier keyframe j < i) pairs, row-major: the brute-force superset of
+    loop_closure.py:315-348's gated candidates (BASELINE config 4)."""
+    i, j = np.tril_indices(n_keyframes, k=-1)
+    return np.stack([i, j], axis=1).astype(np.int32)
+
+
+def candidate_blocks(pairs, sizes, world):
+    """Cut the candidate pair list into `world` contiguous blocks balanced by Nq*Nt."""
+    sizes = np.asarray(sizes, dtype=np.int64)
+    return balanced_ranges(sizes[pairs[:, 0]] * sizes[pairs[:, 1]], world)
+
+
+def train_slices(n_train, world, align=16):
+    """Boundaries of the train-set slices for the dense sweep (multiples of `align` rows so every
+    slice starts 16-byte aligned in the 61-byte-row layout)."""
+    per = -(-n_train // world)
+    per = -(-per // align) * align
+    b = np.minimum(np.arange(world + 1, dtype=np.int64) * per, n_train)
+    return b
+
+
+def merge_top2_host(shard_keys):
+    """Host restatement of slamfe_merge_top2 on uint32 keys (n_shards, nq, 2) -> (nq, 2)."""
+    k = np.asarray(shard_keys).view(np.uint32)
+    flat = np.concatenate([k[s] for s in range(k.shape[0])], axis=1)
+    flat.sort(axis=1)
+    return np.ascontiguousarray(flat[:, :2])
+
+
+def all_gather_padded(t, lengths=None):
+    """All-gather a per-rank tensor whose leading dimension differs between ranks.
+
+    Returns (gathered (world, max_len, ...), lengths (world,)) — fixed-stride tables, one
+    collective for the payload (plus one tiny one for the lengths when they are not given)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return t.unsqueeze(0), np.array([t.shape[0]], dtype=np.int64)
+    world = dist.get_world_size()
+    if lengths is None:
+        ln = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        all_ln = torch.empty((world,), dtype=torch.int64, device=t.device)
+        dist.all_gather_into_tensor(all_ln, ln)
+        lengths = all_ln.cpu().numpy()
+    max_len = int(max(lengths))
+    pad = torch.zeros((max_len,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    out = torch.empty((world, max_len) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, pad)
+    return out, np.asarray(lengths, dtype=np.int64)
+
+
+def sharded_knn(q_dev, t_shard_dev, t_index_base, desc_bytes=None):
+    """Dense sweep (config 5): this rank's train slice vs all queries, all-gather, exact merge.
+    Returns the global (nq, 2) key table on every rank."""
+    import torch.distributed as dist
+    from . import ops
+    row_keys, _ = ops.hamming_top2(q_dev, t_shard_dev, desc_bytes=desc_bytes, t_index_base=int(t_index_base))
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return row_keys
+    import torch
+    world = dist.get_world_size()
+    gathered = torch.empty((world,) + tuple(row_keys.shape), dtype=row_keys.dtype, device=row_keys.device)
+    dist.all_gather_into_tensor(gathered, row_keys)
+    return ops.merge_top2(gathered)

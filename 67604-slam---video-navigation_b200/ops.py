@@ -1,0 +1,246 @@
+"""Device-level operators: torch tensors in, torch tensors out, libslamfe kernels underneath.
+
+PyTorch is used for memory ownership and streams only; every computation is a hand-written
+sm_100a kernel reached through the C-ABI (include/slamfe.h).  All functions are asynchronous on
+the current CUDA stream and raise if the library or the GPU is missing (no CPU fallback).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import KEY_IDX_BITS, KEY_IDX_MASK, KEY_NONE, check, load_library, ptr, stream_handle
+
+
+def _torch():
+    return _cabi.require_cuda()
+
+
+def _desc_tensor(d):
+    torch = _torch()
+    if d.dtype != torch.uint8 or d.dim() != 2 or not d.is_cuda:
+        raise ValueError("descriptors must be a 2-D uint8 CUDA tensor")
+    if d.stride(1) != 1:
+        d = d.contiguous()
+    return d
+
+
+def hamming_top2(q, t, desc_bytes=None, want_cols=False, t_index_base=0):
+    """Top-2 Hamming neighbours of every row of q among the rows of t.
+
+    q, t: (N, stride) uint8 CUDA tensors (stride 61 = cv2 layout, or 64-byte padded rows);
+    desc_bytes defaults to the row width.  Returns (row_keys (Nq, 2) int32-viewed-uint32,
+    col_keys (Nt,) or None).  Key = distance << 22 | index; see include/slamfe.h.
+    """
+    torch = _torch()
+    q, t = _desc_tensor(q), _desc_tensor(t)
+    nq, nt = q.shape[0], t.shape[0]
+    desc_bytes = q.shape[1] if desc_bytes is None else desc_bytes
+    row_keys = torch.empty((nq, 2), dtype=torch.int32, device=q.device)
+    col_keys = torch.empty((nt,), dtype=torch.int32, device=q.device) if want_cols else None
+    with torch.cuda.device(q.device):
+        check(load_library().slamfe_hamming_top2(
+            ptr(q), nq, q.stride(0), ptr(t), nt, t.stride(0) if nt else max(desc_bytes, 1), desc_bytes, t_index_base,
+            ptr(row_keys), ptr(col_keys), stream_handle()), "slamfe_hamming_top2")
+    return row_keys, col_keys
+
+
+def hamming_top2_batched(q, q_off, t, t_off, n_problems, max_nq, max_nt, desc_bytes,
+                         q_cnt=None, t_cnt=None, want_cols=False, row_keys=None, col_keys=None):
+    """Ragged batch of matching problems in one launch (slamfe_hamming_top2_batched).
+
+    q_off / t_off / q_cnt / t_cnt are int32 CUDA tensors (see include/slamfe.h); keys are indexed
+    by global row and hold problem-local indices.
+    """
+    torch = _torch()
+    q, t = _desc_tensor(q), _desc_tensor(t)
+    if row_keys is None:
+        row_keys = torch.empty((q.shape[0], 2), dtype=torch.int32, device=q.device)
+    if want_cols and col_keys is None:
+        col_keys = torch.empty((t.shape[0],), dtype=torch.int32, device=q.device)
+    with torch.cuda.device(q.device):
+        check(load_library().slamfe_hamming_top2_batched(
+            ptr(q), q.stride(0), ptr(q_off), ptr(q_cnt), ptr(t), t.stride(0), ptr(t_off), ptr(t_cnt),
+            n_problems, max_nq, max_nt, desc_bytes,
+            ptr(row_keys), q.shape[0], ptr(col_keys) if want_cols else 0, t.shape[0], stream_handle()),
+            "slamfe_hamming_top2_batched")
+    return row_keys, (col_keys if want_cols else None)
+
+
+def unpack_keys(keys):
+    """keys (...,) -> (idx, dist) int32 tensors of the same shape, -1 where no neighbour."""
+    torch = _torch()
+    keys = keys.contiguous()
+    idx = torch.empty_like(keys)
+    dist = torch.empty_like(keys)
+    with torch.cuda.device(keys.device):
+        check(load_library().slamfe_unpack_keys(ptr(keys), keys.numel(), ptr(idx), ptr(dist), stream_handle()),
+              "slamfe_unpack_keys")
+    return idx, dist
+
+
+def merge_top2(shard_keys):
+    """(n_shards, nq, 2) keys -> (nq, 2) global top-2 (exact: keys carry global indices)."""
+    torch = _torch()
+    shard_keys = shard_keys.contiguous()
+    n_shards, nq = shard_keys.shape[0], shard_keys.shape[1]
+    out = torch.empty((nq, 2), dtype=torch.int32, device=shard_keys.device)
+    with torch.cuda.device(out.device):
+        check(load_library().slamfe_merge_top2(ptr(shard_keys), n_shards, nq, ptr(out), stream_handle()),
+              "slamfe_merge_top2")
+    return out
+
+
+def cross_check(row_keys, col_keys):
+    """crossCheck epilogue: (match_t, match_dist) int32 (nq,), -1 where the pair is not mutual."""
+    torch = _torch()
+    nq, nt = row_keys.shape[0], col_keys.shape[0]
+    mt = torch.empty((nq,), dtype=torch.int32, device=row_keys.device)
+    md = torch.empty((nq,), dtype=torch.int32, device=row_keys.device)
+    with torch.cuda.device(mt.device):
+        check(load_library().slamfe_cross_check(ptr(row_keys), ptr(col_keys), nq, nt, ptr(mt), ptr(md),
+                                                stream_handle()), "slamfe_cross_check")
+    return mt, md
+
+
+def ratio_test(row_keys, num=5, den=3):
+    """mask[i] = num * d1 < den * d2  (5*d1 < 3*d2 == d1 < 0.6*d2, VAN_ex/code/ex1.py:118-122)."""
+    torch = _torch()
+    nq = row_keys.shape[0]
+    mask = torch.empty((nq,), dtype=torch.uint8, device=row_keys.device)
+    with torch.cuda.device(mask.device):
+        check(load_library().slamfe_ratio_test(ptr(row_keys), nq, num, den, ptr(mask), stream_handle()),
+              "slamfe_ratio_test")
+    return mask
+
+
+def stereo_filter(pts_left, pts_right, match_q, match_t):
+    """matching.py:48-69 mask over matches; pts (N,2) float32, match_* int32 CUDA tensors."""
+    torch = _torch()
+    n = match_q.shape[0]
+    mask = torch.empty((n,), dtype=torch.uint8, device=match_q.device)
+    with torch.cuda.device(mask.device):
+        check(load_library().slamfe_stereo_filter(ptr(pts_left), ptr(pts_right), ptr(match_q), ptr(match_t), n,
+                                                  ptr(mask), stream_handle()), "slamfe_stereo_filter")
+    return mask
+
+
+def stereo_links_batched(row_keys, col_keys, l_off, r_off, n_frames, pts_left, pts_right,
+                         desc_left=None, desc_bytes=61, out=None, n_l=None, n_r=None):
+    """Fused crossCheck + row filter + create_links + feature compaction over all frames.
+
+    Returns a dict of CUDA tensors: match_t, n_matches, n_links, link_src, links, feat.
+    """
+    torch = _torch()
+    dev = row_keys.device
+    l_rows = row_keys.shape[0]
+    if out is None:
+        out = {
+            "match_t": torch.empty((l_rows,), dtype=torch.int32, device=dev),
+            "n_matches": torch.empty((n_frames,), dtype=torch.int32, device=dev),
+            "n_links": torch.empty((n_frames,), dtype=torch.int32, device=dev),
+            "link_src": torch.empty((l_rows,), dtype=torch.int32, device=dev),
+            "links": torch.empty((l_rows, 3), dtype=torch.float32, device=dev),
+            "feat": torch.empty((l_rows, 64), dtype=torch.uint8, device=dev) if desc_left is not None else None,
+        }
+    with torch.cuda.device(dev):
+        check(load_library().slamfe_stereo_links_batched(
+            ptr(row_keys), ptr(col_keys), ptr(l_off), ptr(n_l), ptr(r_off), ptr(n_r), n_frames,
+            ptr(pts_left), ptr(pts_right),
+            ptr(desc_left), desc_left.stride(0) if desc_left is not None else 0, desc_bytes,
+            ptr(out["match_t"]), ptr(out["n_matches"]), ptr(out["n_links"]), ptr(out["link_src"]),
+            ptr(out["links"]), ptr(out["feat"]), stream_handle()), "slamfe_stereo_links_batched")
+    return out
+
+
+def triangulate_links(links, P, Q, out=None):
+    """links (n, 3) [x_left, x_right, y] float32 or float64 CUDA tensor -> xyz (n, 3), same dtype."""
+    torch = _torch()
+    links = links.contiguous()
+    n = links.shape[0]
+    if out is None:
+        out = torch.empty((n, 3), dtype=links.dtype, device=links.device)
+    fn = {torch.float64: "slamfe_triangulate_links_f64", torch.float32: "slamfe_triangulate_links_f32"}[links.dtype]
+    Pb, Qb = _cabi.host_doubles(P, 12), _cabi.host_doubles(Q, 12)
+    with torch.cuda.device(links.device):
+        check(getattr(load_library(), fn)(ptr(links), n, Pb, Qb, ptr(out), stream_handle()), fn)
+    return out
+
+
+def triangulate_dlt(pxy, qxy, P, Q):
+    """General 4x4 DLT (distinct y, arbitrary P/Q): pxy, qxy (n, 2) float64 -> xyz (n, 3) float64."""
+    torch = _torch()
+    pxy, qxy = pxy.contiguous(), qxy.contiguous()
+    n = pxy.shape[0]
+    out = torch.empty((n, 3), dtype=torch.float64, device=pxy.device)
+    Pb, Qb = _cabi.host_doubles(P, 12), _cabi.host_doubles(Q, 12)
+    with torch.cuda.device(pxy.device):
+        check(load_library().slamfe_triangulate_dlt_f64(ptr(pxy), ptr(qxy), n, Pb, Qb, ptr(out), stream_handle()),
+              "slamfe_triangulate_dlt_f64")
+    return out
+
+
+def same_rows_stereo(P, Q) -> bool:
+    """True when P[1:] == Q[1:] bitwise (rectified pair): the links kernel applies."""
+    P, Q = np.asarray(P, dtype=np.float64), np.asarray(Q, dtype=np.float64)
+    return bool(np.array_equal(P[1:], Q[1:]))
+
+
+def ransac_score(T, pts, l_pix, r_pix, K, M1, M2, hyp_valid=None, pt_off=None, n_frames=1, max_points=None):
+    """All hypotheses x all correspondences (x all frames) in one launch.
+
+    T (n_frames*H, 3, 4) or (n_frames, H, 3, 4) float64; pts (Ntot, 3), l_pix / r_pix (Ntot, 2)
+    float64; pt_off (n_frames+1,) int32 CUDA tensor for n_frames > 1.
+    Returns (counts (n_frames, H) int32, best (n_frames, 2) int32 [index, count], best_mask (Ntot,) uint8).
+    """
+    torch = _torch()
+    dev = pts.device
+    T = T.contiguous()
+    H = T.numel() // (12 * n_frames) if n_frames else 0
+    pts, l_pix, r_pix = pts.contiguous(), l_pix.contiguous(), r_pix.contiguous()
+    n_tot = pts.shape[0]
+    if max_points is None:
+        max_points = n_tot
+    counts = torch.empty((n_frames, H), dtype=torch.int32, device=dev)
+    best = torch.empty((n_frames, 2), dtype=torch.int32, device=dev)
+    mask = torch.empty((n_tot,), dtype=torch.uint8, device=dev)
+    work = torch.empty((n_frames,), dtype=torch.int32, device=dev)
+    Kb, M1b, M2b = _cabi.host_doubles(K, 9), _cabi.host_doubles(M1, 12), _cabi.host_doubles(M2, 12)
+    with torch.cuda.device(dev):
+        check(load_library().slamfe_ransac_score(
+            ptr(T), ptr(hyp_valid), H, ptr(pts), ptr(l_pix), ptr(r_pix), ptr(pt_off), n_tot, n_frames, max_points,
+            Kb, M1b, M2b, ptr(counts), ptr(best), ptr(mask), ptr(work), stream_handle()), "slamfe_ransac_score")
+    return counts, best, mask
+
+
+def measure_peak(mode: int, iters: int = 4096, ctas_per_sm: int = 8, block: int = 256):
+    """Run a pipe-peak micro-benchmark; returns ops/s (popc/s for modes 0-1, fp64 FMA/s for mode 2)."""
+    import ctypes
+    torch = _torch()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    grid = sms * ctas_per_sm
+    sink = torch.empty((grid * block,), dtype=torch.int32, device="cuda")
+    ops = ctypes.c_int(0)
+    lib = load_library()
+    best = 0.0
+    for _ in range(3):
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        check(lib.slamfe_peak_kernel(mode, iters, grid, block, ptr(sink), ctypes.byref(ops), stream_handle()),
+              "slamfe_peak_kernel")
+        stop.record()
+        stop.synchronize()
+        ms = start.elapsed_time(stop)
+        best = max(best, grid * block * float(iters) * ops.value / (ms * 1e-3))
+    return best
+
+
+def keys_to_numpy(keys_host: np.ndarray):
+    """Host-side decode of packed keys: returns (idx int32, dist int32), -1 for KEY_NONE."""
+    k = keys_host.view(np.uint32)
+    none = k == KEY_NONE
+    idx = (k & KEY_IDX_MASK).astype(np.int32)
+    dist = (k >> KEY_IDX_BITS).astype(np.int32)
+    idx[none] = -1
+    dist[none] = -1
+    return idx, dist

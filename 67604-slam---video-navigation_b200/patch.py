@@ -1,0 +1,76 @@
+"""Rebind the reference's module attributes to the GPU path (the drop-in hook).
+
+The reference has no plugin ABI: callers reach the hot path through module globals and names
+imported BY VALUE, so a replacement must be rebound at every importer:
+
+    matching.MATCHER / MATCHER_LEFT_RIGHT / extract_inliers_outliers   (matching.py:48-73)
+    database.MATCHER, database.extract_inliers_outliers,
+    database.ransac_pnp_for_tracking_db                                 (database.py:4-6)
+    loop_closure.MATCHER, loop_closure.ransac_pnp                       (loop_closure.py:6,12)
+    ransac.triangulate_links, ransac.transformation_agreement,
+    ransac.ransac_pnp_for_tracking_db, ransac.ransac_pnp                (ransac.py:4,28,70,116)
+    triangulation.* , bundle.triangulate_last_frame (bundle.py:10),
+    gtsam_utils.triangulate_last_frame (gtsam_utils.py:7), analysis.linear_least_squares_triangulation
+"""
+from __future__ import annotations
+
+import sys
+
+_REBINDS = {
+    "final_project.algorithms.matching": ("MATCHER", "MATCHER_LEFT_RIGHT", "extract_inliers_outliers"),
+    "final_project.backend.database.database": ("MATCHER", "extract_inliers_outliers", "ransac_pnp_for_tracking_db"),
+    "final_project.backend.loop.loop_closure": ("MATCHER", "ransac_pnp"),
+    "final_project.algorithms.ransac": ("triangulate_links", "transformation_agreement",
+                                        "ransac_pnp_for_tracking_db", "ransac_pnp"),
+    "final_project.algorithms.triangulation": ("linear_least_squares_triangulation", "triangulate_links",
+                                               "triangulate_last_frame"),
+    "final_project.backend.GTSam.bundle": ("triangulate_last_frame",),
+    "final_project.backend.GTSam.gtsam_utils": ("triangulate_last_frame",),
+    "final_project.analysis": ("linear_least_squares_triangulation",),
+}
+
+
+def replacements():
+    from . import matching, ransac, triangulation
+    if matching.MATCHER is None:
+        matching.init_globals()
+    return {
+        "MATCHER": matching.MATCHER,
+        "MATCHER_LEFT_RIGHT": matching.MATCHER_LEFT_RIGHT,
+        "extract_inliers_outliers": matching.extract_inliers_outliers,
+        "linear_least_squares_triangulation": triangulation.linear_least_squares_triangulation,
+        "triangulate_links": triangulation.triangulate_links,
+        "triangulate_last_frame": triangulation.triangulate_last_frame,
+        "transformation_agreement": ransac.transformation_agreement,
+        "ransac_pnp_for_tracking_db": ransac.ransac_pnp_for_tracking_db,
+        "ransac_pnp": ransac.ransac_pnp,
+    }
+
+
+def patch(modules=None):
+    """Rebind every already-imported reference module (or the given {name: module} mapping).
+    Also copies the reference's cameras into slamfe.ransac so both sides score with the same
+    K, M1, M2.  Returns {module_name: [rebound attribute names]}; `unpatch(token)` restores."""
+    from . import ransac
+    rep = replacements()
+    mods = modules if modules is not None else sys.modules
+    done, saved = {}, []
+    ref_ransac = mods.get("final_project.algorithms.ransac")
+    if ref_ransac is not None and hasattr(ref_ransac, "K"):
+        ransac.set_cameras(ref_ransac.K, ref_ransac.M1, ref_ransac.M2)
+    for mod_name, attrs in _REBINDS.items():
+        mod = mods.get(mod_name)
+        if mod is None:
+            continue
+        for a in attrs:
+            if hasattr(mod, a):
+                saved.append((mod, a, getattr(mod, a)))
+                setattr(mod, a, rep[a])
+                done.setdefault(mod_name, []).append(a)
+    done["_saved"] = saved
+    return done
+
+
+def unpatch(token):
+    for mod, a, old in token.get("_saved", []):
+        setattr(mod, a, old)

@@ -1,0 +1,178 @@
+"""Drop-in mirror of final_project/algorithms/ransac.py (same names, signatures, returns).
+
+What changes: the reference scores ONE hypothesis per Python iteration with NumPy
+(ransac.py:106, :174); here all hypotheses of a call are generated first (same global-RNG call
+sequence: np.random.choice + cv2.solvePnP(EPNP) on the host, ransac.py:95-98 — the minimal solver
+is a "next" row) and then scored against all correspondences in a single
+kernel launch that also returns the winner (first strictly-best) and its inlier mask.  With the
+same np.random seed the outputs equal the reference's.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import ops
+from . import utils as _utils
+from .matching import _Staging
+from .triangulation import links_to_array, triangulate_link_array
+from .utils import rodriguez_to_mat
+
+SUCCESS_PROBABILITY = 0.9999999999  # ransac.py:9
+
+K, M1, M2 = _utils.K, _utils.M1, _utils.M2  # ransac.py:11
+P, Q = K @ M1, K @ M2                        # ransac.py:12
+
+_st = _Staging()
+
+
+def set_cameras(k, m1, m2):
+    """Rebind the module-level cameras (the reference fixes them at import, ransac.py:11-12)."""
+    global K, M1, M2, P, Q
+    K, M1, M2 = np.asarray(k, float), np.asarray(m1, float), np.asarray(m2, float)
+    P, Q = K @ M1, K @ M2
+
+
+def get_pixels_from_links(links):
+    """ransac.py:15-25."""
+    pixels_first = []
+    pixels_second = []
+    for link in links:
+        pixels_first.append((link.x_left, link.y))
+        pixels_second.append((link.x_right, link.y))
+    return pixels_first, pixels_second
+
+
+def score_hypotheses(Ts, pts, l_pix, r_pix, hyp_valid=None):
+    """All hypotheses x all points on the GPU.
+    Returns (counts (H,) int32, best_index or -1, best_count, best_mask (N,) bool)."""
+    Ts = np.ascontiguousarray(Ts, dtype=np.float64).reshape(-1, 3, 4)
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+    l_pix = np.ascontiguousarray(l_pix, dtype=np.float64).reshape(-1, 2)
+    r_pix = np.ascontiguousarray(r_pix, dtype=np.float64).reshape(-1, 2)
+    if Ts.shape[0] == 0:
+        return np.zeros(0, np.int32), -1, 0, np.zeros(pts.shape[0], bool)
+    hv = None if hyp_valid is None else _st.to_device("hv", np.asarray(hyp_valid, dtype=np.uint8))
+    counts, best, mask = ops.ransac_score(_st.to_device("T", Ts), _st.to_device("pts", pts),
+                                          _st.to_device("lp", l_pix), _st.to_device("rp", r_pix),
+                                          K, M1, M2, hyp_valid=hv)
+    import torch
+    packed = torch.cat([counts.view(-1), best.view(-1)])
+    host = _st.to_host("cb", packed)
+    mask_h = _st.to_host("mask", mask).astype(bool)
+    return host[:-2].copy(), int(host[-2]), int(host[-1]), mask_h
+
+
+def transformation_agreement(T, traingulated_pts, ordered_cur_left_pix_values, ordered_cur_right_pix_values):
+    """ransac.py:28-56 -> (N,) bool."""
+    pts = np.asarray(traingulated_pts, dtype=np.float64)
+    _, _, _, mask = score_hypotheses(np.asarray(T, dtype=np.float64).reshape(1, 3, 4), pts,
+                                     ordered_cur_left_pix_values, ordered_cur_right_pix_values)
+    return mask
+
+
+def calc_ransac_iteration(inliers_percent):
+    """ransac.py:59-67."""
+    suc_prob = SUCCESS_PROBABILITY
+    outliers_prob = 1 - (inliers_percent / 100) + 0.0000000001
+    min_set_size = 4
+    ransac_iterations = int(np.log(1 - suc_prob) / np.log(1 - np.power(1 - outliers_prob, min_set_size))) + 1
+    return ransac_iterations
+
+
+def _gather(matches_l_l, prev_links, cur_links):
+    """ransac.py:76-81 / :132-138 + :83,:85-88: points and pixel arrays for the matched links."""
+    n = len(matches_l_l)
+    qi = np.fromiter((m.queryIdx for m in matches_l_l), dtype=np.int64, count=n)
+    ti = np.fromiter((m.trainIdx for m in matches_l_l), dtype=np.int64, count=n)
+    prev = links_to_array(prev_links)[qi]
+    cur = links_to_array(cur_links)[ti]
+    points_3d = triangulate_link_array(prev, P, Q)
+    l_pix = np.ascontiguousarray(cur[:, [0, 2]])
+    r_pix = np.ascontiguousarray(cur[:, [1, 2]])
+    return points_3d, l_pix, r_pix
+
+
+def generate_hypotheses(points_3d, l_pix, n_iter):
+    """ransac.py:94-104: the host half of the loop, same RNG/solver call sequence.
+    Returns (Ts (H, 3, 4), ok (H,) uint8)."""
+    import cv2
+    diff_coeff = np.zeros((5, 1))
+    Ts = np.zeros((n_iter, 3, 4))
+    ok = np.zeros(n_iter, dtype=np.uint8)
+    for i in range(n_iter):
+        random_idx = np.random.choice(len(points_3d), 4, replace=False)
+        success, rvec, tvec = cv2.solvePnP(points_3d[random_idx], l_pix[random_idx], K,
+                                           distCoeffs=diff_coeff, flags=cv2.SOLVEPNP_EPNP)
+        if success:
+            Ts[i] = rodriguez_to_mat(rvec, tvec)
+            ok[i] = 1
+    return Ts, ok
+
+
+def ransac_pnp_for_tracking_db(matches_l_l, prev_links, cur_links, inliers_percent):
+    """ransac.py:70-113 -> best_matches_idx (int64 array) or None."""
+    ransac_iterations = calc_ransac_iteration(inliers_percent)
+    points_3d, l_pix, r_pix = _gather(matches_l_l, prev_links, cur_links)
+    Ts, ok = generate_hypotheses(points_3d, l_pix, ransac_iterations)
+    _, best, _, mask = score_hypotheses(Ts, points_3d, l_pix, r_pix, hyp_valid=ok)
+    if best < 0:
+        return None
+    return np.where(mask)[0]
+
+
+class Pose3:
+    """Minimal gtsam.Pose3 stand-in used when gtsam is not installed (ransac.py:199-200)."""
+
+    def __init__(self, R, t):
+        self._R = np.asarray(R, dtype=np.float64).reshape(3, 3)
+        self._t = np.asarray(t, dtype=np.float64).reshape(3)
+
+    def inverse(self):
+        return Pose3(self._R.T, -self._R.T @ self._t)
+
+    def rotation(self):
+        return _Rot3(self._R)
+
+    def translation(self):
+        return self._t
+
+    def matrix(self):
+        m = np.eye(4)
+        m[:3, :3] = self._R
+        m[:3, 3] = self._t
+        return m
+
+
+class _Rot3:
+    def __init__(self, R):
+        self._R = R
+
+    def matrix(self):
+        return self._R
+
+
+def _pose3(T):
+    try:
+        import gtsam
+        return gtsam.Pose3(gtsam.Rot3(T[:3, :3]), gtsam.Point3(T[:3, 3]))
+    except ImportError:
+        return Pose3(T[:3, :3], T[:3, 3])
+
+
+def ransac_pnp(matches_l_l, prev_links, cur_links, inliers_percent=50):
+    """ransac.py:116-204 -> (camera_to_world Pose3, best_matches_idx, best_inliers)."""
+    import cv2
+    ransac_iterations = calc_ransac_iteration(inliers_percent)
+    points_3d, l_pix, r_pix = _gather(matches_l_l, prev_links, cur_links)
+    Ts, ok = generate_hypotheses(points_3d, l_pix, ransac_iterations)
+    _, best, best_inliers, mask = score_hypotheses(Ts, points_3d, l_pix, r_pix, hyp_valid=ok)
+    best_matches_idx = np.where(mask)[0] if best >= 0 else []
+    if len(best_matches_idx) < 4:
+        return None, [], []
+    success, rvec, tvec = cv2.solvePnP(points_3d[best_matches_idx], l_pix[best_matches_idx], K,
+                                       distCoeffs=np.zeros((5, 1)), flags=cv2.SOLVEPNP_EPNP)
+    if success:
+        T = rodriguez_to_mat(rvec, tvec)
+        world_to_camera = _pose3(T)
+        return world_to_camera.inverse(), best_matches_idx, np.int64(best_inliers)
+    return None, None, None

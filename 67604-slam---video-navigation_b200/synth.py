@@ -1,0 +1,144 @@
+"""Seeded synthetic KITTI-00-shaped front-end inputs.
+
+The reference ships no data (KITTI is expected at hard-coded paths,
+final_project/arguments.py:3-14), so every test / bench input is generated here:
+61-byte MLDB-shaped descriptors (byte 60 uses its low 6 bits, like cv2 AKAZE output),
+fp32-representable keypoints on a 1241x376 image, KITTI-00 calibration.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+DESC_BYTES = 61
+IMG_W, IMG_H = 1241, 376
+
+# KITTI sequence-00 projection matrices (calib.txt rows P0 / P1).
+KITTI00_P0 = np.array([[7.188560000000e+02, 0.0, 6.071928000000e+02, 0.0],
+                       [0.0, 7.188560000000e+02, 1.852157000000e+02, 0.0],
+                       [0.0, 0.0, 1.0, 0.0]])
+KITTI00_P1 = np.array([[7.188560000000e+02, 0.0, 6.071928000000e+02, -3.861448000000e+02],
+                       [0.0, 7.188560000000e+02, 1.852157000000e+02, 0.0],
+                       [0.0, 0.0, 1.0, 0.0]])
+
+
+def descriptors(rng: np.random.Generator, n: int) -> np.ndarray:
+    """(n, 61) uint8, i.i.d. bits, byte 60 masked to 6 bits."""
+    d = rng.integers(0, 256, size=(n, DESC_BYTES), dtype=np.uint8)
+    d[:, 60] &= 0x3F
+    return d
+
+
+def flip_bits(rng: np.random.Generator, d: np.ndarray, p: float = 0.08) -> np.ndarray:
+    """Copy of d with every bit flipped independently with probability p."""
+    bits = rng.random(size=(d.shape[0], d.shape[1], 8)) < p
+    mask = np.packbits(bits, axis=2, bitorder="little")[:, :, 0]
+    out = d ^ mask
+    out[:, 60] &= 0x3F
+    return out
+
+
+def paired_descriptors(rng: np.random.Generator, base: np.ndarray, n_out: int | None = None,
+                       match_frac: float = 0.6, flip: float = 0.08, dup_frac: float = 0.01):
+    """A second descriptor set related to `base`: a `match_frac` subset are bit-flipped copies
+    (true matches), the rest fresh random rows, row-permuted; `dup_frac` of the rows are then
+    overwritten with exact duplicates of other rows to force distance ties.
+    Returns (out, src) where src[j] = base row that out[j] came from, or -1."""
+    n = base.shape[0]
+    n_out = n if n_out is None else n_out
+    out = descriptors(rng, n_out)
+    src = np.full(n_out, -1, dtype=np.int64)
+    n_match = min(int(match_frac * n), n_out)
+    from_rows = rng.permutation(n)[:n_match]
+    to_rows = rng.permutation(n_out)[:n_match]
+    out[to_rows] = flip_bits(rng, base[from_rows], flip)
+    src[to_rows] = from_rows
+    n_dup = int(dup_frac * n_out)
+    if n_dup and n_out > 1:
+        a = rng.integers(0, n_out, size=n_dup)
+        b = rng.integers(0, n_out, size=n_dup)
+        out[a] = out[b]
+        src[a] = src[b]
+    return out, src
+
+
+def stereo_frame(rng: np.random.Generator, n: int, outlier_frac: float = 0.15):
+    """One rectified stereo frame: (desc_l, desc_r, pts_l, pts_r), pts float32 (n, 2) = (x, y).
+    Right keypoint of a true match sits at x_r = x_l - d, d ~ U(2.5, 120), y_r = y_l + N(0, 0.5);
+    `outlier_frac` of them violate the row / disparity test."""
+    desc_l = descriptors(rng, n)
+    desc_r, src = paired_descriptors(rng, desc_l)
+    pts_l = np.stack([rng.uniform(20, 1220, n), rng.uniform(5, 370, n)], axis=1).astype(np.float32)
+    pts_r = np.stack([rng.uniform(20, 1220, n), rng.uniform(5, 370, n)], axis=1).astype(np.float32)
+    has = src >= 0
+    d = rng.uniform(2.5, 120, n)
+    xr = pts_l[src[has], 0] - d[has]
+    yr = pts_l[src[has], 1] + rng.normal(0, 0.5, has.sum())
+    bad = rng.random(has.sum()) < outlier_frac
+    yr = np.where(bad & (rng.random(has.sum()) < 0.5), yr + 5.0, yr)
+    xr = np.where(bad, xr + d[has] + 1.0, xr)
+    pts_r[has, 0] = xr.astype(np.float32)
+    pts_r[has, 1] = yr.astype(np.float32)
+    return desc_l, desc_r, pts_l, pts_r
+
+
+def next_frame_descriptors(rng: np.random.Generator, prev: np.ndarray, n: int):
+    """Frame t+1 left descriptors: re-flipped copies of frame t rows plus fresh rows."""
+    out, _ = paired_descriptors(rng, prev, n_out=n)
+    return out
+
+
+def links(rng: np.random.Generator, n: int) -> np.ndarray:
+    """(n, 3) float64 [x_left, x_right, y] with fp32-representable values and valid disparity."""
+    xl = rng.uniform(150, 1220, n).astype(np.float32)
+    d = rng.uniform(2.5, 120, n).astype(np.float32)
+    xr = (xl - d).astype(np.float32)
+    yl = rng.uniform(5, 370, n).astype(np.float32)
+    yr = (yl + rng.normal(0, 0.5, n)).astype(np.float32)
+    y = (yl.astype(np.float64) + yr.astype(np.float64)) / 2
+    return np.stack([xl.astype(np.float64), xr.astype(np.float64), y], axis=1)
+
+
+def cameras():
+    """K, M1, M2 exactly as final_project/utils.py:36-51 derives them from calib.txt."""
+    k = KITTI00_P0[:, :3]
+    m1 = np.linalg.inv(k) @ KITTI00_P0
+    m2 = np.linalg.inv(k) @ KITTI00_P1
+    return k, m1, m2
+
+
+def _rodrigues(rvec):
+    th = np.linalg.norm(rvec)
+    if th < 1e-12:
+        return np.eye(3)
+    k = rvec / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * (Kx @ Kx)
+
+
+def pnp_problem(rng: np.random.Generator, n: int, n_hyp: int, outlier_frac: float = 0.4,
+                hyp_noise: float = 0.02):
+    """RANSAC-PnP scoring inputs (config 3): 3-D points in frame t, their (noisy) left/right
+    pixels in frame t+1 under a ground-truth motion, `outlier_frac` gross outliers, and `n_hyp`
+    pose hypotheses (perturbed ground truth; a few exact, a few far off).
+    Returns (Ts (H,3,4), pts (n,3), l_pix (n,2), r_pix (n,2)) float64."""
+    k, m1, m2 = cameras()
+    z = rng.uniform(4, 60, n)
+    x = (rng.uniform(20, 1220, n) - k[0, 2]) * z / k[0, 0]
+    y = (rng.uniform(5, 370, n) - k[1, 2]) * z / k[1, 1]
+    pts = np.stack([x, y, z], axis=1)
+    rvec = rng.normal(0, 0.01, 3)
+    tvec = np.array([0.0, 0.0, -0.9]) + rng.normal(0, 0.05, 3)
+    T_gt = np.hstack([_rodrigues(rvec), tvec[:, None]])
+    X4 = np.hstack([pts, np.ones((n, 1))]).T
+    pl = (k @ T_gt @ np.vstack([m1, [0, 0, 0, 1]]) @ X4)[:3].T
+    pr = (k @ T_gt @ np.vstack([m2, [0, 0, 0, 1]]) @ X4)[:3].T
+    l_pix = pl[:, :2] / pl[:, 2:3] + rng.normal(0, 0.5, (n, 2))
+    r_pix = pr[:, :2] / pr[:, 2:3] + rng.normal(0, 0.5, (n, 2))
+    out = rng.random(n) < outlier_frac
+    l_pix[out] += rng.uniform(-80, 80, (out.sum(), 2))
+    Ts = np.zeros((n_hyp, 3, 4))
+    for h in range(n_hyp):
+        s = hyp_noise * (0.02 if h % 7 == 0 else (5.0 if h % 11 == 0 else 1.0))
+        Ts[h] = np.hstack([_rodrigues(rvec + rng.normal(0, s, 3)),
+                           (tvec + rng.normal(0, 10 * s, 3))[:, None]])
+    return Ts, pts, l_pix, r_pix

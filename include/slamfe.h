@@ -1,0 +1,211 @@
+/*
+ * slamfe.h — C-ABI of libslamfe.so, the B200 (sm_100a) front-end kernels.
+ *
+ * This is the drop-in boundary for the reference's front-end hot path
+ * (michaelpiro/67604-SLAM---video-navigation, final_project/algorithms/*).  The reference has no
+ * native FFI: its hot path sits behind Python module attributes, and the
+ * arithmetic runs inside OpenCV / NumPy.  Each entry point below names the reference call it
+ * replaces; the Python mirror in `67604-slam---video-navigation_b200/` binds them through ctypes and
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - Every data pointer is a DEVICE pointer owned by the caller (who keeps it alive until the
+ *     stream has drained), except small camera matrices, which are HOST pointers read at call
+ *     time (documented per function).
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it.
+ *   - Return value: 0 on success, a negative SLAMFE_E* code for argument errors, or a positive
+ *     cudaError_t.  Nothing throws; no persistent allocations; no global mutable state.
+ *
+ * Packed match keys
+ *   The matcher's native result is a 32-bit key per neighbour:
+ *       key = (hamming_distance << 22) | train_index        (distance <= 512, index < 2^22)
+ *       SLAMFE_KEY_NONE (0xFFFFFFFF) = no neighbour.
+ *   Unsigned comparison of keys == cv2.BFMatcher ordering: smaller distance first, ties broken
+ *   by the LOWER train index (first minimum).  Min-merging keys across train shards / GPUs is
+ *   therefore exact.
+ */
+#ifndef SLAMFE_H
+#define SLAMFE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *slamfe_stream_t;
+
+#define SLAMFE_KEY_IDX_BITS 22
+#define SLAMFE_KEY_IDX_MASK 0x3FFFFFu
+#define SLAMFE_KEY_NONE 0xFFFFFFFFu
+#define SLAMFE_MAX_DESC_BYTES 64
+
+#define SLAMFE_EINVAL (-1)   /* bad argument (null pointer, negative size, stride < desc_bytes ...) */
+#define SLAMFE_ERANGE (-2)   /* size exceeds what the key encoding / grid can address */
+
+int slamfe_version(void);
+const char *slamfe_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * Hamming matcher
+ * ---------------------------------------------------------------------------------------- */
+
+/*
+ * Brute-force Hamming top-2 of every query row against every train row.
+ * Replaces cv2.BFMatcher(NORM_HAMMING).match / .knnMatch(k=2):
+ *   final_project/backend/database/database.py:54-55, backend/loop/loop_closure.py:422,
+ *   final_project/algorithms/matching.py:15,44, VAN_ex/code/ex1.py:189-190.
+ *
+ *   q, t          descriptor rows, `desc_bytes` (<= 64) useful bytes every `*_stride` bytes
+ *                 (cv2 layout: stride 61 for AKAZE MLDB; 64-byte padded rows also accepted).
+ *   t_index_base  added to the train index stored in the keys (global index of t[0] when the
+ *                 train set is one shard of a larger one).
+ *   row_keys      out, (nq, 2) uint32: best and second-best key per query row.
+ *   col_keys      out or NULL, (nt,) uint32: per TRAIN row the best (distance<<22 | query_index),
+ *                 i.e. the result of matching t against q, from the same single pass.  This is
+ *                 what crossCheck (matching.py:22,44) and the backward match (database.py:55)
+ *                 need; cv2 spends a second full pass on it.
+ */
+int slamfe_hamming_top2(const uint8_t *q, int nq, int q_stride,
+                        const uint8_t *t, int nt, int t_stride,
+                        int desc_bytes, int t_index_base,
+                        uint32_t *row_keys, uint32_t *col_keys, slamfe_stream_t stream);
+
+/*
+ * Ragged batch of independent (query set, train set) problems in ONE launch — one problem per
+ * frame pair / loop-closure candidate pair.  Problem p matches rows
+ * [q_off[p], q_off[p] + nq_p) of `q` against rows [t_off[p], t_off[p] + nt_p) of `t`, where
+ * nq_p = q_cnt ? q_cnt[p] : q_off[p+1] - q_off[p]  (same for t).  All four arrays are DEVICE
+ * int32; q_off/t_off have n_problems + 1 entries unless the matching *_cnt array is given, in which
+ * case n_problems entries suffice.  Keys hold problem-local indices.  row_keys is
+ * (q_rows_total, 2), col_keys (t_rows_total,) or NULL; both are indexed by global row.
+ * max_nq / max_nt are host-side upper bounds on any problem's size (they size the grid).
+ */
+int slamfe_hamming_top2_batched(const uint8_t *q, int q_stride, const int32_t *q_off, const int32_t *q_cnt,
+                                const uint8_t *t, int t_stride, const int32_t *t_off, const int32_t *t_cnt,
+                                int n_problems, int max_nq, int max_nt, int desc_bytes,
+                                uint32_t *row_keys, int64_t q_rows_total,
+                                uint32_t *col_keys, int64_t t_rows_total, slamfe_stream_t stream);
+
+/* keys (n,) -> idx (n,) int32 (-1 for NONE), dist (n,) int32 (-1 for NONE). */
+int slamfe_unpack_keys(const uint32_t *keys, int64_t n, int32_t *idx, int32_t *dist, slamfe_stream_t stream);
+
+/*
+ * Merge per-shard top-2 tables after an all-gather: shard_keys is (n_shards, nq, 2); out (nq, 2)
+ * receives the two smallest keys per query over all shards (exact: keys carry global indices).
+ */
+int slamfe_merge_top2(const uint32_t *shard_keys, int n_shards, int nq, uint32_t *out, slamfe_stream_t stream);
+
+/*
+ * crossCheck epilogue (cv2.BFMatcher(crossCheck=True), matching.py:22,44; and the manual
+ * forward/backward loop database.py:67-77): match_t[i] = train index of query i if the pair is
+ * mutual (col_keys[best_i] points back at i) else -1; match_dist[i] likewise.
+ */
+int slamfe_cross_check(const uint32_t *row_keys, const uint32_t *col_keys, int nq, int nt,
+                       int32_t *match_t, int32_t *match_dist, slamfe_stream_t stream);
+
+/* Ratio test of VAN_ex/code/ex1.py:118-122: mask[i] = (num * d1 < den * d2), e.g. 5*d1 < 3*d2 for 0.6. */
+int slamfe_ratio_test(const uint32_t *row_keys, int nq, int num, int den, uint8_t *mask, slamfe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Rectified-stereo row filter and links
+ * ---------------------------------------------------------------------------------------- */
+
+/*
+ * extract_inliers_outliers (final_project/algorithms/matching.py:48-69): for match m between
+ * left keypoint match_q[m] and right keypoint match_t[m]:
+ *   mask[m] = |yl - yr| < 2  &&  xl > xr + 2        (matching.py:62-63)
+ * pts are (n, 2) float32 (x, y) — cv2.KeyPoint.pt values.
+ */
+int slamfe_stereo_filter(const float *pts_left, const float *pts_right,
+                         const int32_t *match_q, const int32_t *match_t, int n_matches,
+                         uint8_t *mask, slamfe_stream_t stream);
+
+/*
+ * Fused per-frame epilogue of the stereo match, batched over frames (one CTA per frame):
+ * crossCheck (matching.py:44) + row filter (matching.py:48-69) + TrackingDB.create_links
+ * (backend/database/tracking_database.py:224-246) + features[is_valid] compaction.
+ * Inputs are the keys of slamfe_hamming_top2_batched(left, right) with the same row offsets
+ * l_off / r_off and optional per-frame counts l_cnt / r_cnt (NULL: count = offset difference).
+ * Outputs, all indexed with l_off as per-frame capacity (rows past n_links[f] inside a frame's
+ * capacity are filled with link_src = -1, links = 0):
+ *   match_t   (l_rows,)   int32  mutual right index per left row, -1 if not mutual
+ *   n_matches (n_frames,) int32  number of mutual matches      (len(matches), database.py:26)
+ *   n_links   (n_frames,) int32  number of stereo inliers
+ *   link_src  (l_rows,)   int32  left keypoint index of the k-th link, ascending
+ *   links     (l_rows, 3) float32 [x_left, x_right, (yl + yr) / 2]  (tracking_database.py:243)
+ *   feat      (l_rows, 64) uint8 or NULL: compacted descriptors, zero-padded to 64-byte rows
+ */
+int slamfe_stereo_links_batched(const uint32_t *row_keys, const uint32_t *col_keys,
+                                const int32_t *l_off, const int32_t *l_cnt,
+                                const int32_t *r_off, const int32_t *r_cnt, int n_frames,
+                                const float *pts_left, const float *pts_right,
+                                const uint8_t *desc_left, int l_stride, int desc_bytes,
+                                int32_t *match_t, int32_t *n_matches, int32_t *n_links,
+                                int32_t *link_src, float *links, uint8_t *feat, slamfe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Triangulation   (P, Q are HOST pointers to 12 doubles, row-major 3x4)
+ * ---------------------------------------------------------------------------------------- */
+
+/*
+ * triangulate_links / triangulate_last_frame (final_project/algorithms/triangulation.py:27-50):
+ * DLT of (x_left, y), (x_right, y).  For links rows 1 and 3 of the DLT matrix coincide
+ * (P[1]==Q[1], P[2]==Q[2]), so the 4x4 null vector is the exact cofactor vector of the three
+ * distinct rows; computed in fp64 registers.  Returns SLAMFE_EINVAL if P[1:]!=Q[1:] (use the
+ * general entry point).  links: (n, 3) [x_left, x_right, y]; xyz: (n, 3).
+ */
+int slamfe_triangulate_links_f64(const double *links, int64_t n, const double *P, const double *Q,
+                                 double *xyz, slamfe_stream_t stream);
+int slamfe_triangulate_links_f32(const float *links, int64_t n, const double *P, const double *Q,
+                                 float *xyz, slamfe_stream_t stream);
+
+/*
+ * linear_least_squares_triangulation (triangulation.py:5-24) for arbitrary P, Q and distinct
+ * y (analysis.py:400, VAN_ex/code/ex2.py:209): smallest right singular vector of the 4x4 DLT
+ * matrix by one-sided Jacobi in fp64 registers.  pxy, qxy: (n, 2); xyz: (n, 3).
+ */
+int slamfe_triangulate_dlt_f64(const double *pxy, const double *qxy, int64_t n,
+                               const double *P, const double *Q, double *xyz, slamfe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * RANSAC-PnP hypothesis scoring   (K: 9, M1/M2: 12 HOST doubles, row-major)
+ * ---------------------------------------------------------------------------------------- */
+
+/*
+ * transformation_agreement x all hypotheses (final_project/algorithms/ransac.py:28-56 inside the
+ * loops ransac.py:94-112 and :155-182), batched over `n_frames` independent problems in ONE
+ * launch.  Frame f owns hypotheses T[f*H .. f*H+H) (each 3x4 row-major fp64), and points
+ * [pt_off[f], pt_off[f+1]) of pts (.,3) / l_pix (.,2) / r_pix (.,2) (fp64).  pt_off is a DEVICE
+ * int32 array of n_frames + 1 entries, or NULL when n_frames == 1 (then n_points is used).
+ *   hyp_valid  (n_frames*H,) uint8 or NULL: 0 = hypothesis skipped (solvePnP failed, ransac.py:101-104)
+ *   counts     out (n_frames*H,) int32: inlier count per hypothesis (np.sum, ransac.py:109)
+ *   best       out (n_frames, 2) int32: [index of the first hypothesis with the largest count
+ *              (ransac.py:110 keeps strictly-better only), that count]; index -1 if no
+ *              hypothesis scored > 0 inliers
+ *   best_mask  out (total_points,) uint8: inlier mask of the best hypothesis (ransac.py:112)
+ *   work       scratch, (n_frames,) int32, zeroed by the call
+ * fp64 throughout, association order ((K@T)@M_h)@X, IEEE division, strict < 2 (ransac.py:38-56).
+ */
+int slamfe_ransac_score(const double *T, const uint8_t *hyp_valid, int H,
+                        const double *pts, const double *l_pix, const double *r_pix,
+                        const int32_t *pt_off, int n_points, int n_frames, int max_points,
+                        const double *K, const double *M1, const double *M2,
+                        int32_t *counts, int32_t *best, uint8_t *best_mask, int32_t *work,
+                        slamfe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Roofline micro-benchmarks (measure the pipe peaks the matcher / scorer are bound by)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Runs `iters` dependent-chain batches of POPC (mode 0), POPC+LOP3+IADD3 matcher mix (mode 1)
+ * or fp64 FMA (mode 2) on every SM; *ops_per_thread_iter (host) receives the number of
+ * counted operations each thread performs per iteration.  sink: device uint32[grid*block]. */
+int slamfe_peak_kernel(int mode, int iters, int grid, int block, uint32_t *sink,
+                       int *ops_per_thread_iter, slamfe_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAMFE_H */

@@ -1,0 +1,324 @@
+"""ORACLE — test infrastructure only.  NOT part of the product path.
+
+CPU restatement (numpy + the C library built from oracle/hamming_oracle.c) of the
+reference's front-end hot path.  Every function cites the reference file:line it follows.
+Array-in / array-out: the reference's per-object Python containers (cv2.DMatch, cv2.KeyPoint,
+Link) are flattened to ndarrays; `oracle/refshim.py` + `oracle/make_golden.py` check these
+restatements against the unmodified reference and against cv2 4.13.0 in the build container,
+and freeze the outputs under tests/golden/ (parity is pinned by those generated vectors; the
+reference itself ships no tests — SURVEY.md section 4).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+import this module.  The product package never does.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/hamming_oracle.c -> oracle/liboracle.so (gcc, OpenMP)."""
+    src = os.path.join(_HERE, "hamming_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-msse4.2", "-mpopcnt", "-fopenmp", "-shared", "-fPIC",
+                               src, "-o", _LIB_PATH])
+    return _LIB_PATH
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+        u8p = ctypes.POINTER(ctypes.c_uint8)
+        i32p = ctypes.POINTER(ctypes.c_int32)
+        for name in ("oracle_hamming_top2", "oracle_hamming_colmin", "oracle_hamming_matrix"):
+            fn = getattr(_lib, name)
+            fn.restype = None
+            fn.argtypes = [u8p, ctypes.c_int, ctypes.c_int, u8p, ctypes.c_int, ctypes.c_int,
+                           ctypes.c_int] + ([i32p, i32p] if name != "oracle_hamming_matrix" else [i32p])
+    return _lib
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a, a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+
+
+def _i32(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+
+
+# --------------------------------------------------------------------------------------
+# Hamming matcher — cv2.BFMatcher(NORM_HAMMING) semantics
+# --------------------------------------------------------------------------------------
+def hamming_matrix(q, t):
+    """Exact (Nq, Nt) Hamming distance matrix (small cases)."""
+    q, qp = _u8(q)
+    t, tp = _u8(t)
+    D = np.empty((q.shape[0], t.shape[0]), dtype=np.int32)
+    _load().oracle_hamming_matrix(qp, q.shape[0], q.shape[1], tp, t.shape[0], t.shape[1],
+                                  q.shape[1], _i32(D))
+    return D
+
+
+def knn2(q, t):
+    """knnMatch(q, t, k=2) (VAN_ex/code/ex1.py:189-190): per query the two nearest train rows in
+    ascending (distance, trainIdx) order.  Returns idx2, dist2 of shape (Nq, 2), -1 = missing."""
+    q, qp = _u8(q)
+    t, tp = _u8(t)
+    idx2 = np.empty((q.shape[0], 2), dtype=np.int32)
+    dist2 = np.empty((q.shape[0], 2), dtype=np.int32)
+    _load().oracle_hamming_top2(qp, q.shape[0], q.shape[1], tp, t.shape[0], t.shape[1],
+                                q.shape[1], _i32(idx2), _i32(dist2))
+    return idx2, dist2
+
+
+def match(q, t):
+    """MATCHER.match(q, t), crossCheck=False (database.py:54-55, loop_closure.py:422):
+    one entry per query row in query order, first-min train index.  Returns (trainIdx, distance)."""
+    idx2, dist2 = knn2(q, t)
+    return idx2[:, 0].copy(), dist2[:, 0].copy()
+
+
+def colmin(q, t):
+    """First-min of each column = MATCHER.match(t, q) seen from the (q, t) distance matrix."""
+    q, qp = _u8(q)
+    t, tp = _u8(t)
+    idx = np.empty(t.shape[0], dtype=np.int32)
+    dist = np.empty(t.shape[0], dtype=np.int32)
+    _load().oracle_hamming_colmin(qp, q.shape[0], q.shape[1], tp, t.shape[0], t.shape[1],
+                                  q.shape[1], _i32(idx), _i32(dist))
+    return idx, dist
+
+
+def match_crosscheck(l, r):
+    """MATCHER_LEFT_RIGHT.match(l, r), crossCheck=True (matching.py:22,44): keep (i, j) iff j is
+    the first-min of row i and i is the first-min of column j; sorted by queryIdx.
+    Returns (queryIdx, trainIdx, distance)."""
+    ti, td = match(l, r)
+    ci, _ = colmin(l, r)
+    qi = np.arange(l.shape[0], dtype=np.int32)
+    keep = (ti >= 0) & (ci[np.maximum(ti, 0)] == qi)
+    return qi[keep], ti[keep], td[keep]
+
+
+def ratio_test(dist2, ratio=0.6):
+    """ex1.py:118-122 with GOOD_RATIO=0.6 (ex1.py:9): keep iff m.distance < ratio * n.distance,
+    evaluated in float64 exactly as the reference does."""
+    d1 = dist2[:, 0].astype(np.float64)
+    d2 = dist2[:, 1].astype(np.float64)
+    return (dist2[:, 1] >= 0) & (d1 < ratio * d2)
+
+
+def mutual_forward_backward(prev, cur):
+    """database.py:54-77: forward match prev->cur, backward match cur->prev, keep forward match j
+    iff backward[trainIdx].trainIdx == queryIdx.  Returns (fwd_idx, fwd_dist, good_idx)."""
+    fi, fd = match(prev, cur)
+    bi, _ = match(cur, prev)
+    good = np.nonzero(bi[fi] == np.arange(prev.shape[0]))[0]
+    return fi, fd, good
+
+
+# --------------------------------------------------------------------------------------
+# Rectified-stereo row filter + links
+# --------------------------------------------------------------------------------------
+def extract_inliers_outliers(pt_left, pt_right, match_q, match_t):
+    """matching.py:48-69.  pt_* are (N, 2) arrays of KeyPoint.pt (float32 values); inlier iff
+    abs(yl - yr) < 2 and xl > xr + 2 (matching.py:62-63), compared in float64 like Python
+    floats.  Returns (inlier_idx, outlier_idx) into the match list."""
+    pl = np.asarray(pt_left, dtype=np.float64)[np.asarray(match_q)]
+    pr = np.asarray(pt_right, dtype=np.float64)[np.asarray(match_t)]
+    good = (np.abs(pl[:, 1] - pr[:, 1]) < 2) & (pl[:, 0] > pr[:, 0] + 2)
+    return np.nonzero(good)[0], np.nonzero(~good)[0]
+
+
+def create_links(pt_left, pt_right, match_q, match_t):
+    """tracking_database.py:224-246 with all matches inliers: Link(xl, xr, (yl + yr) / 2)
+    (tracking_database.py:243) in match order; is_valid mask over left keypoints.
+    Returns (is_valid (Nl,) bool, links (M, 3) float64 = [x_left, x_right, y])."""
+    pl = np.asarray(pt_left, dtype=np.float64)[np.asarray(match_q)]
+    pr = np.asarray(pt_right, dtype=np.float64)[np.asarray(match_t)]
+    links = np.stack([pl[:, 0], pr[:, 0], (pl[:, 1] + pr[:, 1]) / 2], axis=1)
+    is_valid = np.zeros(len(pt_left), dtype=bool)
+    is_valid[np.asarray(match_q)] = True
+    return is_valid, links
+
+
+# --------------------------------------------------------------------------------------
+# Cameras / small math
+# --------------------------------------------------------------------------------------
+KITTI00_P0 = np.array([[7.188560000000e+02, 0.0, 6.071928000000e+02, 0.0],
+                       [0.0, 7.188560000000e+02, 1.852157000000e+02, 0.0],
+                       [0.0, 0.0, 1.0, 0.0]])
+KITTI00_P1 = np.array([[7.188560000000e+02, 0.0, 6.071928000000e+02, -3.861448000000e+02],
+                       [0.0, 7.188560000000e+02, 1.852157000000e+02, 0.0],
+                       [0.0, 0.0, 1.0, 0.0]])
+
+
+def read_cameras(p0=KITTI00_P0, p1=KITTI00_P1):
+    """utils.py:36-51 / Inputs.py:22-37 minus the file read: k = P0[:, :3];
+    m1 = inv(k) @ P0; m2 = inv(k) @ P1."""
+    k = p0[:, :3]
+    m1 = np.linalg.inv(k) @ p0
+    m2 = np.linalg.inv(k) @ p1
+    return k, m1, m2
+
+
+def rodriguez_to_mat(rvec, tvec):
+    """utils.py:16-18: hstack(cv2.Rodrigues(rvec)[0], tvec)."""
+    import cv2
+    rot, _ = cv2.Rodrigues(rvec)
+    return np.hstack((rot, tvec))
+
+
+# --------------------------------------------------------------------------------------
+# Triangulation
+# --------------------------------------------------------------------------------------
+def linear_least_squares_triangulation(P, Q, kp_left, kp_right):
+    """triangulation.py:5-24: 4x4 DLT, null vector from np.linalg.svd, w==0 guard."""
+    A = np.zeros((4, 4))
+    p_x, p_y = kp_left
+    q_x, q_y = kp_right
+    A[0] = P[2] * p_x - P[0]
+    A[1] = P[2] * p_y - P[1]
+    A[2] = Q[2] * q_x - Q[0]
+    A[3] = Q[2] * q_y - Q[1]
+    _, _, V = np.linalg.svd(A)
+    if V[-1, 3] == 0:
+        return V[-1, :3] / (V[-1, 3] + 1e-20)
+    return V[-1, :3] / V[-1, 3]
+
+
+def triangulate_links(links, p, q):
+    """triangulation.py:41-50 (and :27-38): loop of the DLT over links (x_left, y), (x_right, y).
+    `links` is (M, 3) float64 [x_left, x_right, y]."""
+    links = np.asarray(links, dtype=np.float64)
+    x = np.zeros((len(links), 3))
+    for i in range(len(links)):
+        xl, xr, y = links[i]
+        x[i] = linear_least_squares_triangulation(p, q, (xl, y), (xr, y))
+    return x
+
+
+def triangulate_points(P, Q, pxy, qxy):
+    """General form of triangulation.py:5-24 over arrays of left/right pixels (analysis.py:400,
+    VAN_ex/code/ex2.py:209 call it with distinct y)."""
+    out = np.zeros((len(pxy), 3))
+    for i in range(len(pxy)):
+        out[i] = linear_least_squares_triangulation(P, Q, pxy[i], qxy[i])
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# RANSAC-PnP scoring
+# --------------------------------------------------------------------------------------
+def transformation_agreement(T, pts, l_pix, r_pix, K, M1, M2):
+    """ransac.py:28-56, same association order ((K @ T @ M_h) @ X), true division, strict < 2 on
+    both cameras.  Quirks kept: right camera is K @ T @ [M2; 0001] (M2 applied before T,
+    ransac.py:39) and there is no positive-depth test."""
+    points_4d = np.hstack((pts, np.ones((pts.shape[0], 1)))).T
+    l1 = ((K @ T @ np.vstack((M1, np.array([0, 0, 0, 1])))) @ points_4d)[:3, :].T
+    r1 = ((K @ T @ np.vstack((M2, np.array([0, 0, 0, 1])))) @ points_4d)[:3, :].T
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tl = l1 / l1[:, 2][:, np.newaxis]
+        tr = r1 / r1[:, 2][:, np.newaxis]
+        agree_l = np.logical_and(np.abs(tl[:, 1] - l_pix[:, 1]) < 2, np.abs(tl[:, 0] - l_pix[:, 0]) < 2)
+        agree_r = np.logical_and(np.abs(tr[:, 1] - r_pix[:, 1]) < 2, np.abs(tr[:, 0] - r_pix[:, 0]) < 2)
+    return np.logical_and(agree_l, agree_r)
+
+
+def calc_ransac_iteration(inliers_percent, suc_prob=0.9999999999):
+    """ransac.py:59-67 (SUCCESS_PROBABILITY ransac.py:9)."""
+    outliers_prob = 1 - (inliers_percent / 100) + 0.0000000001
+    return int(np.log(1 - suc_prob) / np.log(1 - np.power(1 - outliers_prob, 4))) + 1
+
+
+def score_hypotheses(Ts, pts, l_pix, r_pix, K, M1, M2):
+    """The scoring half of the RANSAC loops (ransac.py:106-112, :174-182) over GIVEN hypotheses:
+    per-hypothesis inlier counts, the first hypothesis with the strictly-largest count
+    (ransac.py:110 keeps only strictly better -> lowest index on ties) and its inlier mask.
+    best = -1 when no hypothesis scores > 0 inliers."""
+    counts = np.zeros(len(Ts), dtype=np.int64)
+    best, best_cnt, best_mask = -1, 0, np.zeros(len(pts), dtype=bool)
+    for h, T in enumerate(Ts):
+        m = transformation_agreement(T, pts, l_pix, r_pix, K, M1, M2)
+        c = int(np.sum(m))
+        counts[h] = c
+        if c > best_cnt:
+            best, best_cnt, best_mask = h, c, m
+    return counts, best, best_mask
+
+
+def generate_hypotheses(points_3d, l_pix, K, n_iter):
+    """The sampling half of the loops (ransac.py:94-104, :155-171): np.random.choice(n, 4,
+    replace=False) on the GLOBAL numpy RNG, cv2.solvePnP(EPNP) on the 4 points, rodriguez_to_mat.
+    Returns (Ts (H, 3, 4), ok (H,) bool)."""
+    import cv2
+    dist = np.zeros((5, 1))
+    Ts = np.zeros((n_iter, 3, 4))
+    ok = np.zeros(n_iter, dtype=bool)
+    for i in range(n_iter):
+        idx = np.random.choice(len(points_3d), 4, replace=False)
+        s, rvec, tvec = cv2.solvePnP(points_3d[idx], l_pix[idx], K, distCoeffs=dist,
+                                     flags=cv2.SOLVEPNP_EPNP)
+        if s:
+            Ts[i] = rodriguez_to_mat(rvec, tvec)
+            ok[i] = True
+    return Ts, ok
+
+
+def ransac_pnp_for_tracking_db(match_q, match_t, prev_links, cur_links, inliers_percent, K, M1, M2):
+    """ransac.py:70-113 on arrays: gather links by queryIdx/trainIdx (:76-81), triangulate prev
+    (:83), loop sample/solve/score keeping strictly-better counts (:94-112).
+    Returns best_matches_idx (int64) or None."""
+    n_iter = calc_ransac_iteration(inliers_percent)
+    fprev = np.asarray(prev_links)[np.asarray(match_q)]
+    fcur = np.asarray(cur_links)[np.asarray(match_t)]
+    P, Q = K @ M1, K @ M2
+    pts = triangulate_links(fprev, P, Q)
+    l_pix = np.stack([fcur[:, 0], fcur[:, 2]], axis=1)
+    r_pix = np.stack([fcur[:, 1], fcur[:, 2]], axis=1)
+    Ts, ok = generate_hypotheses(pts, l_pix, K, n_iter)
+    best_inliers, best_idx = 0, None
+    for h in range(n_iter):
+        if not ok[h]:
+            continue
+        m = transformation_agreement(Ts[h], pts, l_pix, r_pix, K, M1, M2)
+        c = np.sum(m)
+        if c > best_inliers:
+            best_inliers, best_idx = c, np.where(m)[0]
+    return best_idx
+
+
+# --------------------------------------------------------------------------------------
+# The real third-party engine (cv2), as the reference calls it — used for goldens and as the
+# CPU baseline on the GPU box (cv2 is part of the image; /root/reference is not needed).
+# --------------------------------------------------------------------------------------
+def cv2_match(q, t, cross_check=False):
+    import cv2
+    m = cv2.BFMatcher(normType=cv2.NORM_HAMMING, crossCheck=cross_check).match(q, t)
+    return (np.array([x.queryIdx for x in m], dtype=np.int32),
+            np.array([x.trainIdx for x in m], dtype=np.int32),
+            np.array([x.distance for x in m], dtype=np.float32))
+
+
+def cv2_knn2(q, t):
+    import cv2
+    m = cv2.BFMatcher(normType=cv2.NORM_HAMMING, crossCheck=False).knnMatch(q, t, k=2)
+    idx2 = np.full((len(m), 2), -1, dtype=np.int32)
+    dist2 = np.full((len(m), 2), -1, dtype=np.int32)
+    for i, pair in enumerate(m):
+        for k, x in enumerate(pair):
+            idx2[i, k] = x.trainIdx
+            dist2[i, k] = int(x.distance)
+    return idx2, dist2

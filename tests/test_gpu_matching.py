@@ -1,0 +1,193 @@
+"""Parity of the CUDA Hamming matcher against the golden vectors (cv2 4.13.0 / reference) and the
+oracle: bit-exact indices, distances, ordering and tie-breaks."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CASES = ("akaze", "ragged", "orb", "ties", "one_train")
+
+
+def _keys(ops, t):
+    return ops.keys_to_numpy(t.cpu().numpy())
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_match_golden(slamfe, golden, name):
+    from slamfe import matching
+    g = golden("matching")
+    q, t = g[f"{name}_q"], g[f"{name}_t"]
+    ms = matching.Matcher(crossCheck=False).match(q, t)
+    assert isinstance(ms, tuple) and len(ms) == q.shape[0]
+    assert [m.queryIdx for m in ms] == list(range(q.shape[0]))
+    assert [m.trainIdx for m in ms] == g[f"{name}_match_t"].tolist()
+    assert [m.distance for m in ms] == g[f"{name}_match_d"].tolist()
+    assert all(m.imgIdx == 0 for m in ms) and type(ms[0]).__name__ == "DMatch"
+    arr = np.array(ms)  # database.py:57-65 relies on object-array fancy indexing
+    assert arr.dtype == object and arr[[0, len(ms) - 1]][1].queryIdx == len(ms) - 1
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_crosscheck_golden(slamfe, golden, name):
+    from slamfe import matching
+    g = golden("matching")
+    ms = matching.Matcher(crossCheck=True).match(g[f"{name}_q"], g[f"{name}_t"])
+    assert [m.queryIdx for m in ms] == g[f"{name}_cc_q"].tolist()
+    assert [m.trainIdx for m in ms] == g[f"{name}_cc_t"].tolist()
+    assert [m.distance for m in ms] == g[f"{name}_cc_d"].tolist()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_knn_and_ratio_golden(slamfe, golden, name):
+    import torch
+    from slamfe import matching, ops
+    g = golden("matching")
+    q, t = g[f"{name}_q"], g[f"{name}_t"]
+    knn = matching.Matcher().knnMatch(q, t, k=2)
+    assert len(knn) == q.shape[0] and type(knn[0]) is tuple
+    idx = np.full((len(knn), 2), -1, np.int32)
+    dist = np.full((len(knn), 2), -1, np.int32)
+    for i, pair in enumerate(knn):
+        for c, m in enumerate(pair):
+            assert m.queryIdx == i and m.imgIdx == 0
+            idx[i, c], dist[i, c] = m.trainIdx, int(m.distance)
+    assert np.array_equal(idx, g[f"{name}_knn_idx"]) and np.array_equal(dist, g[f"{name}_knn_dist"])
+    row_keys, _ = ops.hamming_top2(torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda())
+    mask = ops.ratio_test(row_keys).cpu().numpy().astype(bool)
+    assert np.array_equal(mask, g[f"{name}_ratio"])
+    assert np.array_equal(matching.ratio_test_mask(dist), g[f"{name}_ratio"])
+    ui, ud = ops.unpack_keys(row_keys)
+    assert np.array_equal(ui.cpu().numpy(), idx) and np.array_equal(ud.cpu().numpy(), dist)
+
+
+def test_database_forward_backward_golden(slamfe, golden):
+    """database.py:54-77 through the drop-in Matcher, plus the one-pass column minima."""
+    import torch
+    from slamfe import matching, ops
+    g = golden("database")
+    M = matching.Matcher()
+    fwd = np.array(M.match(g["prev"], g["cur"]))
+    bwd = np.array(M.match(g["cur"], g["prev"]))
+    assert [m.trainIdx for m in fwd] == g["fwd_t"].tolist() and [m.trainIdx for m in bwd] == g["bwd_t"].tolist()
+    good = [j for j, m in enumerate(fwd) if bwd[m.trainIdx].trainIdx == m.queryIdx]
+    assert good == g["good_idx"].tolist()
+    rk, ck = ops.hamming_top2(torch.from_numpy(g["prev"]).cuda(), torch.from_numpy(g["cur"]).cuda(), want_cols=True)
+    ci, _ = _keys(ops, ck)
+    assert np.array_equal(ci, g["bwd_t"])
+    mt, md = ops.cross_check(rk, ck)
+    assert np.array_equal(np.nonzero(mt.cpu().numpy() >= 0)[0], g["good_idx"])
+
+
+@pytest.mark.parametrize("nq,nt", [(3000, 3000), (1, 5000), (4999, 1), (130, 129), (513, 2049)])
+def test_random_vs_oracle(slamfe, oracle, nq, nt):
+    import torch
+    from slamfe import ops, synth
+    rng = np.random.default_rng(nq * 7 + nt)
+    q = synth.descriptors(rng, nq)
+    t, _ = synth.paired_descriptors(rng, q, n_out=nt, dup_frac=0.05)
+    rk, ck = ops.hamming_top2(torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda(), want_cols=True)
+    idx, dist = _keys(ops, rk)
+    oi, od = oracle.knn2(q, t)
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+    ci, cd = _keys(ops, ck)
+    oci, ocd = oracle.colmin(q, t)
+    assert np.array_equal(ci, oci) and np.array_equal(cd, ocd)
+
+
+def test_layouts_padded_misaligned_and_short_descriptors(slamfe, oracle):
+    """64-byte padded rows (garbage in the pad bytes must be ignored), a base pointer that is not
+    16-byte aligned (TMA fallback path) and 32-byte descriptors."""
+    import torch
+    from slamfe import ops, synth
+    rng = np.random.default_rng(3)
+    q, t = synth.descriptors(rng, 700), synth.descriptors(rng, 900)
+    oi, od = oracle.knn2(q, t)
+    qp = rng.integers(0, 256, (700, 64), dtype=np.uint8); qp[:, :61] = q
+    tp = rng.integers(0, 256, (900, 64), dtype=np.uint8); tp[:, :61] = t
+    rk, _ = ops.hamming_top2(torch.from_numpy(qp).cuda(), torch.from_numpy(tp).cuda(), desc_bytes=61)
+    i, d = _keys(ops, rk)
+    assert np.array_equal(i, oi) and np.array_equal(d, od)
+    big_q = torch.from_numpy(np.concatenate([np.zeros((1, 61), np.uint8), q])).cuda()
+    big_t = torch.from_numpy(np.concatenate([np.zeros((3, 61), np.uint8), t])).cuda()
+    rk, _ = ops.hamming_top2(big_q[1:], big_t[3:])
+    i, d = _keys(ops, rk)
+    assert np.array_equal(i, oi) and np.array_equal(d, od)
+    q32, t32 = np.ascontiguousarray(q[:, :32]), np.ascontiguousarray(t[:, :32])
+    rk, _ = ops.hamming_top2(torch.from_numpy(q32).cuda(), torch.from_numpy(t32).cuda())
+    i, d = _keys(ops, rk)
+    o32i, o32d = oracle.knn2(q32, t32)
+    assert np.array_equal(i, o32i) and np.array_equal(d, o32d)
+
+
+def test_batched_ragged_vs_oracle(slamfe, oracle):
+    """Ragged batch with device-side counts, empty problems, both CTA shapes."""
+    import torch
+    from slamfe import frontend, ops, synth
+    rng = np.random.default_rng(11)
+    for sizes in ([(300, 280), (0, 50), (17, 0), (1, 1), (515, 700)], [(1100, 900)] * 70 + [(5, 2000)]):
+        qs = [synth.descriptors(rng, a) for a, _ in sizes]
+        ts = [synth.paired_descriptors(rng, synth.descriptors(rng, max(b, 1)), n_out=b, dup_frac=0.05)[0] for _, b in sizes]
+        q_off = frontend.plan_offsets([a for a, _ in sizes]); t_off = frontend.plan_offsets([b for _, b in sizes])
+        Q = np.zeros((q_off[-1], 61), np.uint8); T = np.zeros((t_off[-1], 61), np.uint8)
+        for p, (a, b) in enumerate(sizes):
+            Q[q_off[p]:q_off[p] + a] = qs[p]; T[t_off[p]:t_off[p] + b] = ts[p]
+        dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+        rk, ck = ops.hamming_top2_batched(
+            dev(Q), dev(q_off), dev(T), dev(t_off), len(sizes), max(a for a, _ in sizes), max(b for _, b in sizes), 61,
+            q_cnt=dev(np.array([a for a, _ in sizes], np.int32)), t_cnt=dev(np.array([b for _, b in sizes], np.int32)),
+            want_cols=True)
+        ri, rd = _keys(ops, rk); ci, cd = _keys(ops, ck)
+        for p, (a, b) in enumerate(sizes):
+            if a == 0:
+                continue
+            if b == 0:
+                assert np.all(ri[q_off[p]:q_off[p] + a] == -1)
+                continue
+            oi, od = oracle.knn2(qs[p], ts[p])
+            assert np.array_equal(ri[q_off[p]:q_off[p] + a], oi), p
+            assert np.array_equal(rd[q_off[p]:q_off[p] + a], od), p
+            oci, ocd = oracle.colmin(qs[p], ts[p])
+            assert np.array_equal(ci[t_off[p]:t_off[p] + b], oci) and np.array_equal(cd[t_off[p]:t_off[p] + b], ocd)
+        # rows in the alignment padding stay NONE
+        pad = np.ones(q_off[-1], bool)
+        for p, (a, _) in enumerate(sizes):
+            pad[q_off[p]:q_off[p] + a] = False
+        assert np.all(ri[pad] == -1)
+
+
+def test_train_shards_merge_exactly(slamfe, oracle):
+    """Config 5 on one GPU: train slices with global index bases + slamfe_merge_top2 == full sweep."""
+    import torch
+    from slamfe import dist, ops, synth
+    rng = np.random.default_rng(21)
+    q = synth.descriptors(rng, 1500)
+    t, _ = synth.paired_descriptors(rng, q, n_out=4100, dup_frac=0.05)
+    qd, td = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    b = dist.train_slices(t.shape[0], 4)
+    shards = torch.stack([ops.hamming_top2(qd, td[b[r]:b[r + 1]], t_index_base=int(b[r]))[0] for r in range(4)])
+    merged = ops.merge_top2(shards)
+    i, d = _keys(ops, merged)
+    oi, od = oracle.knn2(q, t)
+    assert np.array_equal(i, oi) and np.array_equal(d, od)
+    assert np.array_equal(dist.merge_top2_host(shards.cpu().numpy()).view(np.int32), merged.cpu().numpy())
+
+
+def test_dense_20k_sweep_vs_oracle(slamfe, oracle):
+    """BASELINE config 5 at full size (20k x 20k): bit-exact against the C oracle, plus the
+    size-independent properties (self-match, row/column duality)."""
+    import torch
+    from slamfe import ops, synth
+    rng = np.random.default_rng(4)
+    q = synth.descriptors(rng, 20000)
+    t, _ = synth.paired_descriptors(rng, q, n_out=20000)
+    qd, td = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    rk, ck = ops.hamming_top2(qd, td, want_cols=True)
+    i, d = _keys(ops, rk)
+    oi, od = oracle.knn2(q, t)
+    assert np.array_equal(i, oi) and np.array_equal(d, od)
+    rk2, ck2 = ops.hamming_top2(td, qd, want_cols=True)  # duality: columns of (q,t) == rows of (t,q)
+    assert np.array_equal(ck.cpu().numpy(), rk2[:, 0].cpu().numpy())
+    assert np.array_equal(ck2.cpu().numpy(), rk[:, 0].cpu().numpy())
+    rs, _ = ops.hamming_top2(qd, qd)  # self sweep: best distance is 0 at an index <= i (duplicates)
+    si, sd = _keys(ops, rs)
+    assert np.all(sd[:, 0] == 0) and np.all(si[:, 0] <= np.arange(20000))

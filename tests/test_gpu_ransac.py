@@ -1,0 +1,102 @@
+"""RANSAC scoring kernel: bit-exact inlier counts and masks against the reference (golden)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+class _Link:
+    def __init__(self, xl, xr, y):
+        self.x_left, self.x_right, self.y = xl, xr, y
+
+
+class _M:
+    def __init__(self, q, t):
+        self.queryIdx, self.trainIdx, self.distance = q, t, 10.0
+
+
+def test_counts_and_masks_golden(slamfe, golden):
+    from slamfe import ransac
+    g = golden("ransac")
+    ransac.set_cameras(g["K"], g["M1"], g["M2"])
+    masks = np.unpackbits(g["masks"], axis=1)[:, : g["pts"].shape[0]].astype(bool)
+    counts, best, best_cnt, mask = ransac.score_hypotheses(g["Ts"], g["pts"], g["l_pix"], g["r_pix"])
+    assert np.array_equal(counts, g["counts"])
+    assert best == int(np.argmax(g["counts"])) and best_cnt == g["counts"].max()
+    assert np.array_equal(mask, masks[best])
+    for h in (0, 3, 17, 95):
+        m = ransac.transformation_agreement(g["Ts"][h], g["pts"], g["l_pix"], g["r_pix"])
+        assert m.dtype == bool and np.array_equal(m, masks[h])
+    # skipped hypotheses (solvePnP failure, ransac.py:101-104) never win
+    valid = np.ones(len(g["Ts"]), np.uint8)
+    valid[best] = 0
+    c2, b2, _, m2 = ransac.score_hypotheses(g["Ts"], g["pts"], g["l_pix"], g["r_pix"], hyp_valid=valid)
+    cc = g["counts"].copy(); cc[best] = 0
+    assert np.array_equal(c2, cc) and b2 == int(np.argmax(cc)) and np.array_equal(m2, masks[b2])
+
+
+def test_no_inliers_and_ties(slamfe, golden):
+    from slamfe import ransac
+    g = golden("ransac")
+    ransac.set_cameras(g["K"], g["M1"], g["M2"])
+    far = np.tile(np.hstack([np.eye(3), [[1e4], [1e4], [5.0]]]), (5, 1, 1))
+    counts, best, cnt, mask = ransac.score_hypotheses(far, g["pts"], g["l_pix"], g["r_pix"])
+    assert counts.sum() == 0 and best == -1 and cnt == 0 and not mask.any()
+    dup = np.stack([g["Ts"][1], g["Ts"][0], g["Ts"][0], g["Ts"][2]])
+    counts, best, _, _ = ransac.score_hypotheses(dup, g["pts"], g["l_pix"], g["r_pix"])
+    assert counts[1] == counts[2] and best == int(np.argmax(counts))  # first of the tied winners
+
+
+def test_batched_frames_vs_oracle(slamfe, oracle):
+    import torch
+    from slamfe import ops, synth
+    rng = np.random.default_rng(51)
+    K, M1, M2 = synth.cameras()
+    H = 130
+    probs = [synth.pnp_problem(rng, n, H) for n in (500, 1, 257, 1300)]
+    off = np.concatenate([[0], np.cumsum([p[1].shape[0] for p in probs])]).astype(np.int32)
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    counts, best, mask = ops.ransac_score(
+        dev(np.concatenate([p[0] for p in probs])), dev(np.concatenate([p[1] for p in probs])),
+        dev(np.concatenate([p[2] for p in probs])), dev(np.concatenate([p[3] for p in probs])), K, M1, M2,
+        pt_off=dev(off), n_frames=len(probs), max_points=1300)
+    counts, best, mask = counts.cpu().numpy(), best.cpu().numpy(), mask.cpu().numpy().astype(bool)
+    for f, (Ts, pts, lp, rp) in enumerate(probs):
+        oc, ob, om = oracle.score_hypotheses(Ts, pts, lp, rp, K, M1, M2)
+        assert np.array_equal(counts[f], oc)
+        assert best[f, 0] == ob and best[f, 1] == (oc[ob] if ob >= 0 else 0)
+        assert np.array_equal(mask[off[f]:off[f + 1]], om)
+
+
+def test_full_size_4096x5000_properties(slamfe, oracle):
+    """BASELINE config 3 shape: counts of a hypothesis subset bit-exact vs the oracle, winner and
+    mask consistent with the counts."""
+    from slamfe import ransac, synth
+    rng = np.random.default_rng(61)
+    K, M1, M2 = synth.cameras()
+    ransac.set_cameras(K, M1, M2)
+    Ts, pts, lp, rp = synth.pnp_problem(rng, 5000, 4096)
+    counts, best, cnt, mask = ransac.score_hypotheses(Ts, pts, lp, rp)
+    for h in range(0, 4096, 97):
+        assert counts[h] == int(oracle.transformation_agreement(Ts[h], pts, lp, rp, K, M1, M2).sum())
+    assert best == int(np.argmax(counts)) and cnt == counts.max() and mask.sum() == cnt
+    assert np.array_equal(mask, oracle.transformation_agreement(Ts[best], pts, lp, rp, K, M1, M2))
+
+
+def test_seeded_ransac_loops_equal_reference(slamfe, golden):
+    """Same np.random seed -> same hypotheses -> the reference's own outputs (golden)."""
+    from slamfe import ransac
+    g = golden("ransac")
+    ransac.set_cameras(g["K"], g["M1"], g["M2"])
+    prev = [_Link(*r) for r in g["prev_links"]]
+    cur = [_Link(*r) for r in g["cur_links"]]
+    ms = [_M(i, int(t)) for i, t in enumerate(g["match_t"])]
+    np.random.seed(7)
+    best = ransac.ransac_pnp_for_tracking_db(ms, prev, cur, 55)
+    assert best.dtype == np.int64 and np.array_equal(best, g["tracking_best_idx"])
+    np.random.seed(11)
+    pose, idx, cnt = ransac.ransac_pnp(ms, prev, cur, inliers_percent=50)
+    assert np.array_equal(idx, g["pnp_best_idx"]) and int(cnt) == int(g["pnp_best_inliers"])
+    assert np.allclose(pose.matrix(), g["pnp_pose"], atol=1e-9)
+    with pytest.raises(ValueError):  # np.random.choice(n < 4, 4, replace=False), ransac.py:95
+        ransac.ransac_pnp_for_tracking_db(ms[:3], prev, cur, 55)

@@ -1,0 +1,113 @@
+"""Host-side logic of the mirror modules (no GPU): error behaviour, key decoding, sharding."""
+import numpy as np
+import pytest
+
+
+def test_calc_ransac_iteration_table(slamfe, golden):
+    from slamfe import ransac
+    for p, n in golden("ransac")["iters"]:
+        assert ransac.calc_ransac_iteration(int(p)) == int(n)
+    assert ransac.calc_ransac_iteration(40) == 888  # loop_closure.py:425
+
+
+def test_cameras_match_reference(slamfe, golden):
+    from slamfe import ransac, utils
+    g = golden("ransac")
+    assert np.array_equal(utils.K, g["K"]) and np.array_equal(utils.M1, g["M1"]) and np.array_equal(utils.M2, g["M2"])
+    assert np.array_equal(ransac.P, g["K"] @ g["M1"]) and np.array_equal(ransac.Q, g["K"] @ g["M2"])
+
+
+def test_key_decode(slamfe):
+    from slamfe import ops
+    keys = np.array([(37 << 22) | 5, 0xFFFFFFFF, (488 << 22) | 4194302, 0], dtype=np.uint32)
+    idx, dist = ops.keys_to_numpy(keys.view(np.int32))
+    assert idx.tolist() == [5, -1, 4194302, 0] and dist.tolist() == [37, -1, 488, 0]
+
+
+def test_ratio_mask(slamfe, golden):
+    from slamfe import matching
+    g = golden("matching")
+    for name in ("akaze", "ties", "one_train"):
+        assert np.array_equal(matching.ratio_test_mask(g[f"{name}_knn_dist"]), g[f"{name}_ratio"])
+
+
+def test_matcher_error_behaviour_matches_cv2(slamfe):
+    """cv2 4.13 behaviour: empty / None -> (), wrong dtype or width -> cv2.error,
+    all decided before the GPU is touched."""
+    import cv2
+    from slamfe import matching
+    m = matching.Matcher(crossCheck=False)
+    ref = cv2.BFMatcher(cv2.NORM_HAMMING)
+    a = np.zeros((4, 61), np.uint8)
+    assert m.match(np.zeros((0, 61), np.uint8), a) == () == tuple(ref.match(np.zeros((0, 61), np.uint8), a))
+    assert m.match(a, np.zeros((0, 61), np.uint8)) == ()
+    assert m.match(None, a) == () and m.knnMatch(a, None, k=2) == ()
+    with pytest.raises(cv2.error):
+        m.match(a.astype(np.float32), a)
+    with pytest.raises(cv2.error):
+        ref.match(a.astype(np.float32), a)
+    with pytest.raises(cv2.error):
+        m.match(a, np.zeros((4, 32), np.uint8))
+    with pytest.raises(cv2.error):
+        ref.match(a, np.zeros((4, 32), np.uint8))
+    with pytest.raises(ValueError):
+        matching.Matcher(normType=cv2.NORM_L2)
+
+
+def test_no_cpu_fallback(slamfe):
+    """Without a CUDA device the product path must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from slamfe import matching, ransac, triangulation
+    a = np.zeros((4, 61), np.uint8)
+    with pytest.raises(slamfe.SlamfeError):
+        matching.Matcher().match(a, a)
+    with pytest.raises(slamfe.SlamfeError):
+        triangulation.triangulate_links(np.ones((3, 3)), ransac.P, ransac.Q)
+    with pytest.raises(slamfe.SlamfeError):
+        ransac.transformation_agreement(np.eye(3, 4), np.ones((3, 3)), np.ones((3, 2)), np.ones((3, 2)))
+    assert matching.extract_inliers_outliers((), (), ())[0].size == 0
+
+
+def test_product_does_not_import_oracle(slamfe):
+    import os
+    import re
+    pkg = slamfe.__path__[0]
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_offsets_are_tma_aligned(slamfe):
+    from slamfe import frontend
+    off = frontend.plan_offsets([3000, 17, 0, 4999])
+    assert off.tolist() == [0, 3008, 3040, 3040, 8048]
+    assert all((int(o) * 61) % 16 == 0 for o in off)
+
+
+def test_balanced_ranges_and_slices(slamfe):
+    from slamfe import dist
+    b = dist.balanced_ranges(np.ones(10), 4)
+    assert b[0] == 0 and b[-1] == 10 and np.all(np.diff(b) >= 2)
+    b = dist.balanced_ranges([1, 1, 1, 1, 10, 1, 1, 1], 3)
+    assert b.tolist() == [0, 4, 5, 8]
+    assert dist.balanced_ranges([], 4).tolist() == [0, 0, 0, 0, 0]
+    s = dist.train_slices(20000, 8)
+    assert s[0] == 0 and s[-1] == 20000 and all(int(x) % 16 == 0 for x in s[:-1])
+    pairs = dist.candidate_pairs(5)
+    assert len(pairs) == 10 and np.all(pairs[:, 0] > pairs[:, 1])
+    blocks = dist.candidate_blocks(pairs, np.array([100, 200, 300, 400, 500]), 2)
+    w = (np.array([100, 200, 300, 400, 500])[pairs[:, 0]] * np.array([100, 200, 300, 400, 500])[pairs[:, 1]])
+    assert abs(w[: blocks[1]].sum() - w[blocks[1]:].sum()) <= w.max()
+
+
+def test_merge_top2_host(slamfe):
+    from slamfe import dist
+    rng = np.random.default_rng(0)
+    keys = rng.integers(0, 2 ** 31, (4, 50, 2), dtype=np.int64).astype(np.uint32)
+    keys.sort(axis=2)
+    merged = dist.merge_top2_host(keys)
+    flat = np.sort(keys.transpose(1, 0, 2).reshape(50, 8), axis=1)
+    assert np.array_equal(merged, flat[:, :2])

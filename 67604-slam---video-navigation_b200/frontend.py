@@ -180,14 +180,16 @@ class FrontEnd:
                                      row_keys=o["fwd_keys"], col_keys=o["bwd_keys"])
         return o
 
-    # ------------------------------------------------------------------------------------
-    def descriptor_pairs(self, seq: PackedSequence, n_links: np.ndarray | None = None) -> int:
-        """Algorithmic descriptor pairs of one run: sum Nl*Nr (+ sum links_f * links_{f+1})."""
-        total = int(np.sum(seq.n_l.astype(np.int64) * seq.n_r.astype(np.int64)))
-        if n_links is not None and len(n_links) > 1:
-            k = n_links.astype(np.int64)
-            total += int(np.sum(k[:-1] * k[1:]))
-        return total
+
+
+def descriptor_pairs(n_l, n_r, n_links=None) -> int:
+    """Algorithmic descriptor pairs of one pass: sum Nl*Nr (stereo; one pass yields both
+    directions) + sum links_f * links_{f+1} (consecutive frames on the filtered features)."""
+    total = int(np.sum(np.asarray(n_l, dtype=np.int64) * np.asarray(n_r, dtype=np.int64)))
+    if n_links is not None and len(n_links) > 1:
+        k = np.asarray(n_links, dtype=np.int64)
+        total += int(np.sum(k[:-1] * k[1:]))
+    return total
 
 
 def results_to_host(o, keys=("match_t", "n_matches", "n_links", "link_src", "links", "xyz", "fwd_keys", "bwd_keys"),

@@ -142,3 +142,97 @@ def pnp_problem(rng: np.random.Generator, n: int, n_hyp: int, outlier_frac: floa
         Ts[h] = np.hstack([_rodrigues(rvec + rng.normal(0, s, 3)),
                            (tvec + rng.normal(0, 10 * s, 3))[:, None]])
     return Ts, pts, l_pix, r_pix
+
+
+# ----------------------------------------------------------------------------------------------
+# Whole-sequence generator on the GPU (torch is plumbing here: RNG + memory), BASELINE config 2.
+# Every frame depends only on (seed, frame index), so any rank can generate any frame range and
+# neighbouring ranks agree on their shared halo frame.
+# ----------------------------------------------------------------------------------------------
+def _fresh_count(seed, f, lo=1000, hi=2500):
+    """Number of 'new' descriptors frame f introduces (pure function of seed and f)."""
+    if f < 0:
+        return 0
+    return int(np.random.default_rng([seed, f, 17]).integers(lo, hi + 1))
+
+
+def sequence_sizes(n_frames, first_frame=0, seed=1, lo=1000, hi=2500):
+    """Per-frame keypoint counts: n_f = fresh_{f-1} + fresh_f in [2*lo, 2*hi] (KITTI-like 2-5k)."""
+    return np.array([_fresh_count(seed, f - 1, lo, hi) + _fresh_count(seed, f, lo, hi) if f > 0
+                     else 2 * _fresh_count(seed, 0, lo, hi)
+                     for f in range(first_frame, first_frame + n_frames)], dtype=np.int32)
+
+
+def torch_sequence(n_frames, first_frame=0, seed=1, device="cuda", lo=1000, hi=2500, row_align=16):
+    """Synthetic stereo sequence in the packed layout of frontend.PackedSequence, generated on
+    `device`.  Frame f's left descriptors are bit-flipped copies (p = 1/16 per bit) of the
+    descriptors frame f-1 introduced plus fresh random ones, row-permuted; its right descriptors
+    are flipped copies of 60 % of the left rows (permuted) plus random rows; 1 % exact duplicates
+    force distance ties; right keypoints of true matches satisfy the rectified-stereo geometry
+    except for 15 % gross outliers.  Returns a dict of tensors + numpy offset arrays."""
+    import torch
+
+    def gen(f, tag):
+        g = torch.Generator(device=device)
+        g.manual_seed((seed * 1000003 + f) * 31 + tag)
+        return g
+
+    def rand_desc(n, g):
+        d = torch.randint(0, 256, (n, DESC_BYTES), dtype=torch.uint8, device=device, generator=g)
+        d[:, 60] &= 0x3F
+        return d
+
+    def flip(d, g):
+        m = torch.randint(0, 256, (4,) + tuple(d.shape), dtype=torch.uint8, device=device, generator=g)
+        out = d ^ (m[0] & m[1] & m[2] & m[3])
+        out[:, 60] &= 0x3F
+        return out
+
+    def fresh(f):
+        return rand_desc(_fresh_count(seed, f, lo, hi), gen(f, 1))
+
+    sizes = sequence_sizes(n_frames, first_frame, seed, lo, hi)
+    off = np.zeros(n_frames + 1, dtype=np.int64)
+    np.cumsum((sizes.astype(np.int64) + row_align - 1) // row_align * row_align, out=off[1:])
+    total = int(off[-1])
+    desc_l = torch.zeros((total, DESC_BYTES), dtype=torch.uint8, device=device)
+    desc_r = torch.zeros((total, DESC_BYTES), dtype=torch.uint8, device=device)
+    pts_l = torch.zeros((total, 2), dtype=torch.float32, device=device)
+    pts_r = torch.zeros((total, 2), dtype=torch.float32, device=device)
+    prev_fresh = fresh(first_frame - 1) if first_frame > 0 else None
+    for i in range(n_frames):
+        f = first_frame + i
+        g = gen(f, 2)
+        cur_fresh = fresh(f)
+        old = flip(prev_fresh, g) if prev_fresh is not None else rand_desc(cur_fresh.shape[0], g)
+        left = torch.cat([old, cur_fresh])[torch.randperm(int(sizes[i]), device=device, generator=g)]
+        n = left.shape[0]
+        assert n == int(sizes[i])
+        n_match = int(0.6 * n)
+        src = torch.randperm(n, device=device, generator=g)[:n_match]
+        dst = torch.randperm(n, device=device, generator=g)[:n_match]
+        right = rand_desc(n, g)
+        right[dst] = flip(left[src], g)
+        n_dup = max(1, n // 100)
+        a = torch.randint(0, n, (n_dup,), device=device, generator=g)
+        b = torch.randint(0, n, (n_dup,), device=device, generator=g)
+        right[a] = right[b]
+        pl = torch.rand((n, 2), device=device, generator=g) * torch.tensor([1200.0, 365.0], device=device) \
+            + torch.tensor([20.0, 5.0], device=device)
+        pr = torch.rand((n, 2), device=device, generator=g) * torch.tensor([1200.0, 365.0], device=device) \
+            + torch.tensor([20.0, 5.0], device=device)
+        d = torch.rand((n_match,), device=device, generator=g) * 117.5 + 2.5
+        bad = torch.rand((n_match,), device=device, generator=g) < 0.15
+        xr = pl[src, 0] - torch.where(bad, -torch.ones_like(d), d)
+        yr = pl[src, 1] + 0.5 * torch.randn((n_match,), device=device, generator=g)
+        pr[dst, 0] = xr
+        pr[dst, 1] = yr
+        o = int(off[i])
+        desc_l[o:o + n] = left
+        desc_r[o:o + n] = right
+        pts_l[o:o + n] = pl
+        pts_r[o:o + n] = pr
+        prev_fresh = cur_fresh
+    off32 = off.astype(np.int32)
+    return {"desc_l": desc_l, "desc_r": desc_r, "pts_l": pts_l, "pts_r": pts_r,
+            "l_off": off32, "r_off": off32.copy(), "n_l": sizes, "n_r": sizes.copy()}

@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""Front-end hot-path benchmark (driver contract: one JSON line on rank 0).
+
+Workload = BASELINE.json configs[1]: a synthetic KITTI-00-shaped stereo sequence of 4541 frames
+PER GPU (1241x376, 2-5k 61-byte AKAZE descriptors per image): L<->R crossCheck matching + row
+filter + links, triangulation of every link, and frame t<->t+1 forward/backward matching on the
+filtered features.  One "step" = one pass over the whole sequence.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl slamfe|reference]
+
+  value         frame pairs/s, whole job, inputs resident in HBM when the timed region starts
+  e2e           same metric through the host-buffer API: pinned host inputs -> H2D -> kernels ->
+                D2H of the result tables, all inside the timed region
+  roofline      the matcher kernel (dominant): algorithmic 16 popc32 per descriptor pair over the
+                live CUDA-event duration of its launch, against the popc-pipe peak measured on
+                this GPU by slamfe_peak_kernel (MEASURED_PEAKS.json has no INT-pipe figure);
+                HBM figures beside it
+  cpu_baseline  the reference's CPU path (cv2.BFMatcher + the oracle's restatement of the
+                reference's Python loops) on a bounded sample of the same frames, host cores
+  --impl reference   the CPU path alone, same metric/config, bounded sample per step
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "frame pairs/s (stereo + consecutive-frame Hamming matching, row filter, triangulation)"
+UNIT = "frame_pairs/s"
+
+
+# --------------------------------------------------------------------------------------------
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=4541, help="frames per GPU (KITTI 00 has 4541)")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--impl", default="slamfe", choices=["slamfe", "reference"])
+    ap.add_argument("--cpu-sample-frames", type=int, default=48)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index=0, period=0.1):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        self.index, self.period = index, period
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {}
+        for n in dir(nv):
+            if n.startswith("nvmlClocksEventReason") or n.startswith("nvmlClocksThrottleReason"):
+                v = getattr(nv, n)
+                if isinstance(v, int) and v:
+                    names.setdefault(v, n.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit and bit & (bit - 1) == 0:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        idle = {"GpuIdle", "None", "ApplicationsClocksSetting"}
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(r for r in self.reasons if r not in idle),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU path of the reference on host cores (oracle = checker / baseline only)
+# --------------------------------------------------------------------------------------------
+def cpu_frames_pass(frames, P, Q, collect=False):
+    """The reference's per-frame work (database.py:12-27, :54-77; ransac.py:83) on the CPU:
+    cv2 crossCheck match, row filter, create_links, np.linalg.svd triangulation per link,
+    forward+backward cv2 matches + mutual check.  Returns per-frame results when collect=True."""
+    import cv2
+    from oracle import ref_oracle as ora
+    lr = cv2.BFMatcher(normType=cv2.NORM_HAMMING, crossCheck=True)
+    mm = cv2.BFMatcher(normType=cv2.NORM_HAMMING, crossCheck=False)
+    out, prev_feat = [], None
+    for dl, dr, pl, pr in frames:
+        ms = lr.match(dl, dr)
+        mq = np.fromiter((m.queryIdx for m in ms), np.int32, len(ms))
+        mt = np.fromiter((m.trainIdx for m in ms), np.int32, len(ms))
+        inl, _ = ora.extract_inliers_outliers(pl, pr, mq, mt)
+        valid, links = ora.create_links(pl, pr, mq[inl], mt[inl])
+        feat = dl[valid]
+        xyz = ora.triangulate_links(links, P, Q)
+        fwd_t = fwd_d = bwd_t = None
+        if prev_feat is not None and len(prev_feat) and len(feat):
+            fwd = mm.match(prev_feat, feat)
+            bwd = mm.match(feat, prev_feat)
+            fwd_t = np.fromiter((m.trainIdx for m in fwd), np.int32, len(fwd))
+            fwd_d = np.fromiter((m.distance for m in fwd), np.int32, len(fwd))
+            bwd_t = np.fromiter((m.trainIdx for m in bwd), np.int32, len(bwd))
+        if collect:
+            out.append({"mq": mq, "mt": mt, "inl": inl, "links": links, "xyz": xyz, "fwd_t": fwd_t, "fwd_d": fwd_d,
+                        "bwd_t": bwd_t})
+        prev_feat = feat
+    return out
+
+
+def host_frames(seq_t, first, count):
+    """Slice `count` frames out of the packed (torch, possibly CUDA) sequence as numpy arrays."""
+    frames = []
+    for f in range(first, first + count):
+        lo, n = int(seq_t["l_off"][f]), int(seq_t["n_l"][f])
+        ro, m = int(seq_t["r_off"][f]), int(seq_t["n_r"][f])
+        frames.append((seq_t["desc_l"][lo:lo + n].cpu().numpy(), seq_t["desc_r"][ro:ro + m].cpu().numpy(),
+                       seq_t["pts_l"][lo:lo + n].cpu().numpy(), seq_t["pts_r"][ro:ro + m].cpu().numpy()))
+    return frames
+
+
+def cpu_threads():
+    import cv2
+    cv2.setNumThreads(os.cpu_count() or 1)
+    return cv2.getNumThreads()
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU path alone.  Rank 0 only; other ranks exit 0 without work."""
+    if rank != 0:
+        return
+    import torch
+    import cv2
+    from slamfe import synth, utils
+    threads = cpu_threads()
+    n = max(2, min(args.cpu_sample_frames, args.frames))
+    seq = synth.torch_sequence(n, first_frame=0, seed=args.seed, device="cpu")
+    frames = host_frames(seq, 0, n)
+    for _ in range(max(args.warmup, 0)):
+        cpu_frames_pass(frames[:4], utils.P, utils.Q)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_frames_pass(frames, utils.P, utils.Q)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = (n - 1) / dt
+    sample = f"{n} consecutive frames of the workload per step (cv2 {cv2.__version__}, numpy {np.__version__})"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(args, world):
+    return {"workload": "configs[1]: synthetic 4541-frame KITTI-00-shaped stereo sequence per GPU "
+                        "(stereo + consecutive-frame matching + triangulation)",
+            "frames_per_gpu": args.frames, "frames_total": args.frames * world,
+            "keypoints_per_image": "2000-5000 (mean 3500)", "descriptor_bytes": 61, "image": "1241x376",
+            "l2_policy": "inputs (~2 GB/GPU) are larger than L2; no flush needed", "seed": args.seed,
+            "sharding": f"contiguous frame-pair blocks, {world} rank(s), +1 halo frame per rank"}
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    from slamfe import dist as sdist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as tdist
+    import slamfe
+    from slamfe import frontend, ops, synth, utils
+    rank, world, local_rank = sdist.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
+    dev = torch.device("cuda", local_rank)
+    slamfe.load_library()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- synthetic inputs, generated on the GPU; rank r owns frames [r*F, (r+1)*F) + 1 halo ----
+    F = args.frames
+    halo = 1 if world > 1 and rank < world - 1 else 0
+    seq_t = synth.torch_sequence(F + halo, first_frame=rank * F, seed=args.seed, device=dev)
+    ds = frontend.DeviceSequence(
+        seq_t["desc_l"], seq_t["desc_r"], seq_t["pts_l"], seq_t["pts_r"],
+        torch.from_numpy(seq_t["l_off"]).to(dev), torch.from_numpy(seq_t["r_off"]).to(dev),
+        torch.from_numpy(seq_t["n_l"]).to(dev), torch.from_numpy(seq_t["n_r"]).to(dev),
+        F + halo, int(seq_t["n_l"].max()), int(seq_t["n_r"].max()))
+    fe = frontend.FrontEnd()
+    pairs_total = F * world - 1  # the last frame of the job has no successor
+
+    def gather_tables(o):
+        """The only collective: all-gather of the per-shard best-match tables (fixed stride)."""
+        if world == 1:
+            return None
+        n_rows = int(seq_t["l_off"][F])
+        cap = torch.tensor([n_rows], device=dev, dtype=torch.int64)
+        caps = torch.empty((world,), device=dev, dtype=torch.int64)
+        tdist.all_gather_into_tensor(caps, cap)
+        stride = int(caps.max())
+        pad = torch.zeros((stride, 2), dtype=torch.int32, device=dev)
+        pad[:n_rows, 0] = o["match_t"][:n_rows]
+        pad[:n_rows, 1] = o["fwd_keys"][:n_rows, 0]
+        out = torch.empty((world, stride, 2), dtype=torch.int32, device=dev)
+        tdist.all_gather_into_tensor(out, pad)
+        summ = torch.stack([o["n_matches"][:F], o["n_links"][:F]], dim=1).contiguous()
+        allsumm = torch.empty((world,) + tuple(summ.shape), dtype=summ.dtype, device=dev)
+        tdist.all_gather_into_tensor(allsumm, summ)
+        return out, allsumm
+
+    def step():
+        o = fe.run(ds)
+        gather_tables(o)
+        return o
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    barrier()
+
+    # ---- timed region: K steps, inputs resident in HBM ----
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            out = step()
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        tdist.all_reduce(t_ms, op=tdist.ReduceOp.MAX)
+    ms_per_step = float(t_ms.item()) / args.steps
+    value = pairs_total / (ms_per_step * 1e-3)
+
+    n_links = out["n_links"].cpu().numpy()
+    # algorithmic descriptor pairs of this rank: its F stereo frames + its consecutive pairs
+    desc_pairs_local = frontend.descriptor_pairs(seq_t["n_l"][:F], seq_t["n_r"][:F], n_links[:F + halo])
+    dp = torch.tensor([desc_pairs_local], device=dev, dtype=torch.float64)
+    if world > 1:
+        tdist.all_reduce(dp, op=tdist.ReduceOp.SUM)
+    desc_pairs_total = float(dp.item())
+
+    # ---- e2e: host buffers in, host tables out, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        pinned_in = {k: torch.empty(seq_t[k].shape, dtype=seq_t[k].dtype, pin_memory=True).copy_(seq_t[k])
+                     for k in ("desc_l", "desc_r", "pts_l", "pts_r")}
+        small = {k: torch.from_numpy(seq_t[k]).pin_memory() for k in ("l_off", "r_off", "n_l", "n_r")}
+        h2d = sum(t.numel() * t.element_size() for t in list(pinned_in.values()) + list(small.values()))
+        dev_in = {k: torch.empty_like(v, device=dev) for k, v in pinned_in.items()}
+        dev_small = {k: torch.empty_like(v, device=dev) for k, v in small.items()}
+        pinned_out, d2h = None, 0
+
+        def e2e_step():
+            nonlocal pinned_out, d2h
+            for k in pinned_in:
+                dev_in[k].copy_(pinned_in[k], non_blocking=True)
+            for k in small:
+                dev_small[k].copy_(small[k], non_blocking=True)
+            d = frontend.DeviceSequence(dev_in["desc_l"], dev_in["desc_r"], dev_in["pts_l"], dev_in["pts_r"],
+                                        dev_small["l_off"], dev_small["r_off"], dev_small["n_l"], dev_small["n_r"],
+                                        ds.n_frames, ds.max_nl, ds.max_nr)
+            o = fe.run(d)
+            gather_tables(o)
+            _, d2h, pinned_out = frontend.results_to_host(o, pinned=pinned_out)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            tdist.all_reduce(e_ms, op=tdist.ReduceOp.MAX)
+        e2e = {"value": pairs_total / (float(e_ms.item()) / args.steps * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": float(e_ms.item()) / args.steps}
+        del pinned_in, dev_in
+
+    # ---- roofline of the dominant kernel: the stereo matcher launch, timed alone with events ----
+    roofline = cpu_baseline = parity = None
+    if rank == 0:
+        FF = ds.n_frames
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(2, args.steps)
+        torch.cuda.synchronize()
+        k0.record()
+        for _ in range(reps):
+            ops.hamming_top2_batched(ds.desc_l, ds.l_off, ds.desc_r, ds.r_off, FF, ds.max_nl, ds.max_nr, 61,
+                                     q_cnt=ds.n_l, t_cnt=ds.n_r, want_cols=True,
+                                     row_keys=out["lr_row_keys"], col_keys=out["lr_col_keys"])
+        k1.record()
+        torch.cuda.synchronize()
+        launch_ms = k0.elapsed_time(k1) / reps
+        nl, nr = seq_t["n_l"][:FF].astype(np.int64), seq_t["n_r"][:FF].astype(np.int64)
+        pairs_launch = float(np.sum(nl * nr))
+        popc_launch = 16.0 * pairs_launch
+        achieved = popc_launch / (launch_ms * 1e-3) / 1e9
+        peak_popc = ops.measure_peak(0) / 1e9
+        peak_mix = ops.measure_peak(1) / 1e9
+        peak_fp64 = ops.measure_peak(2) / 1e9
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        nominal = sms * 16 * 1.965
+        alg_bytes = float(61 * np.sum(nl + nr) + 8 * np.sum(nl) + 4 * np.sum(nr))
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        roofline = {
+            "kernel": "hamming_top2_kernel<2,256,COL> (stereo L<->R launch, all frames)",
+            "bound": "popc", "achieved": achieved, "peak": peak_popc, "unit": "Gpopc32/s",
+            "frac": achieved / peak_popc if peak_popc else None, "traffic": None,
+            "peak_source": "measured on this GPU: slamfe_peak_kernel mode 0 (pure POPC chains)",
+            "peak_matcher_mix": peak_mix, "peak_nominal_16_per_clk_per_sm_at_max_clock": nominal,
+            "frac_of_nominal": achieved / nominal, "launch_ms": launch_ms,
+            "algorithmic_popc_per_launch": popc_launch, "descriptor_pairs_per_launch": pairs_launch,
+            "gdesc_pairs_per_s": pairs_launch / (launch_ms * 1e-3) / 1e9,
+            "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (launch_ms * 1e-3) / 1e9,
+                    "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                    "frac": alg_bytes / (launch_ms * 1e-3) / 1e9 / hbm_peak},
+            "fp64_fma_peak_gfma": peak_fp64,
+            "share_of_step": launch_ms / ms_per_step,
+        }
+
+        # ---- CPU baseline on a bounded sample + parity of the GPU tables on those frames ----
+        if not args.no_cpu_baseline:
+            n = max(2, min(args.cpu_sample_frames, F))
+            frames = host_frames(seq_t, 0, n)
+            threads = cpu_threads()
+            cpu_frames_pass(frames[:3], utils.P, utils.Q)
+            t0 = time.perf_counter()
+            res = cpu_frames_pass(frames, utils.P, utils.Q, collect=True)
+            dt = time.perf_counter() - t0
+            import cv2
+            cpu_baseline = {"value": (n - 1) / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                            "sample": f"first {n} frames of the workload ({dt:.1f} s): cv2 {cv2.__version__} "
+                                      f"BFMatcher crossCheck + fwd/bwd match with all host threads, oracle "
+                                      f"restatement of the reference's Python row filter / create_links / "
+                                      f"per-link np.linalg.svd triangulation (single thread, as the reference)"}
+            host, _, _ = frontend.results_to_host(out)
+            ok, worst = True, 0.0
+            for f, r in enumerate(res):
+                lo, k = int(seq_t["l_off"][f]), len(r["inl"])
+                mt = host["match_t"][lo:lo + int(seq_t["n_l"][f])]
+                ok &= bool(np.array_equal(np.nonzero(mt >= 0)[0], r["mq"]) and np.array_equal(mt[mt >= 0], r["mt"]))
+                ok &= bool(host["n_links"][f] == k and np.array_equal(host["link_src"][lo:lo + k], r["mq"][r["inl"]]))
+                if k:
+                    got = host["xyz"][lo:lo + k].astype(np.float64)
+                    worst = max(worst, float((np.linalg.norm(got - r["xyz"], axis=1) /
+                                              np.linalg.norm(r["xyz"], axis=1)).max()))
+                if f + 1 < n and res[f + 1]["fwd_t"] is not None:
+                    nxt = res[f + 1]
+                    fi, fd = ops.keys_to_numpy(host["fwd_keys"][lo:lo + k])
+                    ok &= bool(np.array_equal(fi[:, 0], nxt["fwd_t"]) and np.array_equal(fd[:, 0], nxt["fwd_d"]))
+                    lo1, k1n = int(seq_t["l_off"][f + 1]), len(nxt["inl"])
+                    bi, _ = ops.keys_to_numpy(host["bwd_keys"][lo1:lo1 + k1n])
+                    ok &= bool(np.array_equal(bi, nxt["bwd_t"]))
+            parity = {"frames_checked": n, "match_tables_bit_exact": ok, "xyz_max_rel_err": worst,
+                      "xyz_tolerance": 1e-5}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, world),
+            "descriptor_pairs_per_s": desc_pairs_total / (ms_per_step * 1e-3),
+            "descriptor_pairs_per_step": desc_pairs_total,
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": fe.launches_per_run * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        tdist.barrier()
+        tdist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -53,12 +53,10 @@ def test_sequence_pipeline_vs_oracle(slamfe, oracle):
         oi, od = oracle.knn2(feats[f], feats[f + 1])
         assert np.array_equal(fi, oi) and np.array_equal(fd, od)
         lo1, k1 = seq.l_off[f + 1], len(feats[f + 1])
-        bi, bd = ops.keys_to_numpy(host["bwd_keys"][lo:lo + k1])  # indexed with problem f's train offset
-        assert lo1 >= 0
         obi, obd = oracle.match(feats[f + 1], feats[f])
         got_b = ops.keys_to_numpy(host["bwd_keys"][lo1:lo1 + k1])
         assert np.array_equal(got_b[0], obi) and np.array_equal(got_b[1], obd)
-    pairs = fe.descriptor_pairs(seq, host["n_links"])
+    pairs = frontend.descriptor_pairs(seq.n_l, seq.n_r, host["n_links"])
     assert pairs == sum(len(a) * len(b) for a, b, _, _ in frames) + sum(
         len(feats[f]) * len(feats[f + 1]) for f in range(len(frames) - 1))
 

@@ -1,0 +1,20 @@
+#!/bin/bash
+# One GPU visit: parity tests, smoke, bench, ncu launch list, ncu full capture of the matcher.
+# Run as: gpurun --timeout 1700 -- 'bash scripts/gpu_round.sh'
+set -u
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 500 > gpurun_out/clocks.csv &
+SMI=$!
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
+python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/smoke.log
+python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "bench ref rc=$?"
+kill $SMI
+BENCH_SMALL="python bench.py --frames 512 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
+$BENCH_SMALL > gpurun_out/plain_small.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $BENCH_SMALL > gpurun_out/ncu_launches.log 2>&1
+echo "ncu launches rc=$?"
+$BENCH_SMALL > gpurun_out/plain_small2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:hamming_top2 -s 4 -c 2 -f -o gpurun_out/prof_hamming $BENCH_SMALL > gpurun_out/ncu_full.log 2>&1
+echo "ncu full rc=$?"
+tail -3 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log; cat gpurun_out/bench.json; cat gpurun_out/bench_ref.json

@@ -15,17 +15,18 @@ KEY_IDX_BITS = 22
 KEY_IDX_MASK = (1 << KEY_IDX_BITS) - 1
 KEY_NONE = 0xFFFFFFFF
 MAX_DESC_BYTES = 64
+MATCH_BEST_ONLY = 1
 
 # name -> (restype, argtypes); mirrors include/slamfe.h one to one
 _SIGNATURES = {
     "slamfe_version": (c_int, []),
     "slamfe_error_string": (c_char_p, [c_int]),
     "slamfe_hamming_top2": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
-                                    c_void_p, c_void_p, c_void_p]),
+                                    c_void_p, c_void_p, c_int, c_void_p]),
     "slamfe_hamming_top2_batched": (c_int, [c_void_p, c_int, c_void_p, c_void_p,
                                             c_void_p, c_int, c_void_p, c_void_p,
                                             c_int, c_int, c_int, c_int,
-                                            c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+                                            c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "slamfe_unpack_keys": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "slamfe_merge_top2": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "slamfe_cross_check": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -4,18 +4,24 @@
 // sites final_project/backend/database/database.py:54-55, backend/loop/loop_closure.py:422,
 // final_project/algorithms/matching.py:15,44 and VAN_ex/code/ex1.py:189-190.
 //
-// Design (INT/popc-pipe bound; no tensor cores — this is XOR+POPC, not a dense contraction):
+// Design (integer-pipe bound; no tensor cores — this is XOR+POPC, not a dense contraction):
 //   * grid = (query tiles, train slices, problems): one launch covers a ragged batch of frame
 //     pairs; the hardware CTA scheduler is the work queue.
-//   * every thread keeps R query descriptors (16 x u32 each) and their running top-2 keys in
-//     registers for the whole train sweep;
+//   * every thread keeps up to RMAX query descriptors (16 x u32 each) and their running best keys
+//     in registers for the whole train sweep;
 //   * the train rows stream through shared memory in 128-row stages: a 1-D TMA bulk copy
 //     (cp.async.bulk + mbarrier) lands the raw 61-byte rows, the CTA re-aligns them to 64-byte
 //     rows (funnel shift) into a double-buffered tile, and all lanes read the same train row
 //     with broadcast LDS.128;
+//   * prefix-XOR carry-save distance (below): 16 LOP3 + 11 LOP3 + 7 POPC per descriptor pair
+//     instead of 16 LOP3 + 16 POPC — POPC runs on the XU pipe at 16 lanes/clk/SM and was the
+//     limiter (ncu: XU 92 %), LOP3 runs on the ALU pipe at 64 lanes/clk/SM;
 //   * key = (distance << 22) | index, so unsigned min == cv2's first-minimum tie-break; the
 //     per-train-row (column) minimum for crossCheck / the backward match comes from the same
-//     pass: lane-min, one REDUX.MIN per warp, shared atomicMin, one global atomicMin per CTA.
+//     pass: lane-min, one warp reduction per row, per-warp shared slots, one global atomicMin
+//     per CTA and train row.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace slamfe {
@@ -89,17 +95,158 @@ __device__ __forceinline__ void merge_row_keys(uint2 *g, uint32_t k1, uint32_t k
     } while (old != assumed);
 }
 
-template <int R, int THREADS, bool COL>
-__global__ void __launch_bounds__(THREADS) hamming_top2_kernel(const HammingParams p)
+// ---- prefix-XOR carry-save Hamming distance --------------------------------------------------
+// Both operands are held in "prefix form": word k stays w[k] for k odd, k = 0 and k = 15, and
+// becomes w[0]^w[1]^...^w[k] for k = 2, 4, ..., 14.  XOR-ing the prefix forms of a query and a
+// train row therefore gives X[k] = x[k] (the plain XOR word) at the unchanged positions and the
+// running parity word x[0]^...^x[k] at the even ones — which is exactly the "ones" output of a
+// chain of full adders that consumes two new words per step:
+//     ones_0 = x0;  (ones_k, twos_k) = full_add(ones_{k-1}, x_{2k-1}, x_{2k})   =>  ones_k = X[2k]
+// The carry of step k only needs ones_{k-1}, x_{2k-1} and ones_k (x_{2k} = ones_{k-1}^x_{2k-1}^ones_k):
+//     twos_k = maj(a, b, a^b^s) with a = X[2k-2], b = X[2k-1], s = X[2k]            (LOP3 0xD4)
+// so a descriptor pair costs 16 XOR + 7 carries (23 LOP3) and 9 POPC:
+//     d = popc(X14) + popc(X15) + 2 * sum_k popc(twos_k)
+// and every further full adder on equal-weight words trades one more POPC for 2 LOP3 (CS = 8..10).
+// POPC issues on the XU pipe (16 lanes/clk/SM), LOP3 on the ALU pipe (64 lanes/clk/SM).
+__device__ __forceinline__ uint32_t lop3_carry_prefix(uint32_t a, uint32_t b, uint32_t s)
 {
-    constexpr int TQ = R * THREADS;
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xD4;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
+    return d;
+}
+__device__ __forceinline__ uint32_t fa_sum(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t fa_carry(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// In-register conversion of 16 aligned words to prefix form.
+__device__ __forceinline__ void to_prefix_form(uint32_t (&w)[W])
+{
+    uint32_t run = w[0] ^ w[1];
+#pragma unroll
+    for (int k = 2; k <= 14; k += 2) {
+        run ^= w[k];
+        const uint32_t odd = w[k + 1];
+        w[k] = run;
+        run ^= odd;
+    }
+}
+
+// acc + popc(x) * (WEIGHT << 22) as one IMAD: the multiply-add runs on the FMA pipe, which is
+// otherwise idle here, instead of IADD3/LEA on the saturated ALU pipe.
+template <uint32_t WEIGHT>
+__device__ __forceinline__ uint32_t popc_mad(uint32_t x, uint32_t acc)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(__popc(x)), "n"(WEIGHT << KEY_IDX_BITS), "r"(acc));
+    return d;
+}
+
+// Returns distance << 22 (the key without its index bits).
+template <int CS>
+__device__ __forceinline__ uint32_t hamming16_key(const uint32_t (&q)[W], const uint4 &t0, const uint4 &t1,
+                                                  const uint4 &t2, const uint4 &t3)
+{
+    static_assert(CS >= 7 && CS <= 10, "CS = number of full adders per descriptor pair");
+    const uint32_t x0 = q[0] ^ t0.x, x1 = q[1] ^ t0.y, x2 = q[2] ^ t0.z, x3 = q[3] ^ t0.w;
+    const uint32_t x4 = q[4] ^ t1.x, x5 = q[5] ^ t1.y, x6 = q[6] ^ t1.z, x7 = q[7] ^ t1.w;
+    const uint32_t x8 = q[8] ^ t2.x, x9 = q[9] ^ t2.y, x10 = q[10] ^ t2.z, x11 = q[11] ^ t2.w;
+    const uint32_t x12 = q[12] ^ t3.x, x13 = q[13] ^ t3.y, x14 = q[14] ^ t3.z, x15 = q[15] ^ t3.w;
+    const uint32_t c0 = lop3_carry_prefix(x0, x1, x2);
+    const uint32_t c1 = lop3_carry_prefix(x2, x3, x4);
+    const uint32_t c2 = lop3_carry_prefix(x4, x5, x6);
+    const uint32_t c3 = lop3_carry_prefix(x6, x7, x8);
+    const uint32_t c4 = lop3_carry_prefix(x8, x9, x10);
+    const uint32_t c5 = lop3_carry_prefix(x10, x11, x12);
+    const uint32_t c6 = lop3_carry_prefix(x12, x13, x14);
+    uint32_t acc = popc_mad<1>(x15, popc_mad<1>(x14, 0u));
+    if (CS == 7) {
+        acc = popc_mad<2>(c0, acc); acc = popc_mad<2>(c1, acc); acc = popc_mad<2>(c2, acc);
+        acc = popc_mad<2>(c3, acc); acc = popc_mad<2>(c4, acc); acc = popc_mad<2>(c5, acc);
+        return popc_mad<2>(c6, acc);
+    }
+    const uint32_t p0 = fa_sum(c0, c1, c2), f0 = fa_carry(c0, c1, c2);
+    if (CS == 8) {
+        acc = popc_mad<2>(p0, acc); acc = popc_mad<4>(f0, acc); acc = popc_mad<2>(c3, acc);
+        acc = popc_mad<2>(c4, acc); acc = popc_mad<2>(c5, acc);
+        return popc_mad<2>(c6, acc);
+    }
+    const uint32_t p1 = fa_sum(c3, c4, c5), f1 = fa_carry(c3, c4, c5);
+    if (CS == 9) {
+        acc = popc_mad<2>(p0, acc); acc = popc_mad<4>(f0, acc); acc = popc_mad<2>(p1, acc);
+        acc = popc_mad<4>(f1, acc);
+        return popc_mad<2>(c6, acc);
+    }
+    const uint32_t p2 = fa_sum(p0, p1, c6), f2 = fa_carry(p0, p1, c6);
+    acc = popc_mad<4>(f0, acc); acc = popc_mad<4>(f1, acc); acc = popc_mad<2>(p2, acc);
+    return popc_mad<4>(f2, acc);
+}
+
+// One shared-memory stage (rows train rows) against the NR query rows each lane holds.
+template <int NR, int RMAX, bool COL, bool TOP2, int CS>
+__device__ __forceinline__ void sweep_stage(const uint4 *__restrict__ tl, int rows, uint32_t jbase,
+                                            const uint32_t (&q)[RMAX][W], uint32_t (&b1)[RMAX], uint32_t (&b2)[RMAX],
+                                            const uint32_t (&colbias)[RMAX], uint32_t *colmin_w, int lane)
+{
+    uint32_t jj = jbase;
+#pragma unroll 2
+    for (int j = 0; j < rows; ++j, ++jj) {
+        const uint4 t0 = tl[4 * j + 0], t1 = tl[4 * j + 1], t2 = tl[4 * j + 2], t3 = tl[4 * j + 3];
+        uint32_t ck = KEY_NONE;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const uint32_t dk = hamming16_key<CS>(q[r], t0, t1, t2, t3);
+            const uint32_t key = dk + jj;
+            if (TOP2) {
+                const uint32_t hi = max(b1[r], key);
+                b2[r] = min(b2[r], hi);
+            }
+            b1[r] = min(b1[r], key);
+            if (COL) ck = min(ck, dk + colbias[r]);
+        }
+        if (COL) {
+            const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, ck);
+            if (lane == 0) colmin_w[j] = m;
+        }
+    }
+}
+
+template <int N, int RMAX, bool COL, bool TOP2, int CS>
+__device__ __forceinline__ void sweep_dispatch(int nr_w, const uint4 *__restrict__ tl, int rows, uint32_t jbase,
+                                               const uint32_t (&q)[RMAX][W], uint32_t (&b1)[RMAX],
+                                               uint32_t (&b2)[RMAX], const uint32_t (&colbias)[RMAX],
+                                               uint32_t *colmin_w, int lane)
+{
+    if (nr_w == N)
+        sweep_stage<N, RMAX, COL, TOP2, CS>(tl, rows, jbase, q, b1, b2, colbias, colmin_w, lane);
+    else if constexpr (N > 1)
+        sweep_dispatch<N - 1, RMAX, COL, TOP2, CS>(nr_w, tl, rows, jbase, q, b1, b2, colbias, colmin_w, lane);
+}
+
+// grid = (query tiles of RMAX*THREADS rows, train slices, problems).  Query rows are dealt to
+// threads in slabs of THREADS rows (row = tile + r*THREADS + tid), so a warp of a partial tile
+// only sweeps the slabs that hold rows (nr_w of them) and an all-empty warp only helps staging.
+template <int THREADS, int RMAX, bool COL, bool TOP2, int CS>
+__global__ void __launch_bounds__(THREADS, (RMAX >= 3 ? 2 : 3)) hamming_top2_kernel(const HammingParams p)
+{
+    constexpr int TQ = RMAX * THREADS;
+    constexpr int NWARP = THREADS / 32;
     __shared__ alignas(128) uint32_t tile[2][TS * W];
     __shared__ alignas(128) uint8_t raw[2][RAW_BYTES];
-    __shared__ uint32_t colmin_s[2][TS];
+    __shared__ uint32_t colmin_s[COL ? 2 : 1][COL ? NWARP : 1][COL ? TS : 1];
     __shared__ alignas(8) uint64_t mbar[2];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+    const int warp = tid >> 5;
     const int prob = blockIdx.z;
 
     int q_row0 = 0, nq = p.nq, t_row0 = 0, nt = p.nt;
@@ -116,6 +263,8 @@ __global__ void __launch_bounds__(THREADS) hamming_top2_kernel(const HammingPara
     if (qt0 >= nq || tb >= nt) return;  // CTA-uniform; outputs were pre-set to KEY_NONE
     const int te = min(nt, tb + p.t_slice);
     const int n_stage = (te - tb + TS - 1) / TS;
+    // warps that hold at least one query row (the others never write column minima)
+    const int n_active_warps = min(NWARP, (nq - qt0 + 31) / 32);
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -140,27 +289,42 @@ __global__ void __launch_bounds__(THREADS) hamming_top2_kernel(const HammingPara
             tma_load_1d(raw[s & 1], stage_src(s), bytes, &mbar[s & 1]);
         }
     };
+    auto flush_cols = [&](int s) {  // threads 0..TS-1: column minima of stage s -> global
+        if (tid < stage_rows(s)) {
+            uint32_t v = KEY_NONE;
+            for (int w = 0; w < n_active_warps; ++w) v = min(v, colmin_s[s & 1][w][tid]);
+            atomicMin(p.col_keys + t_row0 + tb + s * TS + tid, v);
+        }
+    };
     if (tid == 0) {
         issue_stage(0);
         if (n_stage > 1) issue_stage(1);
     }
 
-    // ---- query descriptors -> registers (held for the whole sweep) ----
-    uint32_t q[R][W];
-    uint32_t b1[R], b2[R], colbias[R];
-    int qrow[R];
+    // ---- query descriptors -> registers, prefix form (held for the whole sweep) ----
+    // A lane past the last row of a partial slab mirrors row nq-1: its keys duplicate a real
+    // lane's, so the column minima need no masking; only its row result is not written.
+    const int warp_row0 = qt0 + (tid & ~31);
+    int nr_w = 0;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
+    for (int r = 0; r < RMAX; ++r)
+        if (warp_row0 + r * THREADS < nq) nr_w = r + 1;
+    uint32_t q[RMAX][W];
+    uint32_t b1[RMAX], b2[RMAX], colbias[RMAX];
+    int qrow[RMAX];
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
         qrow[r] = qt0 + tid + r * THREADS;
         b1[r] = KEY_NONE;
         b2[r] = KEY_NONE;
-        if (qrow[r] < nq) {
-            load_desc_global(p.q + static_cast<size_t>(q_row0 + qrow[r]) * p.q_stride, p.desc_bytes, q[r]);
-            colbias[r] = static_cast<uint32_t>(qrow[r]);
+        const int src_row = min(qrow[r], nq - 1);
+        colbias[r] = static_cast<uint32_t>(src_row);
+        if (r < nr_w) {
+            load_desc_global(p.q + static_cast<size_t>(q_row0 + src_row) * p.q_stride, p.desc_bytes, q[r]);
+            to_prefix_form(q[r]);
         } else {
 #pragma unroll
             for (int k = 0; k < W; ++k) q[r][k] = 0;
-            colbias[r] = KEY_NONE;
         }
     }
 
@@ -173,19 +337,13 @@ __global__ void __launch_bounds__(THREADS) hamming_top2_kernel(const HammingPara
             mbar_wait(&mbar[b], (phase >> b) & 1u);
             phase ^= 1u << b;
         }
-        // flush the column minima of stage s-2 (same buffer), then re-arm them
-        if (COL && tid < TS) {
-            if (s >= 2) {
-                const uint32_t v = colmin_s[b][tid];
-                if (v != KEY_NONE) atomicMin(p.col_keys + t_row0 + tb + (s - 2) * TS + tid, v);
-            }
-            colmin_s[b][tid] = KEY_NONE;
-        }
-        // ---- re-align raw rows (any stride) to 64-byte rows ----
+        // flush the column minima of stage s-2 (same buffer) before this stage overwrites them
+        if (COL && s >= 2) flush_cols(s - 2);
+        // ---- re-align raw rows (any stride) to 64-byte rows in prefix form ----
         {
             const uint32_t *raw32 = reinterpret_cast<const uint32_t *>(raw[b]);
             const uint8_t *src = stage_src(s);
-            for (int i = tid; i < TS * W; i += THREADS) {
+            for (int i = tid; i < TS * W; i += THREADS) {  // 16 consecutive lanes = one row
                 const int r = i >> 4, k = i & 15;
                 uint32_t v = 0;
                 if (r < trows) {
@@ -197,59 +355,40 @@ __global__ void __launch_bounds__(THREADS) hamming_top2_kernel(const HammingPara
                     for (int bb = 0; bb < 4; ++bb)
                         if (4 * k + bb < p.desc_bytes) v |= static_cast<uint32_t>(__ldg(g + bb)) << (8 * bb);
                 }
-                tile[b][i] = v;
+                uint32_t pre = v;  // inclusive XOR scan over the 16 words of the row
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, pre, o, 16);
+                    if (k >= o) pre ^= up;
+                }
+                tile[b][i] = (k >= 2 && k <= 14 && !(k & 1)) ? pre : v;
             }
         }
         __syncthreads();  // tile[b] complete; raw[b] and tile[b^1] are free again
         if (tid == 0 && s + 2 < n_stage) issue_stage(s + 2);
 
         // ---- sweep: every lane reads the same train row (broadcast LDS.128) ----
-        const uint32_t jbase = (static_cast<uint32_t>(p.t_index_base + tb + s * TS));
-        const uint4 *tl = reinterpret_cast<const uint4 *>(tile[b]);
-#pragma unroll 2
-        for (int j = 0; j < rows; ++j) {
-            const uint4 t0 = tl[4 * j + 0], t1 = tl[4 * j + 1], t2 = tl[4 * j + 2], t3 = tl[4 * j + 3];
-            uint32_t ck = KEY_NONE;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint32_t d =
-                    (((__popc(q[r][0] ^ t0.x) + __popc(q[r][1] ^ t0.y)) + (__popc(q[r][2] ^ t0.z) + __popc(q[r][3] ^ t0.w))) +
-                     ((__popc(q[r][4] ^ t1.x) + __popc(q[r][5] ^ t1.y)) + (__popc(q[r][6] ^ t1.z) + __popc(q[r][7] ^ t1.w)))) +
-                    (((__popc(q[r][8] ^ t2.x) + __popc(q[r][9] ^ t2.y)) + (__popc(q[r][10] ^ t2.z) + __popc(q[r][11] ^ t2.w))) +
-                     ((__popc(q[r][12] ^ t3.x) + __popc(q[r][13] ^ t3.y)) + (__popc(q[r][14] ^ t3.z) + __popc(q[r][15] ^ t3.w))));
-                const uint32_t dk = d << KEY_IDX_BITS;
-                const uint32_t key = dk + jbase + j;
-                const uint32_t hi = max(b1[r], key);
-                b1[r] = min(b1[r], key);
-                b2[r] = min(b2[r], hi);
-                if (COL) ck = min(ck, dk | colbias[r]);
-            }
-            if (COL) {
-                const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, ck);
-                if (lane == 0 && m != KEY_NONE) atomicMin(&colmin_s[b][j], m);
-            }
-        }
+        const uint32_t jbase = static_cast<uint32_t>(p.t_index_base + tb + s * TS);
+        sweep_dispatch<RMAX, RMAX, COL, TOP2, CS>(nr_w, reinterpret_cast<const uint4 *>(tile[b]), rows, jbase, q, b1,
+                                                  b2, colbias, COL ? colmin_s[b][warp] : nullptr, lane);
     }
 
     if (COL) {
         __syncthreads();
         // stages n_stage-2 and n_stage-1 still sit in shared memory
-        for (int s = max(0, n_stage - 2); s < n_stage; ++s) {
-            if (tid < stage_rows(s)) {
-                const uint32_t v = colmin_s[s & 1][tid];
-                if (v != KEY_NONE) atomicMin(p.col_keys + t_row0 + tb + s * TS + tid, v);
-            }
-        }
+        for (int s = max(0, n_stage - 2); s < n_stage; ++s) flush_cols(s);
     }
 
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
+    for (int r = 0; r < RMAX; ++r) {
         if (qrow[r] < nq) {
             uint2 *g = p.row_keys + q_row0 + qrow[r];
             if (gridDim.y == 1)
                 *g = make_uint2(b1[r], b2[r]);
-            else
+            else if (TOP2)
                 merge_row_keys(g, b1[r], b2[r]);
+            else
+                atomicMin(&g->x, b1[r]);  // second key stays KEY_NONE (pre-set)
         }
     }
 }
@@ -315,19 +454,67 @@ __global__ void ratio_test_kernel(const uint2 *__restrict__ row_keys, int nq, in
 
 int gcd(int a, int b) { return b == 0 ? a : gcd(b, a % b); }
 
-template <int R, int THREADS>
-int launch_hamming(const HammingParams &p, dim3 grid, cudaStream_t stream)
+template <int THREADS, int RMAX, int CS>
+int launch_hamming(const HammingParams &p, dim3 grid, bool top2, cudaStream_t stream)
 {
-    if (p.col_keys)
-        hamming_top2_kernel<R, THREADS, true><<<grid, THREADS, 0, stream>>>(p);
-    else
-        hamming_top2_kernel<R, THREADS, false><<<grid, THREADS, 0, stream>>>(p);
+    if (p.col_keys) {
+        if (top2)
+            hamming_top2_kernel<THREADS, RMAX, true, true, CS><<<grid, THREADS, 0, stream>>>(p);
+        else
+            hamming_top2_kernel<THREADS, RMAX, true, false, CS><<<grid, THREADS, 0, stream>>>(p);
+    } else {
+        if (top2)
+            hamming_top2_kernel<THREADS, RMAX, false, true, CS><<<grid, THREADS, 0, stream>>>(p);
+        else
+            hamming_top2_kernel<THREADS, RMAX, false, false, CS><<<grid, THREADS, 0, stream>>>(p);
+    }
     return launch_status();
 }
 
+// Shipping configuration (scripts/tune_matcher.py sweep on B200): 2 query rows per
+// thread, 9 full adders per descriptor pair.  -DSLAMFE_TUNING builds every variant and lets
+// SLAMFE_HAMMING_R / SLAMFE_HAMMING_CS pick one at run time (development only).
+constexpr int kRows = 2;
+constexpr int kAdders = 9;
+
+#ifdef SLAMFE_TUNING
+int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+template <int RMAX>
+int launch_big_cs(const HammingParams &p, dim3 grid, int cs, bool top2, cudaStream_t stream)
+{
+    switch (cs) {
+        case 7: return launch_hamming<256, RMAX, 7>(p, grid, top2, stream);
+        case 8: return launch_hamming<256, RMAX, 8>(p, grid, top2, stream);
+        case 10: return launch_hamming<256, RMAX, 10>(p, grid, top2, stream);
+        default: return launch_hamming<256, RMAX, 9>(p, grid, top2, stream);
+    }
+}
+int big_rows() { const int r = env_int("SLAMFE_HAMMING_R", kRows); return r < 2 ? 2 : r > 4 ? 4 : r; }
+int launch_big(const HammingParams &p, dim3 grid, bool top2, cudaStream_t stream)
+{
+    const int cs = env_int("SLAMFE_HAMMING_CS", kAdders);
+    switch (big_rows()) {
+        case 3: return launch_big_cs<3>(p, grid, cs, top2, stream);
+        case 4: return launch_big_cs<4>(p, grid, cs, top2, stream);
+        default: return launch_big_cs<2>(p, grid, cs, top2, stream);
+    }
+}
+#else
+int big_rows() { return kRows; }
+int launch_big(const HammingParams &p, dim3 grid, bool top2, cudaStream_t stream)
+{
+    return launch_hamming<256, kRows, kAdders>(p, grid, top2, stream);
+}
+#endif
+
 // Pick the CTA shape and the train slicing so that the grid fills the SMs.
 int run_hamming(HammingParams p, int n_problems, int max_nq, int max_nt, int64_t q_rows_total, int64_t t_rows_total,
-                cudaStream_t stream)
+                int flags, cudaStream_t stream)
 {
     if (n_problems <= 0 || q_rows_total <= 0) return 0;
     SLAMFE_CUDA_OK(cudaMemsetAsync(p.row_keys, 0xFF, sizeof(uint2) * q_rows_total, stream));
@@ -335,6 +522,7 @@ int run_hamming(HammingParams p, int n_problems, int max_nq, int max_nt, int64_t
         SLAMFE_CUDA_OK(cudaMemsetAsync(p.col_keys, 0xFF, sizeof(uint32_t) * t_rows_total, stream));
     if (max_nq <= 0 || max_nt <= 0) return 0;
     p.tma_quantum = 16 / gcd(p.t_stride, 16);
+    const bool top2 = !(flags & SLAMFE_MATCH_BEST_ONLY);
 
     const int sms = sm_count();
     const int stages_total = (max_nt + TS - 1) / TS;
@@ -348,18 +536,20 @@ int run_hamming(HammingParams p, int n_problems, int max_nq, int max_nt, int64_t
         }
         return ctas * slices;
     };
+    const int tq_big = 256 * big_rows();
     int slices_big = 1, slices_small = 1;
-    const long long ctas_big = plan(2 * 256, 4, 3 * sms, slices_big);
+    const long long ctas_big = plan(tq_big, 4, 3 * sms, slices_big);
     const bool big = ctas_big >= 2LL * sms;
     if (!big) plan(128, 1, 4 * sms, slices_small);
     const int slices = big ? slices_big : slices_small;
     const int stages_per_slice = (stages_total + slices - 1) / slices;
     p.t_slice = stages_per_slice * TS;
     const int n_slices = (stages_total + stages_per_slice - 1) / stages_per_slice;
-    const int tq = big ? 512 : 128;
+    const int tq = big ? tq_big : 128;
     const dim3 grid((max_nq + tq - 1) / tq, n_slices, n_problems);
     if (grid.y > 65535u || grid.z > 65535u) return SLAMFE_ERANGE;
-    return big ? launch_hamming<2, 256>(p, grid, stream) : launch_hamming<1, 128>(p, grid, stream);
+    if (!big) return launch_hamming<128, 1, kAdders>(p, grid, top2, stream);
+    return launch_big(p, grid, top2, stream);
 }
 
 int check_desc_args(const void *q, const void *t, int q_stride, int t_stride, int desc_bytes)
@@ -378,7 +568,7 @@ using namespace slamfe;
 
 extern "C" int slamfe_hamming_top2(const uint8_t *q, int nq, int q_stride, const uint8_t *t, int nt, int t_stride,
                                    int desc_bytes, int t_index_base, uint32_t *row_keys, uint32_t *col_keys,
-                                   slamfe_stream_t stream)
+                                   int flags, slamfe_stream_t stream)
 {
     if (nq < 0 || nt < 0 || t_index_base < 0) return SLAMFE_EINVAL;
     if (nq == 0) return 0;
@@ -395,14 +585,14 @@ extern "C" int slamfe_hamming_top2(const uint8_t *q, int nq, int q_stride, const
     p.nq = nq; p.nt = nt; p.t_index_base = t_index_base;
     p.row_keys = reinterpret_cast<uint2 *>(row_keys);
     p.col_keys = col_keys;
-    return run_hamming(p, 1, nq, nt, nq, nt, static_cast<cudaStream_t>(stream));
+    return run_hamming(p, 1, nq, nt, nq, nt, flags, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int slamfe_hamming_top2_batched(const uint8_t *q, int q_stride, const int32_t *q_off, const int32_t *q_cnt,
                                            const uint8_t *t, int t_stride, const int32_t *t_off, const int32_t *t_cnt,
                                            int n_problems, int max_nq, int max_nt, int desc_bytes, uint32_t *row_keys,
                                            int64_t q_rows_total, uint32_t *col_keys, int64_t t_rows_total,
-                                           slamfe_stream_t stream)
+                                           int flags, slamfe_stream_t stream)
 {
     if (n_problems < 0 || max_nq < 0 || max_nt < 0 || q_rows_total < 0 || t_rows_total < 0) return SLAMFE_EINVAL;
     if (n_problems == 0 || q_rows_total == 0) return 0;
@@ -415,7 +605,8 @@ extern "C" int slamfe_hamming_top2_batched(const uint8_t *q, int q_stride, const
     p.q_off = q_off; p.q_cnt = q_cnt; p.t_off = t_off; p.t_cnt = t_cnt;
     p.row_keys = reinterpret_cast<uint2 *>(row_keys);
     p.col_keys = col_keys;
-    return run_hamming(p, n_problems, max_nq, max_nt, q_rows_total, t_rows_total, static_cast<cudaStream_t>(stream));
+    return run_hamming(p, n_problems, max_nq, max_nt, q_rows_total, t_rows_total, flags,
+                       static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int slamfe_unpack_keys(const uint32_t *keys, int64_t n, int32_t *idx, int32_t *dist, slamfe_stream_t stream)

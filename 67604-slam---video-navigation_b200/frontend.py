@@ -125,8 +125,17 @@ def to_device(seq: PackedSequence, device="cuda", non_blocking=True) -> DeviceSe
         seq.n_frames, int(seq.n_l.max()) if seq.n_frames else 0, int(seq.n_r.max()) if seq.n_frames else 0)
 
 
+RESULT_KEYS = ("match_t", "n_matches", "n_links", "link_src", "links", "xyz", "fwd_keys", "bwd_keys")
+
+
 class FrontEnd:
-    """Runs the four batched stages over a DeviceSequence; owns (and reuses) the output buffers."""
+    """Runs the four batched stages over a DeviceSequence; owns (and reuses) the output buffers.
+
+    run(ds)          inputs already resident in HBM, everything on the current stream;
+    run_host(seq)    host (pinned) inputs -> host (pinned) result tables: the sequence is cut into
+                     chunks of frames and the H2D copy of chunk c+1, the kernels of chunk c and
+                     the D2H copy of chunk c-1 run concurrently on three streams.
+    """
 
     def __init__(self, P=None, Q=None):
         from . import utils
@@ -134,16 +143,19 @@ class FrontEnd:
         self.Q = utils.Q if Q is None else np.asarray(Q, dtype=np.float64)
         self._out = None
         self._key = None
+        self._in = None
+        self._in_key = None
+        self._pinned_out = None
+        self._streams = None
         # kernels launched by one run(): 2 matcher launches, stereo epilogue, triangulation
         # (cudaMemsetAsync initialisation of the key tables is not counted)
         self.launches_per_run = 4
+        self.last_launches = 0
 
-    def _buffers(self, ds: DeviceSequence):
+    def _buffers(self, L, R, F, dev):
         torch = _cabi.require_cuda()
-        L, R, F = ds.desc_l.shape[0], ds.desc_r.shape[0], ds.n_frames
-        key = (L, R, F, ds.desc_l.device)
+        key = (L, R, F, dev)
         if self._key != key:
-            dev = ds.desc_l.device
             i32 = dict(dtype=torch.int32, device=dev)
             self._out = {
                 "lr_row_keys": torch.empty((L, 2), **i32), "lr_col_keys": torch.empty((R,), **i32),
@@ -157,29 +169,172 @@ class FrontEnd:
             self._key = key
         return self._out
 
-    def run(self, ds: DeviceSequence):
-        """All stages, asynchronous on the current stream.  Returns the dict of output tensors."""
-        o = self._buffers(ds)
-        F = ds.n_frames
-        if F == 0:
-            return o
-        # 1. stereo match, every frame
-        ops.hamming_top2_batched(ds.desc_l, ds.l_off, ds.desc_r, ds.r_off, F, ds.max_nl, ds.max_nr, DESC_BYTES,
-                                 q_cnt=ds.n_l, t_cnt=ds.n_r, want_cols=True,
+    # -- stages on a frame range; all tensors are views whose offsets are relative to the view --
+    @staticmethod
+    def _stereo_stages(P, Q, desc_l, desc_r, pts_l, pts_r, l_off, r_off, n_l, n_r, n, max_nl, max_nr, o):
+        """Stages 1-3 for n frames: o holds views of the output tables for the same rows/frames."""
+        # 1. stereo match, every frame (best neighbour + column minima: crossCheck needs no more)
+        ops.hamming_top2_batched(desc_l, l_off, desc_r, r_off, n, max_nl, max_nr, DESC_BYTES,
+                                 q_cnt=n_l, t_cnt=n_r, want_cols=True, best_only=True,
                                  row_keys=o["lr_row_keys"], col_keys=o["lr_col_keys"])
         # 2. crossCheck + row filter + links + features[is_valid]
-        ops.stereo_links_batched(o["lr_row_keys"], o["lr_col_keys"], ds.l_off, ds.r_off, F, ds.pts_l, ds.pts_r,
-                                 desc_left=ds.desc_l, desc_bytes=DESC_BYTES, out=o, n_l=ds.n_l, n_r=ds.n_r)
+        ops.stereo_links_batched(o["lr_row_keys"], o["lr_col_keys"], l_off, r_off, n, pts_l, pts_r,
+                                 desc_left=desc_l, desc_bytes=DESC_BYTES, out=o, n_l=n_l, n_r=n_r)
         # 3. triangulate every link
-        ops.triangulate_links(o["links"], self.P, self.Q, out=o["xyz"])
+        ops.triangulate_links(o["links"], P, Q, out=o["xyz"])
+
+    @staticmethod
+    def _pair_stage(feat_q, q_off, q_cnt, feat_t, t_off, t_cnt, n_pairs, max_links, fwd_keys, bwd_keys):
+        """Stage 4: problem p matches the filtered features of frame p (rows of feat_q) against
+        those of frame p+1 (rows of feat_t); forward rows + backward columns from one pass."""
+        ops.hamming_top2_batched(feat_q, q_off, feat_t, t_off, n_pairs, max_links, max_links, DESC_BYTES,
+                                 q_cnt=q_cnt, t_cnt=t_cnt, want_cols=True, best_only=True,
+                                 row_keys=fwd_keys, col_keys=bwd_keys)
+
+    def run(self, ds: DeviceSequence):
+        """All stages, asynchronous on the current stream.  Returns the dict of output tensors."""
+        o = self._buffers(ds.desc_l.shape[0], ds.desc_r.shape[0], ds.n_frames, ds.desc_l.device)
+        F = ds.n_frames
+        self.last_launches = 0
+        if F == 0:
+            return o
+        self._stereo_stages(self.P, self.Q, ds.desc_l, ds.desc_r, ds.pts_l, ds.pts_r, ds.l_off, ds.r_off,
+                            ds.n_l, ds.n_r, F, ds.max_nl, ds.max_nr, o)
+        self.last_launches += 3
         # 4. consecutive frames on the filtered features: problem f = (frame f, frame f+1)
         if F > 1:
             max_links = min(ds.max_nl, ds.max_nr)
-            ops.hamming_top2_batched(o["feat"], ds.l_off, o["feat"], ds.l_off[1:], F - 1, max_links, max_links,
-                                     DESC_BYTES, q_cnt=o["n_links"], t_cnt=o["n_links"][1:], want_cols=True,
-                                     row_keys=o["fwd_keys"], col_keys=o["bwd_keys"])
+            self._pair_stage(o["feat"], ds.l_off, o["n_links"], o["feat"], ds.l_off[1:], o["n_links"][1:],
+                             F - 1, max_links, o["fwd_keys"], o["bwd_keys"])
+            self.last_launches += 1
         return o
 
+    # -- host in, host out ---------------------------------------------------------------------
+    def _input_buffers(self, seq: PackedSequence, dev):
+        torch = _cabi.require_cuda()
+        L, R, F = seq.desc_l.shape[0], seq.desc_r.shape[0], seq.n_frames
+        key = (L, R, F, dev)
+        if self._in_key != key:
+            self._in = {
+                "desc_l": torch.empty((L, DESC_BYTES), dtype=torch.uint8, device=dev),
+                "desc_r": torch.empty((R, DESC_BYTES), dtype=torch.uint8, device=dev),
+                "pts_l": torch.empty((L, 2), dtype=torch.float32, device=dev),
+                "pts_r": torch.empty((R, 2), dtype=torch.float32, device=dev),
+            }
+            self._in_key = key
+            self._pinned_out = None
+        return self._in
+
+    def run_host(self, seq: PackedSequence, chunk_frames=288, device="cuda", keys=RESULT_KEYS):
+        """Pinned host inputs -> pinned host result tables, copies overlapped with the kernels.
+
+        Returns (dict of numpy views of the pinned result tables, h2d_bytes, d2h_bytes).  The call
+        returns after the last table has landed in host memory."""
+        torch = _cabi.require_cuda()
+        if seq.tensors is None:
+            raise ValueError("run_host needs a pinned PackedSequence (pack_sequence(..., pin=True))")
+        dev = torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        F = seq.n_frames
+        L, R = seq.desc_l.shape[0], seq.desc_r.shape[0]
+        din = self._input_buffers(seq, dev)
+        o = self._buffers(L, R, F, dev)
+        if self._pinned_out is None:
+            self._pinned_out = {k: torch.empty(o[k].shape, dtype=o[k].dtype, pin_memory=True) for k in RESULT_KEYS}
+        hout = self._pinned_out
+        if self._streams is None:
+            self._streams = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
+        s_in, s_cmp, s_out = self._streams
+        self.last_launches = 0
+        if F == 0:
+            return {k: hout[k].numpy() for k in keys}, 0, 0
+        l_off, r_off = seq.l_off.astype(np.int64), seq.r_off.astype(np.int64)
+        max_nl, max_nr = int(seq.n_l.max()), int(seq.n_r.max())
+        max_links = min(max_nl, max_nr)
+        bounds = list(range(0, F, max(1, int(chunk_frames)))) + [F]
+        # chunk-relative offset tables for every chunk, one small upload
+        parts, index, pos = [], [], 0
+        for c in range(len(bounds) - 1):
+            f0, f1 = bounds[c], bounds[c + 1]
+            p0 = max(f0 - 1, 0)
+            tabs = (l_off[f0:f1 + 1] - l_off[f0], r_off[f0:f1 + 1] - r_off[f0],
+                    l_off[p0:f1 - 1] - l_off[p0], l_off[p0 + 1:f1] - l_off[p0 + 1])
+            loc = []
+            for t in tabs:
+                loc.append((pos, pos + len(t)))
+                parts.append(t)
+                pos += len(t)
+            index.append(loc)
+        small = np.concatenate(parts + [seq.n_l.astype(np.int64), seq.n_r.astype(np.int64)]).astype(np.int32)
+        small_pin = torch.from_numpy(small).pin_memory()
+        cur = torch.cuda.current_stream(dev)
+        for s in (s_in, s_cmp, s_out):
+            s.wait_stream(cur)
+        h2d = d2h = 0
+        with torch.cuda.stream(s_in):
+            small_dev = small_pin.to(dev, non_blocking=True)
+            h2d += small_pin.numel() * 4
+        n_l_dev, n_r_dev = small_dev[pos:pos + F], small_dev[pos + F:pos + 2 * F]
+        ev_done = []
+        for c in range(len(bounds) - 1):
+            f0, f1 = bounds[c], bounds[c + 1]
+            n = f1 - f0
+            a, b = int(l_off[f0]), int(l_off[f1])
+            ra, rb = int(r_off[f0]), int(r_off[f1])
+            with torch.cuda.stream(s_in):
+                for k, lo, hi in (("desc_l", a, b), ("pts_l", a, b), ("desc_r", ra, rb), ("pts_r", ra, rb)):
+                    src = seq.tensors[k][lo:hi]
+                    din[k][lo:hi].copy_(src, non_blocking=True)
+                    h2d += src.numel() * src.element_size()
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            (l0, l1), (r0, r1), (q0, q1), (t0, t1) = index[c]
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_in)
+                view = {k: o[k][a:b] for k in ("lr_row_keys", "match_t", "link_src", "links", "feat", "xyz")}
+                view["lr_col_keys"] = o["lr_col_keys"][ra:rb]
+                view["n_matches"], view["n_links"] = o["n_matches"][f0:f1], o["n_links"][f0:f1]
+                self._stereo_stages(self.P, self.Q, din["desc_l"][a:b], din["desc_r"][ra:rb], din["pts_l"][a:b],
+                                    din["pts_r"][ra:rb], small_dev[l0:l1], small_dev[r0:r1], n_l_dev[f0:f1],
+                                    n_r_dev[f0:f1], n, max_nl, max_nr, view)
+                self.last_launches += 3
+                p0 = max(f0 - 1, 0)
+                n_pairs = f1 - 1 - p0
+                if n_pairs > 0:
+                    qa, qb = int(l_off[p0]), int(l_off[f1 - 1])   # rows of frames p0 .. f1-2
+                    ta = int(l_off[p0 + 1])                         # rows of frames p0+1 .. f1-1
+                    self._pair_stage(o["feat"][qa:qb], small_dev[q0:q1], o["n_links"][p0:f1 - 1],
+                                     o["feat"][ta:b], small_dev[t0:t1], o["n_links"][p0 + 1:f1],
+                                     n_pairs, max_links, o["fwd_keys"][qa:qb], o["bwd_keys"][ta:b])
+                    self.last_launches += 1
+                if f1 == F:  # the last frame has no successor, frame 0 no predecessor
+                    o["fwd_keys"][int(l_off[F - 1]):].fill_(-1)
+                if f0 == 0:
+                    o["bwd_keys"][:int(l_off[1])].fill_(-1)
+                ev_cmp = torch.cuda.Event()
+                ev_cmp.record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp)
+                # complete after this chunk: per-row tables of its frames, forward keys up to f1-2
+                fa = int(l_off[max(f0 - 1, 0)])
+                fb = b if f1 == F else int(l_off[f1 - 1])
+                for k in keys:
+                    if k in ("n_matches", "n_links"):
+                        lo, hi = f0, f1
+                    elif k == "fwd_keys":
+                        lo, hi = fa, fb
+                    else:
+                        lo, hi = a, b
+                    if hi > lo:
+                        hout[k][lo:hi].copy_(o[k][lo:hi], non_blocking=True)
+                        d2h += (hi - lo) * o[k][0:1].numel() * o[k].element_size()
+                ev = torch.cuda.Event()
+                ev.record(s_out)
+                ev_done.append(ev)
+        ev_done[-1].synchronize()
+        cur.wait_stream(s_out)
+        return {k: hout[k].numpy() for k in keys}, int(h2d), int(d2h)
 
 
 def descriptor_pairs(n_l, n_r, n_links=None) -> int:
@@ -192,8 +347,7 @@ def descriptor_pairs(n_l, n_r, n_links=None) -> int:
     return total
 
 
-def results_to_host(o, keys=("match_t", "n_matches", "n_links", "link_src", "links", "xyz", "fwd_keys", "bwd_keys"),
-                    pinned=None):
+def results_to_host(o, keys=RESULT_KEYS, pinned=None):
     """Copy the result tables to (pinned) host memory; returns (dict of numpy arrays, bytes, pinned)."""
     torch = _cabi.require_cuda()
     if pinned is None:

@@ -114,7 +114,7 @@ class Matcher:
         q, t = chk
         qd = self._st.to_device("q", q)
         td = self._st.to_device("t", t)
-        row_keys, col_keys = ops.hamming_top2(qd, td, want_cols=self.crossCheck)
+        row_keys, col_keys = ops.hamming_top2(qd, td, want_cols=self.crossCheck, best_only=True)
         if self.crossCheck:
             mt, md = ops.cross_check(row_keys, col_keys)
             import torch

@@ -25,12 +25,14 @@ def _desc_tensor(d):
     return d
 
 
-def hamming_top2(q, t, desc_bytes=None, want_cols=False, t_index_base=0):
+def hamming_top2(q, t, desc_bytes=None, want_cols=False, t_index_base=0, best_only=False):
     """Top-2 Hamming neighbours of every row of q among the rows of t.
 
     q, t: (N, stride) uint8 CUDA tensors (stride 61 = cv2 layout, or 64-byte padded rows);
     desc_bytes defaults to the row width.  Returns (row_keys (Nq, 2) int32-viewed-uint32,
     col_keys (Nt,) or None).  Key = distance << 22 | index; see include/slamfe.h.
+    best_only=True skips the second neighbour (row_keys[:, 1] = KEY_NONE): enough for .match()
+    and crossCheck, and cheaper.
     """
     torch = _torch()
     q, t = _desc_tensor(q), _desc_tensor(t)
@@ -41,12 +43,13 @@ def hamming_top2(q, t, desc_bytes=None, want_cols=False, t_index_base=0):
     with torch.cuda.device(q.device):
         check(load_library().slamfe_hamming_top2(
             ptr(q), nq, q.stride(0), ptr(t), nt, t.stride(0) if nt else max(desc_bytes, 1), desc_bytes, t_index_base,
-            ptr(row_keys), ptr(col_keys), stream_handle()), "slamfe_hamming_top2")
+            ptr(row_keys), ptr(col_keys), _cabi.MATCH_BEST_ONLY if best_only else 0, stream_handle()),
+            "slamfe_hamming_top2")
     return row_keys, col_keys
 
 
 def hamming_top2_batched(q, q_off, t, t_off, n_problems, max_nq, max_nt, desc_bytes,
-                         q_cnt=None, t_cnt=None, want_cols=False, row_keys=None, col_keys=None):
+                         q_cnt=None, t_cnt=None, want_cols=False, row_keys=None, col_keys=None, best_only=False):
     """Ragged batch of matching problems in one launch (slamfe_hamming_top2_batched).
 
     q_off / t_off / q_cnt / t_cnt are int32 CUDA tensors (see include/slamfe.h); keys are indexed
@@ -62,7 +65,8 @@ def hamming_top2_batched(q, q_off, t, t_off, n_problems, max_nq, max_nt, desc_by
         check(load_library().slamfe_hamming_top2_batched(
             ptr(q), q.stride(0), ptr(q_off), ptr(q_cnt), ptr(t), t.stride(0), ptr(t_off), ptr(t_cnt),
             n_problems, max_nq, max_nt, desc_bytes,
-            ptr(row_keys), q.shape[0], ptr(col_keys) if want_cols else 0, t.shape[0], stream_handle()),
+            ptr(row_keys), q.shape[0], ptr(col_keys) if want_cols else 0, t.shape[0],
+            _cabi.MATCH_BEST_ONLY if best_only else 0, stream_handle()),
             "slamfe_hamming_top2_batched")
     return row_keys, (col_keys if want_cols else None)
 

@@ -41,6 +41,9 @@ typedef void *slamfe_stream_t;
 #define SLAMFE_KEY_NONE 0xFFFFFFFFu
 #define SLAMFE_MAX_DESC_BYTES 64
 
+/* matcher flags */
+#define SLAMFE_MATCH_BEST_ONLY 1 /* keep only the best neighbour (.match / crossCheck); row_keys[:,1] = KEY_NONE */
+
 #define SLAMFE_EINVAL (-1)   /* bad argument (null pointer, negative size, stride < desc_bytes ...) */
 #define SLAMFE_ERANGE (-2)   /* size exceeds what the key encoding / grid can address */
 
@@ -66,11 +69,13 @@ const char *slamfe_error_string(int code);
  *                 i.e. the result of matching t against q, from the same single pass.  This is
  *                 what crossCheck (matching.py:22,44) and the backward match (database.py:55)
  *                 need; cv2 spends a second full pass on it.
+ *   flags         0, or SLAMFE_MATCH_BEST_ONLY when the second neighbour is not needed
+ *                 (.match() and crossCheck; knnMatch(k=2) / the ratio test need 0).
  */
 int slamfe_hamming_top2(const uint8_t *q, int nq, int q_stride,
                         const uint8_t *t, int nt, int t_stride,
                         int desc_bytes, int t_index_base,
-                        uint32_t *row_keys, uint32_t *col_keys, slamfe_stream_t stream);
+                        uint32_t *row_keys, uint32_t *col_keys, int flags, slamfe_stream_t stream);
 
 /*
  * Ragged batch of independent (query set, train set) problems in ONE launch — one problem per
@@ -86,7 +91,7 @@ int slamfe_hamming_top2_batched(const uint8_t *q, int q_stride, const int32_t *q
                                 const uint8_t *t, int t_stride, const int32_t *t_off, const int32_t *t_cnt,
                                 int n_problems, int max_nq, int max_nt, int desc_bytes,
                                 uint32_t *row_keys, int64_t q_rows_total,
-                                uint32_t *col_keys, int64_t t_rows_total, slamfe_stream_t stream);
+                                uint32_t *col_keys, int64_t t_rows_total, int flags, slamfe_stream_t stream);
 
 /* keys (n,) -> idx (n,) int32 (-1 for NONE), dist (n,) int32 (-1 for NONE). */
 int slamfe_unpack_keys(const uint32_t *keys, int64_t n, int32_t *idx, int32_t *dist, slamfe_stream_t stream);

@@ -53,12 +53,12 @@ def test_argument_errors_do_not_need_a_gpu(slamfe):
     buf = ctypes.create_string_buffer(1024)
     p = ctypes.addressof(buf)
     # negative sizes / null outputs / bad strides are rejected before any CUDA call
-    assert lib.slamfe_hamming_top2(p, -1, 61, p, 4, 61, 61, 0, p, None, None) == EINVAL
-    assert lib.slamfe_hamming_top2(p, 4, 61, p, 4, 61, 61, 0, None, None, None) == EINVAL
-    assert lib.slamfe_hamming_top2(p, 4, 61, p, 4, 61, 65, 0, p, None, None) == EINVAL
-    assert lib.slamfe_hamming_top2(p, 4, 32, p, 4, 61, 61, 0, p, None, None) == EINVAL
-    assert lib.slamfe_hamming_top2(p, 4, 61, p, 1 << 23, 61, 61, 0, p, None, None) == ERANGE
-    assert lib.slamfe_hamming_top2(p, 0, 61, p, 4, 61, 61, 0, p, None, None) == 0  # empty query: no-op
+    assert lib.slamfe_hamming_top2(p, -1, 61, p, 4, 61, 61, 0, p, None, 0, None) == EINVAL
+    assert lib.slamfe_hamming_top2(p, 4, 61, p, 4, 61, 61, 0, None, None, 0, None) == EINVAL
+    assert lib.slamfe_hamming_top2(p, 4, 61, p, 4, 61, 65, 0, p, None, 0, None) == EINVAL
+    assert lib.slamfe_hamming_top2(p, 4, 32, p, 4, 61, 61, 0, p, None, 0, None) == EINVAL
+    assert lib.slamfe_hamming_top2(p, 4, 61, p, 1 << 23, 61, 61, 0, p, None, 0, None) == ERANGE
+    assert lib.slamfe_hamming_top2(p, 0, 61, p, 4, 61, 61, 0, p, None, 0, None) == 0  # empty query: no-op
     assert lib.slamfe_unpack_keys(None, 5, p, p, None) == EINVAL
     assert lib.slamfe_unpack_keys(p, 0, p, p, None) == 0
     assert lib.slamfe_merge_top2(p, 2, -3, p, None) == EINVAL
@@ -69,4 +69,4 @@ def test_argument_errors_do_not_need_a_gpu(slamfe):
     # rows 1-2 of P and Q differ: the links entry point refuses (general DLT must be used)
     assert lib.slamfe_triangulate_links_f64(p, 4, P, Q, p, None) == EINVAL
     assert lib.slamfe_ransac_score(None, None, 4, p, p, p, None, 5, 1, 5, None, None, None, p, p, p, p, None) == EINVAL
-    assert lib.slamfe_peak_kernel(9, 0, 1, 1, p, None, None) == EINVAL
+    assert lib.slamfe_peak_kernel(9, 0, 1, 1, p, None, 0, None) == EINVAL

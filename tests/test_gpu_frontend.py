@@ -50,8 +50,9 @@ def test_sequence_pipeline_vs_oracle(slamfe, oracle):
     for f in range(len(frames) - 1):
         lo, k = seq.l_off[f], len(feats[f])
         fi, fd = ops.keys_to_numpy(host["fwd_keys"][lo:lo + k])
-        oi, od = oracle.knn2(feats[f], feats[f + 1])
-        assert np.array_equal(fi, oi) and np.array_equal(fd, od)
+        oi, od = oracle.match(feats[f], feats[f + 1])  # the pipeline keeps the best neighbour only
+        assert np.array_equal(fi[:, 0], oi) and np.array_equal(fd[:, 0], od)
+        assert (fi[:, 1] == -1).all()
         lo1, k1 = seq.l_off[f + 1], len(feats[f + 1])
         obi, obd = oracle.match(feats[f + 1], feats[f])
         got_b = ops.keys_to_numpy(host["bwd_keys"][lo1:lo1 + k1])
@@ -59,6 +60,31 @@ def test_sequence_pipeline_vs_oracle(slamfe, oracle):
     pairs = frontend.descriptor_pairs(seq.n_l, seq.n_r, host["n_links"])
     assert pairs == sum(len(a) * len(b) for a, b, _, _ in frames) + sum(
         len(feats[f]) * len(feats[f + 1]) for f in range(len(frames) - 1))
+
+
+@pytest.mark.parametrize("chunk", [1, 2, 4, 100])
+def test_host_pipeline_equals_resident_run(slamfe, chunk):
+    """run_host (chunked, copies overlapped on three streams) must give the tables of run()."""
+    import torch
+    from slamfe import frontend
+    rng = np.random.default_rng(72)
+    frames = make_sequence(rng, [700, 900, 40, 1100, 650, 800, 500])
+    seq = frontend.pack_sequence(frames)
+    fe = frontend.FrontEnd()
+    ref, _, _ = frontend.results_to_host(fe.run(frontend.to_device(seq)))
+    ref = {k: v.copy() for k, v in ref.items()}
+    fe2 = frontend.FrontEnd()
+    for _ in range(2):  # second pass reuses every buffer
+        got, h2d, d2h = fe2.run_host(seq, chunk_frames=chunk)
+        assert h2d >= seq.h2d_bytes() and d2h > 0
+        for f in range(seq.n_frames):
+            lo, k = seq.l_off[f], ref["n_links"][f]
+            assert got["n_links"][f] == k and got["n_matches"][f] == ref["n_matches"][f]
+            n = seq.n_l[f]
+            assert np.array_equal(got["match_t"][lo:lo + n], ref["match_t"][lo:lo + n])
+            for key in ("link_src", "links", "xyz", "fwd_keys", "bwd_keys"):
+                assert np.array_equal(got[key][lo:lo + k], ref[key][lo:lo + k]), (key, f)
+    torch.cuda.synchronize()
 
 
 def test_patch_rebinds_reference_style_modules(slamfe):

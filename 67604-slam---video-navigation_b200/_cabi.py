@@ -27,6 +27,10 @@ _SIGNATURES = {
                                             c_void_p, c_int, c_void_p, c_void_p,
                                             c_int, c_int, c_int, c_int,
                                             c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]),
+    "slamfe_hamming_top2_pairs": (c_int, [c_void_p, c_int, c_void_p, c_void_p,
+                                          c_void_p, c_int, c_void_p, c_void_p,
+                                          c_void_p, c_int, c_int, c_int, c_int,
+                                          c_void_p, c_int64, c_int, c_void_p]),
     "slamfe_unpack_keys": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "slamfe_merge_top2": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "slamfe_cross_check": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),

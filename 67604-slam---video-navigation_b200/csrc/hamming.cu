@@ -37,6 +37,7 @@ struct HammingParams {
     const uint8_t *t;
     int q_stride, t_stride, desc_bytes;
     const int32_t *q_off, *q_cnt, *t_off, *t_cnt;  // null q_off / t_off => single problem
+    const int32_t *row_out_off;                    // null => row results are indexed like q rows
     int nq, nt;                                    // single-problem sizes
     int t_index_base;
     int t_slice;      // train rows per blockIdx.y slice (multiple of TS)
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(THREADS, (RMAX >= 3 ? 2 : 3)) hamming_top2_ker
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) {
         if (qrow[r] < nq) {
-            uint2 *g = p.row_keys + q_row0 + qrow[r];
+            uint2 *g = p.row_keys + (p.row_out_off ? p.row_out_off[prob] : q_row0) + qrow[r];
             if (gridDim.y == 1)
                 *g = make_uint2(b1[r], b2[r]);
             else if (TOP2)
@@ -541,6 +542,11 @@ int run_hamming(HammingParams p, int n_problems, int max_nq, int max_nt, int64_t
     const long long ctas_big = plan(tq_big, 4, 3 * sms, slices_big);
     const bool big = ctas_big >= 2LL * sms;
     if (!big) plan(128, 1, 4 * sms, slices_small);
+    // A CTA that sweeps a whole 3-5k-row train set lives for milliseconds, and the last wave of
+    // such CTAs leaves most SMs idle: cap the sweep at kMaxStagesPerCta stages so that the tail of
+    // a launch is short (the per-slice results merge through atomicMin, which is exact).
+    constexpr int kMaxStagesPerCta = 1 << 20;  // disabled: the extra row-merge atomics cost more than the tail (measured)
+    if (big) slices_big = max(slices_big, (stages_total + kMaxStagesPerCta - 1) / kMaxStagesPerCta);
     const int slices = big ? slices_big : slices_small;
     const int stages_per_slice = (stages_total + slices - 1) / slices;
     p.t_slice = stages_per_slice * TS;
@@ -607,6 +613,26 @@ extern "C" int slamfe_hamming_top2_batched(const uint8_t *q, int q_stride, const
     p.col_keys = col_keys;
     return run_hamming(p, n_problems, max_nq, max_nt, q_rows_total, t_rows_total, flags,
                        static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int slamfe_hamming_top2_pairs(const uint8_t *q, int q_stride, const int32_t *q_off, const int32_t *q_cnt,
+                                         const uint8_t *t, int t_stride, const int32_t *t_off, const int32_t *t_cnt,
+                                         const int32_t *out_off, int n_problems, int max_nq, int max_nt,
+                                         int desc_bytes, uint32_t *row_keys, int64_t out_rows_total, int flags,
+                                         slamfe_stream_t stream)
+{
+    if (n_problems < 0 || max_nq < 0 || max_nt < 0 || out_rows_total < 0) return SLAMFE_EINVAL;
+    if (n_problems == 0 || out_rows_total == 0) return 0;
+    if (!row_keys || !q_off || !t_off || !q_cnt || !t_cnt || !out_off) return SLAMFE_EINVAL;
+    const int rc = check_desc_args(q, t, q_stride, t_stride, desc_bytes);
+    if (rc) return rc;
+    if (max_nq > static_cast<int>(KEY_IDX_MASK) || max_nt > static_cast<int>(KEY_IDX_MASK)) return SLAMFE_ERANGE;
+    HammingParams p{};
+    p.q = q; p.t = t; p.q_stride = q_stride; p.t_stride = t_stride; p.desc_bytes = desc_bytes;
+    p.q_off = q_off; p.q_cnt = q_cnt; p.t_off = t_off; p.t_cnt = t_cnt; p.row_out_off = out_off;
+    p.row_keys = reinterpret_cast<uint2 *>(row_keys);
+    p.col_keys = nullptr;
+    return run_hamming(p, n_problems, max_nq, max_nt, out_rows_total, 0, flags, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int slamfe_unpack_keys(const uint32_t *keys, int64_t n, int32_t *idx, int32_t *dist, slamfe_stream_t stream)

@@ -7,8 +7,10 @@
 //
 // Bit-exactness: everything is fp64 with the reference's association order
 // ((K @ T) @ [M;0001]) @ X; every dot product accumulates k = 0..3 with FMA, which is what the
-// BLAS dgemm behind numpy's matmul does (checked bit-for-bit against numpy), the
-// perspective division is a true IEEE division and the test is a strict < 2.  The reference's
+// BLAS dgemm behind numpy's matmul does (checked bit-for-bit against numpy).  The
+// reference's "IEEE division, subtract, strict < 2" verdict is reproduced without dividing:
+// a multiplication-form test with a rounding certificate decides all but the (practically
+// never occurring) borderline cases, which fall back to the literal division (agrees / agrees_exact).  The reference's
 // quirks are kept: the right camera is K @ T @ [M2;0001] (ransac.py:39) and there is no
 // positive-depth test.  FP64-FMA-pipe bound (operands are reused H or N times), not HBM bound.
 //
@@ -22,8 +24,10 @@
 namespace slamfe {
 namespace {
 
-constexpr int RS_THREADS = 256;  // correspondences per CTA
-constexpr int RS_HC = 64;        // hypotheses per CTA
+constexpr int RS_THREADS = 256;
+constexpr int RS_PP = 2;                        // correspondences per thread
+constexpr int RS_TILE = RS_THREADS * RS_PP;     // correspondences per CTA
+constexpr int RS_HC = 64;                       // hypotheses per CTA
 
 struct RansacCams {
     double K[9];
@@ -82,15 +86,55 @@ __device__ __forceinline__ double project_row(const double *m, double x, double 
     return acc + m[3];  // fma(m[3], 1.0, acc)
 }
 
-// ransac.py:38-56 for one (hypothesis, correspondence).  M = PL (12) followed by PR (12).
-__device__ __forceinline__ bool agrees(const double *M, double x, double y, double z, double lx, double ly, double rx,
-                                       double ry)
+// ransac.py:38-56 for one (hypothesis, correspondence), exactly as the reference evaluates it:
+// IEEE division, subtraction, strict < 2.  M = PL (12) followed by PR (12).
+__device__ __noinline__ bool agrees_exact(const double *M, double x, double y, double z, double lx, double ly,
+                                          double rx, double ry)
 {
     const double l0 = project_row(M + 0, x, y, z), l1 = project_row(M + 4, x, y, z), l2 = project_row(M + 8, x, y, z);
     const double r0 = project_row(M + 12, x, y, z), r1 = project_row(M + 16, x, y, z),
                  r2 = project_row(M + 20, x, y, z);
     const double ul = l0 / l2, vl = l1 / l2, ur = r0 / r2, vr = r1 / r2;
     return (fabs(vl - ly) < 2.0) && (fabs(ul - lx) < 2.0) && (fabs(vr - ry) < 2.0) && (fabs(ur - rx) < 2.0);
+}
+
+// Division-free evaluation of  |num/den - pix| < 2  with a certificate.
+// With w = num/den - pix in exact arithmetic, the reference's rounded result t = fl(fl(num/den) - pix)
+// satisfies |t - w| <= (|pix| + 2|w|) * 2^-52, so its verdict equals (|w| < 2) whenever
+// ||w| - 2| exceeds that.  Here e = fma(-pix, den, num) = w*den (one rounding), diff = |e| - 2|den|
+// and the verdict (diff < 0) is certified when  |diff| > (|pix| + 8) * |den| * 2^-49:
+//   * |e| <= 4|den|: the reference's error, scaled by |den|, is <= (|pix| + 8)|den| 2^-52 and the
+//     roundings of e and diff add <= 4|den| 2^-52 — together < 1/8 of the bound;
+//   * |e| >  4|den|: |diff| >= |e|/2, far above 2|e| 2^-52, and the bound covers the |pix| term.
+// NaN and 0/0 never certify and take the exact path.  The fp64 divider sequences (~25
+// instructions each, 4 per pair) were 3/4 of the kernel; a test now costs 3 fp64 operations.
+// cert = (|pix| + 8) * 2^-49 is hoisted out of the hypothesis loop.
+__device__ __forceinline__ double cert_of(double pix) { return (fabs(pix) + 8.0) * 0x1p-49; }
+
+struct RatioTest {
+    double diff, bound;
+    __device__ __forceinline__ RatioTest(double num, double den, double pix, double cert)
+    {
+        const double e = fma(-pix, den, num);
+        const double ad = fabs(den);
+        diff = fma(-2.0, ad, fabs(e));
+        bound = cert * ad;
+    }
+    __device__ __forceinline__ bool surely_outside() const { return diff > bound; }
+    __device__ __forceinline__ bool surely_inside() const { return diff < -bound; }
+};
+
+__device__ __forceinline__ bool agrees(const double *M, double x, double y, double z, double lx, double ly, double rx,
+                                       double ry)
+{
+    const double l0 = project_row(M + 0, x, y, z), l1 = project_row(M + 4, x, y, z), l2 = project_row(M + 8, x, y, z);
+    const double r0 = project_row(M + 12, x, y, z), r1 = project_row(M + 16, x, y, z),
+                 r2 = project_row(M + 20, x, y, z);
+    const RatioTest t0(l1, l2, ly, cert_of(ly)), t1(l0, l2, lx, cert_of(lx));
+    const RatioTest t2(r1, r2, ry, cert_of(ry)), t3(r0, r2, rx, cert_of(rx));
+    if (t0.surely_outside() | t1.surely_outside() | t2.surely_outside() | t3.surely_outside()) return false;
+    if (t0.surely_inside() & t1.surely_inside() & t2.surely_inside() & t3.surely_inside()) return true;
+    return agrees_exact(M, x, y, z, lx, ly, rx, ry);
 }
 
 __global__ void __launch_bounds__(RS_THREADS) ransac_score_kernel(const RansacParams p)
@@ -107,10 +151,9 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_score_kernel(const RansacPa
     const int np = p.pt_off ? p.pt_off[f + 1] - p0 : p.n_points;
     const int h0 = blockIdx.y * RS_HC;
     const int nh = min(RS_HC, p.H - h0);
-    const int i = blockIdx.x * RS_THREADS + tid;
     const size_t hbase = static_cast<size_t>(f) * p.H;
 
-    if (blockIdx.x * RS_THREADS < np) {  // CTA-uniform
+    if (blockIdx.x * RS_TILE < np) {  // CTA-uniform
         if (tid < RS_HC) {
             s_cnt[tid] = 0;
             bool ok = tid < nh;
@@ -118,20 +161,55 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_score_kernel(const RansacPa
             s_valid[tid] = ok;
             if (ok) hypothesis_matrices(p.cam, p.T + (hbase + h0 + tid) * 12, &sM[tid][0], &sM[tid][12]);
         }
-        double x = 0, y = 0, z = 0, lx = 0, ly = 0, rx = 0, ry = 0;
-        const bool have = i < np;
-        if (have) {
-            const size_t g = static_cast<size_t>(p0 + i);
-            x = p.pts[3 * g]; y = p.pts[3 * g + 1]; z = p.pts[3 * g + 2];
-            lx = p.l_pix[2 * g]; ly = p.l_pix[2 * g + 1];
-            rx = p.r_pix[2 * g]; ry = p.r_pix[2 * g + 1];
+        // RS_PP correspondences per thread, in registers for the whole hypothesis sweep
+        double x[RS_PP], y[RS_PP], z[RS_PP], lx[RS_PP], ly[RS_PP], rx[RS_PP], ry[RS_PP];
+        double clx[RS_PP], cly[RS_PP], crx[RS_PP], cry[RS_PP];
+        bool have[RS_PP];
+#pragma unroll
+        for (int k = 0; k < RS_PP; ++k) {
+            const int i = blockIdx.x * RS_TILE + k * RS_THREADS + tid;
+            have[k] = i < np;
+            x[k] = y[k] = z[k] = lx[k] = ly[k] = rx[k] = ry[k] = 0.0;
+            if (have[k]) {
+                const size_t g = static_cast<size_t>(p0 + i);
+                x[k] = p.pts[3 * g]; y[k] = p.pts[3 * g + 1]; z[k] = p.pts[3 * g + 2];
+                lx[k] = p.l_pix[2 * g]; ly[k] = p.l_pix[2 * g + 1];
+                rx[k] = p.r_pix[2 * g]; ry[k] = p.r_pix[2 * g + 1];
+            }
+            clx[k] = cert_of(lx[k]); cly[k] = cert_of(ly[k]); crx[k] = cert_of(rx[k]); cry[k] = cert_of(ry[k]);
         }
         __syncthreads();
         for (int h = 0; h < nh; ++h) {
             if (!s_valid[h]) continue;  // CTA-uniform
-            const bool in = have && agrees(&sM[h][0], x, y, z, lx, ly, rx, ry);
-            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, in);
-            if (lane == 0 && bal) atomicAdd(&s_cnt[h], __popc(bal));
+            const double *M = &sM[h][0];
+            // left camera first: most hypotheses of a RANSAC run are bad, and a warp whose points
+            // are all certainly outside on the left image skips the right camera altogether
+            bool maybe[RS_PP], left_in[RS_PP];
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < RS_PP; ++k) {
+                const double l0 = project_row(M + 0, x[k], y[k], z[k]), l1 = project_row(M + 4, x[k], y[k], z[k]),
+                             l2 = project_row(M + 8, x[k], y[k], z[k]);
+                const RatioTest tv(l1, l2, ly[k], cly[k]), tu(l0, l2, lx[k], clx[k]);
+                maybe[k] = have[k] && !(tv.surely_outside() | tu.surely_outside());
+                left_in[k] = tv.surely_inside() & tu.surely_inside();
+                any |= maybe[k];
+            }
+            if (!__any_sync(0xFFFFFFFFu, any)) continue;  // warp-uniform
+#pragma unroll
+            for (int k = 0; k < RS_PP; ++k) {
+                const double r0 = project_row(M + 12, x[k], y[k], z[k]), r1 = project_row(M + 16, x[k], y[k], z[k]),
+                             r2 = project_row(M + 20, x[k], y[k], z[k]);
+                const RatioTest tv(r1, r2, ry[k], cry[k]), tu(r0, r2, rx[k], crx[k]);
+                bool in = false;
+                if (maybe[k] && !(tv.surely_outside() | tu.surely_outside())) {
+                    in = (left_in[k] & tv.surely_inside() & tu.surely_inside())
+                             ? true
+                             : agrees_exact(M, x[k], y[k], z[k], lx[k], ly[k], rx[k], ry[k]);
+                }
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, in);
+                if (lane == 0 && bal) atomicAdd(&s_cnt[h], __popc(bal));
+            }
         }
         __syncthreads();
         if (tid < nh && s_cnt[tid]) atomicAdd(p.counts + hbase + h0 + tid, s_cnt[tid]);
@@ -212,7 +290,7 @@ extern "C" int slamfe_ransac_score(const double *T, const uint8_t *hyp_valid, in
     for (int k = 0; k < 9; ++k) p.cam.K[k] = K[k];
     for (int k = 0; k < 12; ++k) { p.cam.M1[k] = M1[k]; p.cam.M2[k] = M2[k]; }
     p.counts = counts; p.best = best; p.work = work; p.best_mask = best_mask;
-    const dim3 grid(max(1, (max_points + RS_THREADS - 1) / RS_THREADS), max(1, (H + RS_HC - 1) / RS_HC), n_frames);
+    const dim3 grid(max(1, (max_points + RS_TILE - 1) / RS_TILE), max(1, (H + RS_HC - 1) / RS_HC), n_frames);
     if (grid.y > 65535u || grid.z > 65535u) return SLAMFE_ERANGE;
     ransac_score_kernel<<<grid, RS_THREADS, 0, s>>>(p);
     return launch_status();

@@ -20,60 +20,99 @@ struct Cams {
     double Q[12];
 };
 
-__device__ __forceinline__ double det3(double a0, double a1, double a2, double b0, double b1, double b2, double c0,
-                                       double c1, double c2)
-{
-    return a0 * (b1 * c2 - b2 * c1) - a1 * (b0 * c2 - b2 * c0) + a2 * (b0 * c1 - b1 * c0);
-}
-
 // Null vector of the rank-3 DLT system of a link; returns X = n[:3] / n[3].
+// Rows: a = P[2]*xl - P[0] (triangulation.py:17), b = P[2]*y - P[1] (:18, == :20 for links),
+// d = Q[2]*xr - Q[0] (:19).  n = generalized cross product of (a, b, d): the six 2x2 minors of
+// (b, d) are shared by the four cofactors (36 fp64 operations + one reciprocal per link).
 __device__ __forceinline__ void triangulate_link(const Cams &c, double xl, double xr, double y, double &X, double &Y,
                                                  double &Z)
 {
     double a[4], b[4], d[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        a[k] = c.P[8 + k] * xl - c.P[k];      // triangulation.py:17
-        b[k] = c.P[8 + k] * y - c.P[4 + k];   // triangulation.py:18 (== :20 for links)
-        d[k] = c.Q[8 + k] * xr - c.Q[k];      // triangulation.py:19
+        a[k] = fma(c.P[8 + k], xl, -c.P[k]);
+        b[k] = fma(c.P[8 + k], y, -c.P[4 + k]);
+        d[k] = fma(c.Q[8 + k], xr, -c.Q[k]);
     }
-    const double n0 = det3(a[1], a[2], a[3], b[1], b[2], b[3], d[1], d[2], d[3]);
-    const double n1 = -det3(a[0], a[2], a[3], b[0], b[2], b[3], d[0], d[2], d[3]);
-    const double n2 = det3(a[0], a[1], a[3], b[0], b[1], b[3], d[0], d[1], d[3]);
-    double n3 = -det3(a[0], a[1], a[2], b[0], b[1], b[2], d[0], d[1], d[2]);
+    const double m01 = b[0] * d[1] - b[1] * d[0], m02 = b[0] * d[2] - b[2] * d[0], m03 = b[0] * d[3] - b[3] * d[0];
+    const double m12 = b[1] * d[2] - b[2] * d[1], m13 = b[1] * d[3] - b[3] * d[1], m23 = b[2] * d[3] - b[3] * d[2];
+    const double n0 = a[1] * m23 - a[2] * m13 + a[3] * m12;
+    const double n1 = -(a[0] * m23 - a[2] * m03 + a[3] * m02);
+    const double n2 = a[0] * m13 - a[1] * m03 + a[3] * m01;
+    double n3 = -(a[0] * m12 - a[1] * m02 + a[2] * m01);
     double s = 1.0;
     if (n3 == 0.0) {  // triangulation.py:22-23 guard on the unit-norm singular vector
         s = rsqrt(n0 * n0 + n1 * n1 + n2 * n2);
         n3 = 1e-20;
     }
-    X = n0 * s / n3;
-    Y = n1 * s / n3;
-    Z = n2 * s / n3;
+    const double inv = s / n3;
+    X = n0 * inv;
+    Y = n1 * inv;
+    Z = n2 * inv;
 }
 
 constexpr int TRI_THREADS = 256;
+constexpr int TRI_ITEMS = 4;                          // links per thread
+constexpr int TRI_TILE = TRI_THREADS * TRI_ITEMS;     // links per CTA
 
+// One CTA = 1024 links.  The AoS rows [x_left, x_right, y] / [X, Y, Z] move between HBM and shared
+// memory as 16-byte vectors (fully coalesced, 3 (fp32) or 6 (fp64) loads in flight per thread);
+// thread t then works on links t, t+256, t+512, t+768 (stride-3 word accesses: conflict-free).
 template <typename T>
 __global__ void __launch_bounds__(TRI_THREADS) triangulate_links_kernel(const T *__restrict__ links, int64_t n,
                                                                         const Cams c, T *__restrict__ xyz)
 {
-    __shared__ T s[3 * TRI_THREADS];
-    const int64_t base = static_cast<int64_t>(blockIdx.x) * TRI_THREADS;
-    const int cnt = static_cast<int>(min(static_cast<int64_t>(TRI_THREADS), n - base));
-    for (int e = threadIdx.x; e < 3 * cnt; e += TRI_THREADS) s[e] = links[3 * base + e];
-    __syncthreads();
-    double X = 0, Y = 0, Z = 0;
-    if (threadIdx.x < cnt)
-        triangulate_link(c, static_cast<double>(s[3 * threadIdx.x]), static_cast<double>(s[3 * threadIdx.x + 1]),
-                         static_cast<double>(s[3 * threadIdx.x + 2]), X, Y, Z);
-    __syncthreads();
-    if (threadIdx.x < cnt) {
-        s[3 * threadIdx.x] = static_cast<T>(X);
-        s[3 * threadIdx.x + 1] = static_cast<T>(Y);
-        s[3 * threadIdx.x + 2] = static_cast<T>(Z);
+    constexpr int VEC = 16 / sizeof(T);               // elements per 16-byte vector
+    constexpr int NV = 3 * TRI_TILE / VEC;            // vectors per full tile
+    __shared__ alignas(16) T s[3 * TRI_TILE];
+    const int tid = threadIdx.x;
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * TRI_TILE;
+    const int cnt = static_cast<int>(min(static_cast<int64_t>(TRI_TILE), n - base));
+    const T *src = links + 3 * base;
+    T *dst = xyz + 3 * base;
+    const bool full = cnt == TRI_TILE;
+    const bool vec_in = full && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    const bool vec_out = full && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+    if (vec_in) {
+        const uint4 *v = reinterpret_cast<const uint4 *>(src);
+        uint4 r[NV / TRI_THREADS];
+#pragma unroll
+        for (int k = 0; k < NV / TRI_THREADS; ++k) r[k] = __ldcs(v + tid + k * TRI_THREADS);
+#pragma unroll
+        for (int k = 0; k < NV / TRI_THREADS; ++k) reinterpret_cast<uint4 *>(s)[tid + k * TRI_THREADS] = r[k];
+    } else {
+        for (int e = tid; e < 3 * cnt; e += TRI_THREADS) s[e] = src[e];
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < 3 * cnt; e += TRI_THREADS) xyz[3 * base + e] = s[e];
+    T out[TRI_ITEMS][3];
+#pragma unroll
+    for (int k = 0; k < TRI_ITEMS; ++k) {
+        const int i = tid + k * TRI_THREADS;
+        double X = 0, Y = 0, Z = 0;
+        if (i < cnt)
+            triangulate_link(c, static_cast<double>(s[3 * i]), static_cast<double>(s[3 * i + 1]),
+                             static_cast<double>(s[3 * i + 2]), X, Y, Z);
+        out[k][0] = static_cast<T>(X);
+        out[k][1] = static_cast<T>(Y);
+        out[k][2] = static_cast<T>(Z);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TRI_ITEMS; ++k) {
+        const int i = tid + k * TRI_THREADS;
+        s[3 * i] = out[k][0];
+        s[3 * i + 1] = out[k][1];
+        s[3 * i + 2] = out[k][2];
+    }
+    __syncthreads();
+    if (vec_out) {
+#pragma unroll
+        for (int k = 0; k < NV / TRI_THREADS; ++k)
+            __stcs(reinterpret_cast<uint4 *>(dst) + tid + k * TRI_THREADS,
+                   reinterpret_cast<const uint4 *>(s)[tid + k * TRI_THREADS]);
+    } else {
+        for (int e = tid; e < 3 * cnt; e += TRI_THREADS) dst[e] = s[e];
+    }
 }
 
 // One Jacobi rotation between columns p and q of G (4x4, column norms -> singular values).
@@ -172,7 +211,7 @@ int run_links(const T *links, int64_t n, const double *P, const double *Q, T *xy
     if (rc) return rc;
     for (int k = 4; k < 12; ++k)
         if (c.P[k] != c.Q[k]) return SLAMFE_EINVAL;  // not a shared-row stereo pair: use the DLT entry point
-    const int64_t blocks = (n + TRI_THREADS - 1) / TRI_THREADS;
+    const int64_t blocks = (n + TRI_TILE - 1) / TRI_TILE;
     if (blocks > 0x7FFFFFFF) return SLAMFE_ERANGE;
     triangulate_links_kernel<T><<<static_cast<unsigned>(blocks), TRI_THREADS, 0, stream>>>(links, n, c, xyz);
     return launch_status();

@@ -134,7 +134,7 @@ class FrontEnd:
     run(ds)          inputs already resident in HBM, everything on the current stream;
     run_host(seq)    host (pinned) inputs -> host (pinned) result tables: the sequence is cut into
                      chunks of frames and the H2D copy of chunk c+1, the kernels of chunk c and
-                     the D2H copy of chunk c-1 run concurrently on three streams.
+                     the D2H copy of chunk c-1 run concurrently (copy-in, 2 compute, copy-out streams).
     """
 
     def __init__(self, P=None, Q=None):
@@ -244,8 +244,8 @@ class FrontEnd:
             self._pinned_out = {k: torch.empty(o[k].shape, dtype=o[k].dtype, pin_memory=True) for k in RESULT_KEYS}
         hout = self._pinned_out
         if self._streams is None:
-            self._streams = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
-        s_in, s_cmp, s_out = self._streams
+            self._streams = tuple(torch.cuda.Stream(device=dev) for _ in range(4))
+        s_in, s_cmp_a, s_cmp_b, s_out = self._streams
         self.last_launches = 0
         if F == 0:
             return {k: hout[k].numpy() for k in keys}, 0, 0
@@ -269,7 +269,7 @@ class FrontEnd:
         small = np.concatenate(parts + [seq.n_l.astype(np.int64), seq.n_r.astype(np.int64)]).astype(np.int32)
         small_pin = torch.from_numpy(small).pin_memory()
         cur = torch.cuda.current_stream(dev)
-        for s in (s_in, s_cmp, s_out):
+        for s in self._streams:
             s.wait_stream(cur)
         h2d = d2h = 0
         with torch.cuda.stream(s_in):
@@ -277,7 +277,11 @@ class FrontEnd:
             h2d += small_pin.numel() * 4
         n_l_dev, n_r_dev = small_dev[pos:pos + F], small_dev[pos + F:pos + 2 * F]
         ev_done = []
+        ev_links_prev = None
         for c in range(len(bounds) - 1):
+            # chunks alternate between two compute streams, so the tail of one chunk's matcher
+            # launch (few long CTAs left) overlaps the head of the next chunk's
+            s_cmp = s_cmp_a if c % 2 == 0 else s_cmp_b
             f0, f1 = bounds[c], bounds[c + 1]
             n = f1 - f0
             a, b = int(l_off[f0]), int(l_off[f1])
@@ -299,6 +303,11 @@ class FrontEnd:
                                     din["pts_r"][ra:rb], small_dev[l0:l1], small_dev[r0:r1], n_l_dev[f0:f1],
                                     n_r_dev[f0:f1], n, max_nl, max_nr, view)
                 self.last_launches += 3
+                ev_links = torch.cuda.Event()
+                ev_links.record(s_cmp)
+                if ev_links_prev is not None:  # frame f0-1's features come from the other stream
+                    s_cmp.wait_event(ev_links_prev)
+                ev_links_prev = ev_links
                 p0 = max(f0 - 1, 0)
                 n_pairs = f1 - 1 - p0
                 if n_pairs > 0:
@@ -333,7 +342,8 @@ class FrontEnd:
                 ev.record(s_out)
                 ev_done.append(ev)
         ev_done[-1].synchronize()
-        cur.wait_stream(s_out)
+        for s in self._streams:
+            cur.wait_stream(s)
         return {k: hout[k].numpy() for k in keys}, int(h2d), int(d2h)
 
 

@@ -71,6 +71,27 @@ def hamming_top2_batched(q, q_off, t, t_off, n_problems, max_nq, max_nt, desc_by
     return row_keys, (col_keys if want_cols else None)
 
 
+def hamming_pairs(q, q_off, q_cnt, t, t_off, t_cnt, out_off, n_problems, max_nq, max_nt, desc_bytes=None,
+                  row_keys=None, out_rows_total=None, best_only=False):
+    """Candidate-pair matching (slamfe_hamming_top2_pairs): problem p = rows q_off[p].. of q against
+    rows t_off[p].. of t, results at row_keys[out_off[p] + i].  All index tensors int32 CUDA."""
+    torch = _torch()
+    q, t = _desc_tensor(q), _desc_tensor(t)
+    desc_bytes = q.shape[1] if desc_bytes is None else desc_bytes
+    if row_keys is None:
+        if out_rows_total is None:
+            raise ValueError("give row_keys or out_rows_total")
+        row_keys = torch.empty((out_rows_total, 2), dtype=torch.int32, device=q.device)
+    if out_rows_total is None:
+        out_rows_total = row_keys.shape[0]
+    with torch.cuda.device(q.device):
+        check(load_library().slamfe_hamming_top2_pairs(
+            ptr(q), q.stride(0), ptr(q_off), ptr(q_cnt), ptr(t), t.stride(0), ptr(t_off), ptr(t_cnt), ptr(out_off),
+            n_problems, max_nq, max_nt, desc_bytes, ptr(row_keys), out_rows_total,
+            _cabi.MATCH_BEST_ONLY if best_only else 0, stream_handle()), "slamfe_hamming_top2_pairs")
+    return row_keys
+
+
 def unpack_keys(keys):
     """keys (...,) -> (idx, dist) int32 tensors of the same shape, -1 where no neighbour."""
     torch = _torch()

@@ -93,6 +93,20 @@ int slamfe_hamming_top2_batched(const uint8_t *q, int q_stride, const int32_t *q
                                 uint32_t *row_keys, int64_t q_rows_total,
                                 uint32_t *col_keys, int64_t t_rows_total, int flags, slamfe_stream_t stream);
 
+/*
+ * Candidate-pair form (loop closure, backend/loop/loop_closure.py:422 inside :405-436, and BASELINE
+ * config 4 "each keyframe vs all prior keyframes"): problem p matches q rows
+ * [q_off[p], q_off[p] + q_cnt[p]) against t rows [t_off[p], t_off[p] + t_cnt[p]); the same rows may
+ * appear in many problems (q and t may be the same keyframe pool), so the result rows are indexed by
+ * PROBLEM: the keys of problem p's query i land in row_keys[out_off[p] + i] ((out_rows_total, 2)).
+ * All five index arrays are DEVICE int32 with n_problems entries.  No column minima
+ * (MATCHER.match at loop_closure.py:422 has crossCheck=False).
+ */
+int slamfe_hamming_top2_pairs(const uint8_t *q, int q_stride, const int32_t *q_off, const int32_t *q_cnt,
+                              const uint8_t *t, int t_stride, const int32_t *t_off, const int32_t *t_cnt,
+                              const int32_t *out_off, int n_problems, int max_nq, int max_nt, int desc_bytes,
+                              uint32_t *row_keys, int64_t out_rows_total, int flags, slamfe_stream_t stream);
+
 /* keys (n,) -> idx (n,) int32 (-1 for NONE), dist (n,) int32 (-1 for NONE). */
 int slamfe_unpack_keys(const uint32_t *keys, int64_t n, int32_t *idx, int32_t *dist, slamfe_stream_t stream);
 

@@ -191,3 +191,39 @@ def test_dense_20k_sweep_vs_oracle(slamfe, oracle):
     rs, _ = ops.hamming_top2(qd, qd)  # self sweep: best distance is 0 at an index <= i (duplicates)
     si, sd = _keys(ops, rs)
     assert np.all(sd[:, 0] == 0) and np.all(si[:, 0] <= np.arange(20000))
+
+
+@pytest.mark.parametrize("best_only", [False, True])
+def test_candidate_pairs_vs_oracle(slamfe, oracle, best_only):
+    """Loop-closure form (loop_closure.py:422): a pool of keyframes, every keyframe against all
+    earlier ones, results indexed by candidate pair; the same keyframe is query in many pairs."""
+    import torch
+    from slamfe import dist, ops, synth
+    rng = np.random.default_rng(41)
+    sizes = [260, 40, 513, 129, 300, 1]
+    pool = [synth.descriptors(rng, n) for n in sizes]
+    pool[3][:60] = pool[0][:60]            # revisit: exact duplicates force index tie-breaks
+    pool[4][10:200] = synth.flip_bits(rng, pool[2][10:200], 0.05)
+    off = np.zeros(len(sizes) + 1, np.int64)
+    np.cumsum([-(-n // 16) * 16 for n in sizes], out=off[1:])
+    flat = np.zeros((off[-1], 61), np.uint8)
+    for k, d in enumerate(pool):
+        flat[off[k]:off[k] + sizes[k]] = d
+    pairs = dist.candidate_pairs(len(sizes))
+    nq = np.array([sizes[i] for i, _ in pairs], np.int32)
+    out_off = np.zeros(len(pairs) + 1, np.int64)
+    np.cumsum(nq, out=out_off[1:])
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).cuda()
+    fd = torch.from_numpy(flat).cuda()
+    keys = ops.hamming_pairs(fd, dev(off[pairs[:, 0]]), dev(nq), fd, dev(off[pairs[:, 1]]),
+                             dev([sizes[j] for _, j in pairs]), dev(out_off[:-1]), len(pairs), max(sizes), max(sizes),
+                             61, out_rows_total=int(out_off[-1]), best_only=best_only)
+    idx, dst = ops.keys_to_numpy(keys.cpu().numpy())
+    for p, (i, j) in enumerate(pairs):
+        oi, od = oracle.knn2(pool[i], pool[j])
+        got_i, got_d = idx[out_off[p]:out_off[p + 1]], dst[out_off[p]:out_off[p + 1]]
+        assert np.array_equal(got_i[:, 0], oi[:, 0]) and np.array_equal(got_d[:, 0], od[:, 0]), (i, j)
+        if best_only:
+            assert (got_i[:, 1] == -1).all()
+        else:
+            assert np.array_equal(got_i[:, 1], oi[:, 1]) and np.array_equal(got_d[:, 1], od[:, 1]), (i, j)

@@ -113,3 +113,43 @@ def test_seeded_ransac_loops_equal_reference(slamfe, golden, oracle, monkeypatch
     assert np.allclose(pose.matrix(), g["pnp_pose"], atol=1e-9)
     with pytest.raises(ValueError):  # np.random.choice(n < 4, 4, replace=False), ransac.py:95
         ransac.ransac_pnp_for_tracking_db(ms[:3], prev, cur, 55)
+
+
+def test_borderline_reprojection_errors_take_the_exact_path(slamfe, oracle):
+    """The scorer decides |num/den - pix| < 2 without dividing and falls back to the literal IEEE
+    division when its rounding certificate fails.  Pixels placed within a few ulps of the +-2
+    threshold (and degenerate z = 0 / behind-camera points) must still score exactly as the
+    reference formula (ransac.py:38-56) does in numpy."""
+    from slamfe import ransac, synth
+    rng = np.random.default_rng(77)
+    K, M1, M2 = synth.cameras()
+    ransac.set_cameras(K, M1, M2)
+    Ts, pts, lp, rp = synth.pnp_problem(rng, 4000, 6)
+    pts[:40, 2] *= -1.0                       # behind the camera: no cheirality test in the reference
+    T = Ts[0]
+    def project(Tm):
+        Th = np.vstack([Tm, [0, 0, 0, 1]]); X = np.hstack([pts, np.ones((len(pts), 1))]).T
+        l = K @ Tm @ np.vstack([M1, [0, 0, 0, 1]]) @ X
+        r = K @ Tm @ np.vstack([M2, [0, 0, 0, 1]]) @ X
+        return l[:2] / l[2], r[:2] / r[2]
+    (ul, vl), (ur, vr) = [a for a in project(T)]
+    lp = np.stack([ul, vl], axis=1).copy(); rp = np.stack([ur, vr], axis=1).copy()
+    n = len(pts)
+    which = rng.integers(0, 4, n)              # one coordinate per point sits on the threshold
+    sign = rng.choice([-2.0, 2.0], n)
+    ulps = rng.integers(-4, 5, n)
+    for arr, col, sel in ((lp, 0, 0), (lp, 1, 1), (rp, 0, 2), (rp, 1, 3)):
+        m = which == sel
+        v = arr[m, col] + sign[m]
+        for _ in range(4):
+            v = np.where(ulps[m] > 0, np.nextafter(v, np.inf), np.where(ulps[m] < 0, np.nextafter(v, -np.inf), v))
+        arr[m, col] = v
+    pts[-3:] = [[0.0, 0.0, 0.0], [1.0, 2.0, 0.0], [np.nan, 1.0, 5.0]]   # 0/0, x/0, NaN
+    Ts[1] = np.hstack([np.eye(3), np.zeros((3, 1))])
+    counts, best, cnt, mask = ransac.score_hypotheses(Ts, pts, lp, rp)
+    oc, ob, om = oracle.score_hypotheses(Ts, pts, lp, rp, K, M1, M2)
+    assert np.array_equal(counts, oc) and best == ob and np.array_equal(mask, om)
+    for h in range(len(Ts)):
+        got = ransac.transformation_agreement(Ts[h], pts, lp, rp)
+        assert np.array_equal(got, oracle.transformation_agreement(Ts[h], pts, lp, rp, K, M1, M2)), h
+    assert 0 < counts[0] < n                   # the thresholded hypothesis is genuinely split

@@ -195,9 +195,11 @@ __device__ __forceinline__ uint32_t hamming16_key(const uint32_t (&q)[W], const 
 template <int NR, int RMAX, bool COL, bool TOP2, int CS>
 __device__ __forceinline__ void sweep_stage(const uint4 *__restrict__ tl, int rows, uint32_t jbase,
                                             const uint32_t (&q)[RMAX][W], uint32_t (&b1)[RMAX], uint32_t (&b2)[RMAX],
-                                            const uint32_t (&colbias)[RMAX], uint32_t *colmin_w, int lane)
+                                            const uint32_t (&colbias)[RMAX], uint32_t colmin_in, int lane)
 {
     uint32_t jj = jbase;
+    uint32_t colmin_w;  // pinned in a register: ptxas otherwise rematerialises the address every row
+    asm volatile("mov.u32 %0, %1;" : "=r"(colmin_w) : "r"(colmin_in));
 #pragma unroll 2
     for (int j = 0; j < rows; ++j, ++jj) {
         const uint4 t0 = tl[4 * j + 0], t1 = tl[4 * j + 1], t2 = tl[4 * j + 2], t3 = tl[4 * j + 3];
@@ -215,7 +217,9 @@ __device__ __forceinline__ void sweep_stage(const uint4 *__restrict__ tl, int ro
         }
         if (COL) {
             const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, ck);
-            if (lane == 0) colmin_w[j] = m;
+            // explicit shared-space store: one address register + immediate, no generic-pointer
+            // conversion inside the loop (ptxas rematerialised it every row under register pressure)
+            if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(colmin_w + 4u * j), "r"(m) : "memory");
         }
     }
 }
@@ -224,7 +228,7 @@ template <int N, int RMAX, bool COL, bool TOP2, int CS>
 __device__ __forceinline__ void sweep_dispatch(int nr_w, const uint4 *__restrict__ tl, int rows, uint32_t jbase,
                                                const uint32_t (&q)[RMAX][W], uint32_t (&b1)[RMAX],
                                                uint32_t (&b2)[RMAX], const uint32_t (&colbias)[RMAX],
-                                               uint32_t *colmin_w, int lane)
+                                               uint32_t colmin_w, int lane)
 {
     if (nr_w == N)
         sweep_stage<N, RMAX, COL, TOP2, CS>(tl, rows, jbase, q, b1, b2, colbias, colmin_w, lane);
@@ -371,7 +375,7 @@ __global__ void __launch_bounds__(THREADS, (RMAX >= 3 ? 2 : 3)) hamming_top2_ker
         // ---- sweep: every lane reads the same train row (broadcast LDS.128) ----
         const uint32_t jbase = static_cast<uint32_t>(p.t_index_base + tb + s * TS);
         sweep_dispatch<RMAX, RMAX, COL, TOP2, CS>(nr_w, reinterpret_cast<const uint4 *>(tile[b]), rows, jbase, q, b1,
-                                                  b2, colbias, COL ? colmin_s[b][warp] : nullptr, lane);
+                                                  b2, colbias, COL ? smem_u32(&colmin_s[b][warp][0]) : 0u, lane);
     }
 
     if (COL) {

@@ -96,6 +96,20 @@ def merge_top2_host(shard_keys):
     return np.ascontiguousarray(flat[:, :2])
 
 
+def _all_gather_stacked(t):
+    """all_gather_into_tensor with a (world, ...) result; the flat (world*n, ...) output form is
+    the one both NCCL and gloo accept."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    t = t.contiguous()
+    if t.dim() == 0:
+        t = t.reshape(1)
+    flat = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(flat, t)
+    return flat.view((world, t.shape[0]) + tuple(t.shape[1:]))
+
+
 def all_gather_padded(t, lengths=None):
     """All-gather a per-rank tensor whose leading dimension differs between ranks.
 
@@ -108,27 +122,51 @@ def all_gather_padded(t, lengths=None):
     world = dist.get_world_size()
     if lengths is None:
         ln = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-        all_ln = torch.empty((world,), dtype=torch.int64, device=t.device)
-        dist.all_gather_into_tensor(all_ln, ln)
-        lengths = all_ln.cpu().numpy()
+        lengths = _all_gather_stacked(ln).reshape(-1).cpu().numpy()
     max_len = int(max(lengths))
     pad = torch.zeros((max_len,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     pad[: t.shape[0]] = t
-    out = torch.empty((world, max_len) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-    dist.all_gather_into_tensor(out, pad)
-    return out, np.asarray(lengths, dtype=np.int64)
+    return _all_gather_stacked(pad), np.asarray(lengths, dtype=np.int64)
 
 
-def sharded_knn(q_dev, t_shard_dev, t_index_base, desc_bytes=None):
-    """Dense sweep (config 5): this rank's train slice vs all queries, all-gather, exact merge.
-    Returns the global (nq, 2) key table on every rank."""
+def gather_and_merge_top2(row_keys):
+    """All-gather every rank's (nq, 2) key table (keys carry GLOBAL train indices) and min-merge
+    them: exact global top-2 on every rank.  CUDA tensors merge with slamfe_merge_top2 over NCCL,
+    CPU tensors (gloo, used by the host-logic tests) with the host restatement."""
+    import torch
     import torch.distributed as dist
-    from . import ops
-    row_keys, _ = ops.hamming_top2(q_dev, t_shard_dev, desc_bytes=desc_bytes, t_index_base=int(t_index_base))
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return row_keys
+    gathered = _all_gather_stacked(row_keys)
+    if row_keys.is_cuda:
+        from . import ops
+        return ops.merge_top2(gathered)
+    return torch.from_numpy(merge_top2_host(gathered.numpy()).view(np.int32))
+
+
+def sharded_knn(q_dev, t_shard_dev, t_index_base, desc_bytes=None, best_only=False):
+    """Dense sweep (config 5): this rank's train slice vs all queries, all-gather, exact merge.
+    Returns the global (nq, 2) key table on every rank."""
+    from . import ops
+    row_keys, _ = ops.hamming_top2(q_dev, t_shard_dev, desc_bytes=desc_bytes, t_index_base=int(t_index_base),
+                                   best_only=best_only)
+    return gather_and_merge_top2(row_keys)
+
+
+def gather_pair_tables(tables, n_units):
+    """All-gather per-shard result tables of the frame-pair / candidate-block shardings.
+    `tables` maps name -> tensor whose leading dimension is this rank's unit count (frames,
+    candidate pairs, rows).  Returns name -> (world, max_units, ...) plus the per-rank unit counts;
+    one collective per table (+1 for the counts)."""
     import torch
-    world = dist.get_world_size()
-    gathered = torch.empty((world,) + tuple(row_keys.shape), dtype=row_keys.dtype, device=row_keys.device)
-    dist.all_gather_into_tensor(gathered, row_keys)
-    return ops.merge_top2(gathered)
+    import torch.distributed as dist
+    first = next(iter(tables.values()))
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return {k: v.unsqueeze(0) for k, v in tables.items()}, np.array([n_units], dtype=np.int64)
+    ln = torch.tensor([n_units], dtype=torch.int64, device=first.device)
+    lengths = _all_gather_stacked(ln).reshape(-1).cpu().numpy()
+    out = {}
+    for k, v in tables.items():
+        per_unit = v.shape[0] // max(n_units, 1) if n_units else 1
+        out[k], _ = all_gather_padded(v, lengths=lengths * per_unit if v.shape[0] != n_units else lengths)
+    return out, lengths

@@ -225,7 +225,7 @@ class FrontEnd:
             self._pinned_out = None
         return self._in
 
-    def run_host(self, seq: PackedSequence, chunk_frames=288, device="cuda", keys=RESULT_KEYS):
+    def run_host(self, seq: PackedSequence, chunk_frames=576, device="cuda", keys=RESULT_KEYS):
         """Pinned host inputs -> pinned host result tables, copies overlapped with the kernels.
 
         Returns (dict of numpy views of the pinned result tables, h2d_bytes, d2h_bytes).  The call

@@ -17,4 +17,9 @@ echo "ncu launches rc=$?"
 $BENCH_SMALL > gpurun_out/plain_small2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:hamming_top2 -s 4 -c 2 -f -o gpurun_out/prof_hamming $BENCH_SMALL > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"
+# DRAM traffic of the dominant launch at the FULL bench size (one launch, dram metrics only)
+BENCH_FULL="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e"
+$BENCH_FULL > gpurun_out/plain_full.log 2>&1 &&
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:hamming_top2 -s 6 -c 2 --csv --log-file gpurun_out/traffic_full.csv $BENCH_FULL > gpurun_out/ncu_traffic.log 2>&1
+echo "ncu traffic rc=$?"
 tail -3 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log; cat gpurun_out/bench.json; cat gpurun_out/bench_ref.json

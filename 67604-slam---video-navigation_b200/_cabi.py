@@ -16,6 +16,7 @@ KEY_IDX_MASK = (1 << KEY_IDX_BITS) - 1
 KEY_NONE = 0xFFFFFFFF
 MAX_DESC_BYTES = 64
 MATCH_BEST_ONLY = 1
+MATCH_COMPACT_KEYS = 2
 
 # name -> (restype, argtypes); mirrors include/slamfe.h one to one
 _SIGNATURES = {
@@ -25,7 +26,7 @@ _SIGNATURES = {
                                     c_void_p, c_void_p, c_int, c_void_p]),
     "slamfe_hamming_top2_batched": (c_int, [c_void_p, c_int, c_void_p, c_void_p,
                                             c_void_p, c_int, c_void_p, c_void_p,
-                                            c_int, c_int, c_int, c_int,
+                                            c_int, c_int, c_int, c_int, c_int,
                                             c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "slamfe_hamming_top2_pairs": (c_int, [c_void_p, c_int, c_void_p, c_void_p,
                                           c_void_p, c_int, c_void_p, c_void_p,

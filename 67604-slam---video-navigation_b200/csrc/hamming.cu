@@ -44,6 +44,7 @@ struct HammingParams {
     int tma_quantum;  // rows per 16-byte-multiple chunk of the train layout
     uint2 *row_keys;
     uint32_t *col_keys;
+    int compact;      // best-only results as one u32 per query row instead of (best, second)
 };
 
 // Load one descriptor (desc_bytes useful bytes) from global memory into 16 zero-padded words.
@@ -387,7 +388,16 @@ __global__ void __launch_bounds__(THREADS, (RMAX >= 3 ? 2 : 3)) hamming_top2_ker
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) {
         if (qrow[r] < nq) {
-            uint2 *g = p.row_keys + (p.row_out_off ? p.row_out_off[prob] : q_row0) + qrow[r];
+            const size_t row = static_cast<size_t>(p.row_out_off ? p.row_out_off[prob] : q_row0) + qrow[r];
+            if (!TOP2 && p.compact) {
+                uint32_t *c = reinterpret_cast<uint32_t *>(p.row_keys) + row;
+                if (gridDim.y == 1)
+                    *c = b1[r];
+                else
+                    atomicMin(c, b1[r]);
+                continue;
+            }
+            uint2 *g = p.row_keys + row;
             if (gridDim.y == 1)
                 *g = make_uint2(b1[r], b2[r]);
             else if (TOP2)
@@ -522,12 +532,15 @@ int run_hamming(HammingParams p, int n_problems, int max_nq, int max_nt, int64_t
                 int flags, cudaStream_t stream)
 {
     if (n_problems <= 0 || q_rows_total <= 0) return 0;
-    SLAMFE_CUDA_OK(cudaMemsetAsync(p.row_keys, 0xFF, sizeof(uint2) * q_rows_total, stream));
+    const bool top2 = !(flags & SLAMFE_MATCH_BEST_ONLY);
+    if ((flags & SLAMFE_MATCH_COMPACT_KEYS) && top2) return SLAMFE_EINVAL;
+    p.compact = (flags & SLAMFE_MATCH_COMPACT_KEYS) ? 1 : 0;
+    SLAMFE_CUDA_OK(cudaMemsetAsync(p.row_keys, 0xFF, (p.compact ? sizeof(uint32_t) : sizeof(uint2)) * q_rows_total,
+                                   stream));
     if (p.col_keys && t_rows_total > 0)
         SLAMFE_CUDA_OK(cudaMemsetAsync(p.col_keys, 0xFF, sizeof(uint32_t) * t_rows_total, stream));
     if (max_nq <= 0 || max_nt <= 0) return 0;
     p.tma_quantum = 16 / gcd(p.t_stride, 16);
-    const bool top2 = !(flags & SLAMFE_MATCH_BEST_ONLY);
 
     const int sms = sm_count();
     const int stages_total = (max_nt + TS - 1) / TS;
@@ -600,19 +613,22 @@ extern "C" int slamfe_hamming_top2(const uint8_t *q, int nq, int q_stride, const
 
 extern "C" int slamfe_hamming_top2_batched(const uint8_t *q, int q_stride, const int32_t *q_off, const int32_t *q_cnt,
                                            const uint8_t *t, int t_stride, const int32_t *t_off, const int32_t *t_cnt,
-                                           int n_problems, int max_nq, int max_nt, int desc_bytes, uint32_t *row_keys,
-                                           int64_t q_rows_total, uint32_t *col_keys, int64_t t_rows_total,
-                                           int flags, slamfe_stream_t stream)
+                                           int n_problems, int max_nq, int max_nt, int desc_bytes, int t_index_base,
+                                           uint32_t *row_keys, int64_t q_rows_total, uint32_t *col_keys,
+                                           int64_t t_rows_total, int flags, slamfe_stream_t stream)
 {
-    if (n_problems < 0 || max_nq < 0 || max_nt < 0 || q_rows_total < 0 || t_rows_total < 0) return SLAMFE_EINVAL;
+    if (n_problems < 0 || max_nq < 0 || max_nt < 0 || q_rows_total < 0 || t_rows_total < 0 || t_index_base < 0)
+        return SLAMFE_EINVAL;
     if (n_problems == 0 || q_rows_total == 0) return 0;
     if (!row_keys || !q_off || !t_off) return SLAMFE_EINVAL;
     const int rc = check_desc_args(q, t, q_stride, t_stride, desc_bytes);
     if (rc) return rc;
-    if (max_nq > static_cast<int>(KEY_IDX_MASK) || max_nt > static_cast<int>(KEY_IDX_MASK)) return SLAMFE_ERANGE;
+    if (max_nq > static_cast<int>(KEY_IDX_MASK) ||
+        static_cast<int64_t>(t_index_base) + max_nt > static_cast<int64_t>(KEY_IDX_MASK))
+        return SLAMFE_ERANGE;
     HammingParams p{};
     p.q = q; p.t = t; p.q_stride = q_stride; p.t_stride = t_stride; p.desc_bytes = desc_bytes;
-    p.q_off = q_off; p.q_cnt = q_cnt; p.t_off = t_off; p.t_cnt = t_cnt;
+    p.q_off = q_off; p.q_cnt = q_cnt; p.t_off = t_off; p.t_cnt = t_cnt; p.t_index_base = t_index_base;
     p.row_keys = reinterpret_cast<uint2 *>(row_keys);
     p.col_keys = col_keys;
     return run_hamming(p, n_problems, max_nq, max_nt, q_rows_total, t_rows_total, flags,

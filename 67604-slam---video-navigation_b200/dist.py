@@ -26,13 +26,16 @@ def init_from_env(backend=None):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and not dist.is_initialized():
+        import datetime
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
+        # a mismatched collective must fail in minutes, not hold N GPUs for the default 10 minutes
+        timeout = datetime.timedelta(seconds=int(os.environ.get("SLAMFE_PG_TIMEOUT_S", "120")))
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
-            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank), timeout=timeout)
         else:
-            dist.init_process_group(backend)
+            dist.init_process_group(backend, timeout=timeout)
     elif torch.cuda.is_available():
         torch.cuda.set_device(local_rank)
     return rank, world, local_rank

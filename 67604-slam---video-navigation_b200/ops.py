@@ -16,6 +16,10 @@ def _torch():
     return _cabi.require_cuda()
 
 
+def _flags(best_only, compact=False):
+    return (_cabi.MATCH_BEST_ONLY if best_only else 0) | (_cabi.MATCH_COMPACT_KEYS if compact else 0)
+
+
 def _desc_tensor(d):
     torch = _torch()
     if d.dtype != torch.uint8 or d.dim() != 2 or not d.is_cuda:
@@ -49,46 +53,52 @@ def hamming_top2(q, t, desc_bytes=None, want_cols=False, t_index_base=0, best_on
 
 
 def hamming_top2_batched(q, q_off, t, t_off, n_problems, max_nq, max_nt, desc_bytes,
-                         q_cnt=None, t_cnt=None, want_cols=False, row_keys=None, col_keys=None, best_only=False):
+                         q_cnt=None, t_cnt=None, want_cols=False, row_keys=None, col_keys=None, best_only=False,
+                         t_index_base=0, compact=False):
     """Ragged batch of matching problems in one launch (slamfe_hamming_top2_batched).
 
     q_off / t_off / q_cnt / t_cnt are int32 CUDA tensors (see include/slamfe.h); keys are indexed
-    by global row and hold problem-local indices.
+    by global row and hold problem-local indices (+ t_index_base).  compact=True (with best_only)
+    returns one uint32 key per row instead of (best, second).
     """
     torch = _torch()
     q, t = _desc_tensor(q), _desc_tensor(t)
+    if compact and not best_only:
+        raise ValueError("compact keys need best_only=True")
     if row_keys is None:
-        row_keys = torch.empty((q.shape[0], 2), dtype=torch.int32, device=q.device)
+        row_keys = torch.empty((q.shape[0],) if compact else (q.shape[0], 2), dtype=torch.int32, device=q.device)
     if want_cols and col_keys is None:
         col_keys = torch.empty((t.shape[0],), dtype=torch.int32, device=q.device)
     with torch.cuda.device(q.device):
         check(load_library().slamfe_hamming_top2_batched(
             ptr(q), q.stride(0), ptr(q_off), ptr(q_cnt), ptr(t), t.stride(0), ptr(t_off), ptr(t_cnt),
-            n_problems, max_nq, max_nt, desc_bytes,
+            n_problems, max_nq, max_nt, desc_bytes, int(t_index_base),
             ptr(row_keys), q.shape[0], ptr(col_keys) if want_cols else 0, t.shape[0],
-            _cabi.MATCH_BEST_ONLY if best_only else 0, stream_handle()),
+            _flags(best_only, compact), stream_handle()),
             "slamfe_hamming_top2_batched")
     return row_keys, (col_keys if want_cols else None)
 
 
 def hamming_pairs(q, q_off, q_cnt, t, t_off, t_cnt, out_off, n_problems, max_nq, max_nt, desc_bytes=None,
-                  row_keys=None, out_rows_total=None, best_only=False):
+                  row_keys=None, out_rows_total=None, best_only=False, compact=False):
     """Candidate-pair matching (slamfe_hamming_top2_pairs): problem p = rows q_off[p].. of q against
-    rows t_off[p].. of t, results at row_keys[out_off[p] + i].  All index tensors int32 CUDA."""
+    rows t_off[p].. of t, results at row_keys[out_off[p] + i].  All index tensors int32 CUDA.
+    compact=True (with best_only): row_keys is (rows,) — one key per query row."""
     torch = _torch()
     q, t = _desc_tensor(q), _desc_tensor(t)
     desc_bytes = q.shape[1] if desc_bytes is None else desc_bytes
     if row_keys is None:
         if out_rows_total is None:
             raise ValueError("give row_keys or out_rows_total")
-        row_keys = torch.empty((out_rows_total, 2), dtype=torch.int32, device=q.device)
+        row_keys = torch.empty((out_rows_total,) if compact else (out_rows_total, 2), dtype=torch.int32,
+                               device=q.device)
     if out_rows_total is None:
         out_rows_total = row_keys.shape[0]
     with torch.cuda.device(q.device):
         check(load_library().slamfe_hamming_top2_pairs(
             ptr(q), q.stride(0), ptr(q_off), ptr(q_cnt), ptr(t), t.stride(0), ptr(t_off), ptr(t_cnt), ptr(out_off),
             n_problems, max_nq, max_nt, desc_bytes, ptr(row_keys), out_rows_total,
-            _cabi.MATCH_BEST_ONLY if best_only else 0, stream_handle()), "slamfe_hamming_top2_pairs")
+            _flags(best_only, compact), stream_handle()), "slamfe_hamming_top2_pairs")
     return row_keys
 
 

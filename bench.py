@@ -48,6 +48,10 @@ def parse_args():
     ap.add_argument("--frames", type=int, default=4541, help="frames per GPU (KITTI 00 has 4541)")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--impl", default="slamfe", choices=["slamfe", "reference"])
+    ap.add_argument("--workload", default="sequence", choices=["sequence", "ransac", "loop", "dense"],
+                    help="sequence = BASELINE configs[1] (the headline line); the others are configs[2..4], see "
+                         "bench_extra.py")
+    ap.add_argument("--keyframes", type=int, default=450, help="--workload loop: number of keyframes")
     ap.add_argument("--cpu-sample-frames", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -210,6 +214,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.workload != "sequence":
+        import bench_extra
+        bench_extra.run(args, ClockSampler)
         return
 
     import torch

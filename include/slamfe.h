@@ -43,6 +43,7 @@ typedef void *slamfe_stream_t;
 
 /* matcher flags */
 #define SLAMFE_MATCH_BEST_ONLY 1 /* keep only the best neighbour (.match / crossCheck); row_keys[:,1] = KEY_NONE */
+#define SLAMFE_MATCH_COMPACT_KEYS 2 /* with BEST_ONLY: row_keys is (rows,) uint32, one key per query row */
 
 #define SLAMFE_EINVAL (-1)   /* bad argument (null pointer, negative size, stride < desc_bytes ...) */
 #define SLAMFE_ERANGE (-2)   /* size exceeds what the key encoding / grid can address */
@@ -83,13 +84,15 @@ int slamfe_hamming_top2(const uint8_t *q, int nq, int q_stride,
  * [q_off[p], q_off[p] + nq_p) of `q` against rows [t_off[p], t_off[p] + nt_p) of `t`, where
  * nq_p = q_cnt ? q_cnt[p] : q_off[p+1] - q_off[p]  (same for t).  All four arrays are DEVICE
  * int32; q_off/t_off have n_problems + 1 entries unless the matching *_cnt array is given, in which
- * case n_problems entries suffice.  Keys hold problem-local indices.  row_keys is
+ * case n_problems entries suffice.  Keys hold problem-local train indices + t_index_base (the global
+ * index of every problem's first train row when the train sets are one shard of larger ones; same
+ * base for all problems).  row_keys is
  * (q_rows_total, 2), col_keys (t_rows_total,) or NULL; both are indexed by global row.
  * max_nq / max_nt are host-side upper bounds on any problem's size (they size the grid).
  */
 int slamfe_hamming_top2_batched(const uint8_t *q, int q_stride, const int32_t *q_off, const int32_t *q_cnt,
                                 const uint8_t *t, int t_stride, const int32_t *t_off, const int32_t *t_cnt,
-                                int n_problems, int max_nq, int max_nt, int desc_bytes,
+                                int n_problems, int max_nq, int max_nt, int desc_bytes, int t_index_base,
                                 uint32_t *row_keys, int64_t q_rows_total,
                                 uint32_t *col_keys, int64_t t_rows_total, int flags, slamfe_stream_t stream);
 

@@ -1,0 +1,19 @@
+#!/bin/bash
+# All four bench workloads at N GPUs: gpurun --gpus N --timeout 900 -- 'bash scripts/gpu_scale.sh N'
+set -u
+N=${1:-2}
+for w in sequence ransac loop dense; do
+  if [ "$N" = "1" ]; then
+    python bench.py --workload $w --gpus 1 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/scale_${w}_${N}gpu.json 2> gpurun_out/scale_${w}_${N}gpu.err
+  else
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --workload $w --gpus $N --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/scale_${w}_${N}gpu.json 2> gpurun_out/scale_${w}_${N}gpu.err
+  fi
+  echo "$w rc=$?"
+  python - <<PY
+import json
+try:
+    d=json.loads(open('gpurun_out/scale_${w}_${N}gpu.json').read().strip().splitlines()[-1])
+    print('$w', 'N', d['n_gpus'], 'value', d['value'], d['unit'], 'ms', round(d['ms_per_step'],2), 'e2e', d['e2e']['value'], d['scaling'])
+except Exception as e: print('$w parse failed', e)
+PY
+done

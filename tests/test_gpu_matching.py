@@ -227,3 +227,33 @@ def test_candidate_pairs_vs_oracle(slamfe, oracle, best_only):
             assert (got_i[:, 1] == -1).all()
         else:
             assert np.array_equal(got_i[:, 1], oi[:, 1]) and np.array_equal(got_d[:, 1], od[:, 1]), (i, j)
+
+
+def test_compact_keys_and_batched_index_base(slamfe, oracle):
+    """SLAMFE_MATCH_COMPACT_KEYS (one key per row) and the batched t_index_base (train shards)."""
+    import torch
+    from slamfe import ops, synth
+    rng = np.random.default_rng(43)
+    F, nq, nt = 3, 700, 1040
+    q = np.concatenate([synth.descriptors(rng, nq) for _ in range(F)])
+    t = np.concatenate([synth.paired_descriptors(rng, q[f * nq:(f + 1) * nq], n_out=nt, dup_frac=0.05)[0]
+                        for f in range(F)])
+    qd, td = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    i32 = lambda a: torch.tensor(a, dtype=torch.int32, device="cuda")
+    base, cnt = 512, nt - 512            # second train shard of every frame
+    keys, _ = ops.hamming_top2_batched(qd, i32([f * nq for f in range(F)]), td, i32([f * nt + base for f in range(F)]),
+                                       F, nq, cnt, 61, q_cnt=i32([nq] * F), t_cnt=i32([cnt] * F), t_index_base=base)
+    comp, _ = ops.hamming_top2_batched(qd, i32([f * nq for f in range(F)]), td, i32([f * nt + base for f in range(F)]),
+                                       F, nq, cnt, 61, q_cnt=i32([nq] * F), t_cnt=i32([cnt] * F), t_index_base=base,
+                                       best_only=True, compact=True)
+    assert comp.shape == (F * nq,)
+    ki, kd = ops.keys_to_numpy(keys.cpu().numpy())
+    ci, cd = ops.keys_to_numpy(comp.cpu().numpy())
+    for f in range(F):
+        oi, od = oracle.knn2(q[f * nq:(f + 1) * nq], t[f * nt + base:(f + 1) * nt])
+        sl = slice(f * nq, (f + 1) * nq)
+        assert np.array_equal(ki[sl], oi + base) and np.array_equal(kd[sl], od)
+        assert np.array_equal(ci[sl], oi[:, 0] + base) and np.array_equal(cd[sl], od[:, 0])
+    with pytest.raises(ValueError):
+        ops.hamming_top2_batched(qd, i32([0]), td, i32([0]), 1, nq, nt, 61, q_cnt=i32([nq]), t_cnt=i32([nt]),
+                                 compact=True)

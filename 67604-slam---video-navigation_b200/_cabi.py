@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_int, c_int32, c_int64, c_void_p, POINTER
+from ctypes import c_char_p, c_int, c_int32, c_int64, c_uint64, c_void_p, POINTER
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libslamfe.so")
@@ -47,6 +47,8 @@ _SIGNATURES = {
     "slamfe_ransac_score": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "slamfe_ransac_hypotheses": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                         c_void_p, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "slamfe_peak_kernel": (c_int, [c_int, c_int, c_int, c_int, c_void_p, POINTER(c_int), c_void_p]),
 }
 

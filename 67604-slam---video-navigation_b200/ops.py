@@ -248,6 +248,23 @@ def ransac_score(T, pts, l_pix, r_pix, K, M1, M2, hyp_valid=None, pt_off=None, n
     return counts, best, mask
 
 
+def ransac_hypotheses(pts, l_pix, K, H, seed=0, pt_off=None, pt_cnt=None, n_frames=1, n_hyp=None, sample_idx=None):
+    """Pose hypotheses on the GPU (slamfe_ransac_hypotheses): P3P + 4th-point disambiguation on 4
+    sampled correspondences per hypothesis.  Returns (T (n_frames*H, 3, 4) float64, valid (n_frames*H,)
+    uint8) — directly usable as the T / hyp_valid arguments of ransac_score."""
+    torch = _torch()
+    dev = pts.device
+    pts, l_pix = pts.contiguous(), l_pix.contiguous()
+    T = torch.empty((n_frames * H, 3, 4), dtype=torch.float64, device=dev)
+    valid = torch.empty((n_frames * H,), dtype=torch.uint8, device=dev)
+    Kb = _cabi.host_doubles(K, 9)
+    with torch.cuda.device(dev):
+        check(load_library().slamfe_ransac_hypotheses(
+            ptr(pts), ptr(l_pix), ptr(pt_off), ptr(pt_cnt), pts.shape[0], n_frames, H, ptr(n_hyp), ptr(sample_idx),
+            int(seed) & 0xFFFFFFFFFFFFFFFF, Kb, ptr(T), ptr(valid), stream_handle()), "slamfe_ransac_hypotheses")
+    return T, valid
+
+
 def measure_peak(mode: int, iters: int = 4096, ctas_per_sm: int = 8, block: int = 256):
     """Run a pipe-peak micro-benchmark; returns ops/s (popc/s for modes 0-1, fp64 FMA/s for mode 2)."""
     import ctypes

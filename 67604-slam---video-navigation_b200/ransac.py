@@ -109,12 +109,56 @@ def generate_hypotheses(points_3d, l_pix, n_iter):
     return Ts, ok
 
 
+# Hypothesis generator of the RANSAC entry points below:
+#   "cv2"      host loop with the reference's exact call sequence (np.random.choice + cv2 EPnP):
+#              with the same np.random seed the outputs equal the reference's (default);
+#   "p3p_gpu"  slamfe_ransac_hypotheses: sampling + minimal solver on the GPU, the whole RANSAC stays
+#              on the device.  Different (exact, minimal) solver and RNG, so individual hypotheses
+#              differ from cv2's; the result is statistically equivalent.
+HYPOTHESIS_GENERATOR = "cv2"
+_gpu_seed = [0x5EED]
+
+
+def set_hypothesis_generator(name, seed=None):
+    global HYPOTHESIS_GENERATOR
+    if name not in ("cv2", "p3p_gpu"):
+        raise ValueError("generator must be 'cv2' or 'p3p_gpu'")
+    HYPOTHESIS_GENERATOR = name
+    if seed is not None:
+        _gpu_seed[0] = int(seed)
+
+
+def ransac_device(points_3d, l_pix, r_pix, n_iter, seed=None, sample_idx=None):
+    """Generate n_iter hypotheses on the GPU and score them, one H2D and one D2H.
+    Returns (best_index or -1, best_count, best_mask (N,) bool, T_best (3,4) or None)."""
+    import torch
+    pts = _st.to_device("pts", np.ascontiguousarray(points_3d, dtype=np.float64).reshape(-1, 3))
+    lp = _st.to_device("lp", np.ascontiguousarray(l_pix, dtype=np.float64).reshape(-1, 2))
+    rp = _st.to_device("rp", np.ascontiguousarray(r_pix, dtype=np.float64).reshape(-1, 2))
+    if seed is None:
+        _gpu_seed[0] += 1
+        seed = _gpu_seed[0]
+    si = None if sample_idx is None else _st.to_device("si", np.ascontiguousarray(sample_idx, dtype=np.int32))
+    T, valid = ops.ransac_hypotheses(pts, lp, K, n_iter, seed=seed, sample_idx=si)
+    _, best, mask = ops.ransac_score(T, pts, lp, rp, K, M1, M2, hyp_valid=valid)
+    b = _st.to_host("cb", best.view(-1))
+    mask_h = _st.to_host("mask", mask).astype(bool)
+    bi = int(b[0])
+    Tb = _st.to_host("Tb", T[bi]).copy() if bi >= 0 else None
+    return bi, int(b[1]), mask_h, Tb
+
+
 def ransac_pnp_for_tracking_db(matches_l_l, prev_links, cur_links, inliers_percent):
     """ransac.py:70-113 -> best_matches_idx (int64 array) or None."""
     ransac_iterations = calc_ransac_iteration(inliers_percent)
     points_3d, l_pix, r_pix = _gather(matches_l_l, prev_links, cur_links)
-    Ts, ok = generate_hypotheses(points_3d, l_pix, ransac_iterations)
-    _, best, _, mask = score_hypotheses(Ts, points_3d, l_pix, r_pix, hyp_valid=ok)
+    if HYPOTHESIS_GENERATOR == "p3p_gpu":
+        if len(points_3d) < 4:  # np.random.choice(n < 4, 4, replace=False) raises in the reference
+            raise ValueError("Cannot take a larger sample than population when 'replace=False'")
+        best, _, mask, _ = ransac_device(points_3d, l_pix, r_pix, ransac_iterations)
+    else:
+        Ts, ok = generate_hypotheses(points_3d, l_pix, ransac_iterations)
+        _, best, _, mask = score_hypotheses(Ts, points_3d, l_pix, r_pix, hyp_valid=ok)
     if best < 0:
         return None
     return np.where(mask)[0]
@@ -164,8 +208,13 @@ def ransac_pnp(matches_l_l, prev_links, cur_links, inliers_percent=50):
     import cv2
     ransac_iterations = calc_ransac_iteration(inliers_percent)
     points_3d, l_pix, r_pix = _gather(matches_l_l, prev_links, cur_links)
-    Ts, ok = generate_hypotheses(points_3d, l_pix, ransac_iterations)
-    _, best, best_inliers, mask = score_hypotheses(Ts, points_3d, l_pix, r_pix, hyp_valid=ok)
+    if HYPOTHESIS_GENERATOR == "p3p_gpu":
+        if len(points_3d) < 4:
+            raise ValueError("Cannot take a larger sample than population when 'replace=False'")
+        best, best_inliers, mask, _ = ransac_device(points_3d, l_pix, r_pix, ransac_iterations)
+    else:
+        Ts, ok = generate_hypotheses(points_3d, l_pix, ransac_iterations)
+        _, best, best_inliers, mask = score_hypotheses(Ts, points_3d, l_pix, r_pix, hyp_valid=ok)
     best_matches_idx = np.where(mask)[0] if best >= 0 else []
     if len(best_matches_idx) < 4:
         return None, [], []

@@ -217,6 +217,26 @@ int slamfe_ransac_score(const double *T, const uint8_t *hyp_valid, int H,
                         int32_t *counts, int32_t *best, uint8_t *best_mask, int32_t *work,
                         slamfe_stream_t stream);
 
+/*
+ * RANSAC-PnP hypothesis generation (the host half of the loops ransac.py:94-104, :155-171:
+ * np.random.choice(n, 4) + cv2.solvePnP(EPNP) on the 4 points + rodriguez_to_mat, utils.py:16-18).
+ * One thread per (frame, hypothesis): 4 distinct correspondences of the frame (from `sample_idx`
+ * (n_frames*H, 4) int32 if given, else drawn with a counter-based RNG from `seed`), P3P on the first
+ * three, the fourth picks the pose by left-image reprojection error.  NOT bit-comparable with
+ * OpenCV's EPnP (implementation-defined on 4 points; the reference samples unseeded): exact minimal
+ * solver, pinned against cv2.SOLVEPNP_P3P and ground truth.
+ *   pts (.,3), l_pix (.,2) fp64 DEVICE; frame f owns points [pt_off[f], pt_off[f] + n_f) with
+ *   n_f = pt_cnt ? pt_cnt[f] : pt_off[f+1] - pt_off[f]  (pt_off NULL: one frame of n_points points)
+ *   n_hyp    (n_frames,) int32 DEVICE or NULL: hypotheses wanted for frame f (<= H); the rest of the
+ *            frame's H slots are marked invalid (calc_ransac_iteration differs per frame, ransac.py:59-67)
+ *   T        out (n_frames*H, 12) fp64 row-major [R|t], zero where invalid
+ *   hyp_valid out (n_frames*H,) uint8: 0 = degenerate sample / no admissible pose / fewer than 4 points
+ * The outputs are the T / hyp_valid inputs of slamfe_ransac_score.  K: 9 HOST doubles.
+ */
+int slamfe_ransac_hypotheses(const double *pts, const double *l_pix, const int32_t *pt_off, const int32_t *pt_cnt,
+                             int n_points, int n_frames, int H, const int32_t *n_hyp, const int32_t *sample_idx,
+                             uint64_t seed, const double *K, double *T, uint8_t *hyp_valid, slamfe_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Roofline micro-benchmarks (measure the pipe peaks the matcher / scorer are bound by)
  * ---------------------------------------------------------------------------------------- */

@@ -33,6 +33,57 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+_P3P_LIB_PATH = os.path.join(_HERE, "libp3p_host.so")
+_p3p_lib = None
+
+
+def build_p3p_shim(force: bool = False) -> str:
+    """Compile oracle/p3p_host_shim.cpp (the product's csrc/p3p.cuh solver header, built for the
+    HOST) -> oracle/libp3p_host.so, so that CPU tests can pin the solver's arithmetic."""
+    src = os.path.join(_HERE, "p3p_host_shim.cpp")
+    hdr = os.path.join(os.path.dirname(_HERE), "67604-slam---video-navigation_b200", "csrc", "p3p.cuh")
+    newest = max(os.path.getmtime(src), os.path.getmtime(hdr))
+    if force or not os.path.exists(_P3P_LIB_PATH) or os.path.getmtime(_P3P_LIB_PATH) < newest:
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++", src, "-o",
+                               _P3P_LIB_PATH])
+    return _P3P_LIB_PATH
+
+
+class P3PHost:
+    """ctypes view of the host build of csrc/p3p.cuh (test infrastructure)."""
+
+    def __init__(self):
+        global _p3p_lib
+        if _p3p_lib is None:
+            build_p3p_shim()
+            _p3p_lib = ctypes.CDLL(_P3P_LIB_PATH)
+        self.lib = _p3p_lib
+        self._dp = ctypes.POINTER(ctypes.c_double)
+
+    def solve(self, pts4, pix4, K):
+        """(T (3,4), ok) for one 4-point sample."""
+        T = np.zeros(12)
+        P = np.ascontiguousarray(pts4, dtype=np.float64)
+        uv = np.ascontiguousarray(pix4, dtype=np.float64)
+        Kc = np.ascontiguousarray(K, dtype=np.float64)
+        Ki = np.ascontiguousarray(np.linalg.inv(Kc))
+        ok = self.lib.p3p_host_solve(P.ctypes.data_as(self._dp), uv.ctypes.data_as(self._dp),
+                                     Kc.ctypes.data_as(self._dp), Ki.ctypes.data_as(self._dp),
+                                     T.ctypes.data_as(self._dp))
+        return T.reshape(3, 4), bool(ok)
+
+    def quartic(self, A):
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        r = np.zeros(4)
+        n = self.lib.p3p_host_quartic(A.ctypes.data_as(self._dp), r.ctypes.data_as(self._dp))
+        return r[:n]
+
+    def sample4(self, seed, frame, hyp, n):
+        idx = (ctypes.c_int * 4)()
+        self.lib.p3p_host_sample4(ctypes.c_uint64(seed), ctypes.c_uint32(frame), ctypes.c_uint32(hyp), int(n), idx)
+        return np.array(list(idx), dtype=np.int32)
+
+
 def _load():
     global _lib
     if _lib is None:

@@ -257,3 +257,18 @@ def test_compact_keys_and_batched_index_base(slamfe, oracle):
     with pytest.raises(ValueError):
         ops.hamming_top2_batched(qd, i32([0]), td, i32([0]), 1, nq, nt, 61, q_cnt=i32([nq]), t_cnt=i32([nt]),
                                  compact=True)
+
+
+def test_knn_inner_tuple_lengths(slamfe):
+    """cv2: knnMatch(k=2) against a single train row returns length-1 inner tuples; k=1 likewise."""
+    from slamfe import matching, synth
+    rng = np.random.default_rng(44)
+    q, t = synth.descriptors(rng, 5), synth.descriptors(rng, 1)
+    m = matching.Matcher()
+    knn = m.knnMatch(q, t, k=2)
+    assert len(knn) == 5 and all(len(p) == 1 and p[0].trainIdx == 0 and p[0].queryIdx == i for i, p in enumerate(knn))
+    t3 = synth.descriptors(rng, 3)
+    k1 = m.knnMatch(q, t3, k=1)
+    k2 = m.knnMatch(q, t3, k=2)
+    assert all(len(p) == 1 for p in k1) and all(len(p) == 2 for p in k2)
+    assert [p[0].trainIdx for p in k1] == [p[0].trainIdx for p in k2] == [x.trainIdx for x in m.match(q, t3)]

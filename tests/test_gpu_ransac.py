@@ -153,3 +153,89 @@ def test_borderline_reprojection_errors_take_the_exact_path(slamfe, oracle):
         got = ransac.transformation_agreement(Ts[h], pts, lp, rp)
         assert np.array_equal(got, oracle.transformation_agreement(Ts[h], pts, lp, rp, K, M1, M2)), h
     assert 0 < counts[0] < n                   # the thresholded hypothesis is genuinely split
+
+
+def test_hypothesis_kernel_equals_host_build_of_the_same_solver(slamfe, oracle):
+    """slamfe_ransac_hypotheses with given samples against the HOST build of csrc/p3p.cuh (pinned on
+    the CPU against ground truth and cv2.SOLVEPNP_P3P by tests/test_oracle.py)."""
+    import torch
+    from slamfe import ops, synth
+    host = oracle.P3PHost()
+    rng = np.random.default_rng(91)
+    K, _, _ = synth.cameras()
+    sizes = [700, 3, 60, 1200]           # one frame has too few points for a sample
+    H = 300
+    probs = [synth.pnp_problem(rng, n, 1) for n in sizes]
+    pts = np.concatenate([p[1] for p in probs]); lp = np.concatenate([p[2] for p in probs])
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    samples = np.stack([np.stack([rng.choice(max(n, 4), 4, replace=False) for _ in range(H)]) for n in sizes])
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    T, valid = ops.ransac_hypotheses(dev(pts), dev(lp), K, H, pt_off=dev(off), n_frames=len(sizes),
+                                     sample_idx=dev(samples.reshape(-1, 4).astype(np.int32)))
+    T, valid = T.cpu().numpy().reshape(len(sizes), H, 3, 4), valid.cpu().numpy().reshape(len(sizes), H).astype(bool)
+    assert not valid[1].any() and (T[1] == 0).all()
+    same_flag = close = total = 0
+    for f, n in enumerate(sizes):
+        if n < 4:
+            continue
+        for h in range(H):
+            idx = samples[f, h]
+            Th, okh = host.solve(pts[off[f] + idx], lp[off[f] + idx], K)
+            total += 1
+            same_flag += okh == valid[f, h]
+            if okh and valid[f, h]:
+                close += np.abs(T[f, h] - Th).max() <= 1e-7 * max(1.0, np.abs(Th).max())
+            if not valid[f, h]:
+                assert (T[f, h] == 0).all()
+    assert same_flag >= 0.995 * total and close >= 0.99 * valid.sum() and valid.sum() > 0.9 * total
+
+
+def test_hypothesis_kernel_sampling_and_per_frame_counts(slamfe, oracle):
+    import torch
+    from slamfe import ops, synth
+    host = oracle.P3PHost()
+    rng = np.random.default_rng(92)
+    K, _, _ = synth.cameras()
+    _, pts, lp, _ = synth.pnp_problem(rng, 500, 1)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    off = dev(np.array([0, 200], np.int32)); cnt = dev(np.array([200, 300], np.int32))
+    n_hyp = dev(np.array([64, 17], np.int32))
+    a = ops.ransac_hypotheses(dev(pts), dev(lp), K, 64, seed=11, pt_off=off, pt_cnt=cnt, n_frames=2, n_hyp=n_hyp)
+    b = ops.ransac_hypotheses(dev(pts), dev(lp), K, 64, seed=11, pt_off=off, pt_cnt=cnt, n_frames=2, n_hyp=n_hyp)
+    c = ops.ransac_hypotheses(dev(pts), dev(lp), K, 64, seed=12, pt_off=off, pt_cnt=cnt, n_frames=2, n_hyp=n_hyp)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and not torch.equal(a[0], c[0])
+    T, valid = a[0].cpu().numpy().reshape(2, 64, 3, 4), a[1].cpu().numpy().reshape(2, 64).astype(bool)
+    assert not valid[1, 17:].any() and valid[1, :17].sum() >= 14 and valid[0].sum() >= 55
+    for f, (base, n) in enumerate(((0, 200), (200, 300))):   # the device RNG is the header's sample4
+        for h in range(0, 17, 4):
+            idx = host.sample4(11, f, h, n)
+            Th, okh = host.solve(pts[base + idx], lp[base + idx], K)
+            assert okh == valid[f, h]
+            if okh:
+                assert np.abs(T[f, h] - Th).max() <= 1e-7 * max(1.0, np.abs(Th).max())
+
+
+def test_device_resident_ransac_matches_the_cv2_path_statistically(slamfe, golden, oracle):
+    """ransac_pnp_for_tracking_db with the GPU generator vs the reference-exact cv2 path on the same
+    problem: same inlier set up to RANSAC's own randomness (the reference is unseeded)."""
+    from slamfe import ransac
+    g = golden("ransac")
+    ransac.set_cameras(g["K"], g["M1"], g["M2"])
+    prev = [_Link(*r) for r in g["prev_links"]]
+    cur = [_Link(*r) for r in g["cur_links"]]
+    matches = [_M(i, int(t)) for i, t in enumerate(g["match_t"])]
+    ref_idx = g["tracking_best_idx"]          # the unmodified reference's own (seeded) run
+    try:
+        ransac.set_hypothesis_generator("p3p_gpu", seed=1)
+        got_idx = ransac.ransac_pnp_for_tracking_db(matches, prev, cur, 55)
+        pose, idx2, n_in = ransac.ransac_pnp(matches, prev, cur, inliers_percent=50)
+        with pytest.raises(ValueError):
+            ransac.ransac_pnp_for_tracking_db(matches[:3], prev, cur, 55)
+    finally:
+        ransac.set_hypothesis_generator("cv2")
+    a, b = set(ref_idx.tolist()), set(got_idx.tolist())
+    assert len(a & b) / len(a | b) >= 0.9 and abs(len(a) - len(b)) <= 0.05 * len(a)
+    assert pose is not None and abs(int(n_in) - int(g["pnp_best_inliers"])) <= 0.05 * int(g["pnp_best_inliers"])
+    ref_pose = g["pnp_pose"]
+    assert np.abs(pose.matrix()[:3, 3] - ref_pose[:3, 3]).max() < 0.05   # metres
+    assert np.abs(pose.matrix()[:3, :3] - ref_pose[:3, :3]).max() < 0.01

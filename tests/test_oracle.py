@@ -151,3 +151,115 @@ def test_oracle_vs_reference_shim(oracle):
     mq = np.array([m.queryIdx for m in ms]); mt = np.array([m.trainIdx for m in ms])
     oi, oo = oracle.extract_inliers_outliers(pl, pr, mq, mt)
     assert np.array_equal(inl, oi) and np.array_equal(outl, oo)
+
+
+# ---------------------------------------------------------------------------------------------
+# Minimal-sample pose solver (GPU hypothesis generation): the numpy oracle and the
+# HOST build of the product's solver header are pinned against ground truth and cv2.SOLVEPNP_P3P.
+# ---------------------------------------------------------------------------------------------
+def _pose_samples(rng, n, noise=0.0):
+    from slamfe import synth
+    K, _, _ = synth.cameras()
+    out = []
+    for _ in range(n):
+        z = rng.uniform(4, 60, 4)
+        P = np.stack([(rng.uniform(20, 1220, 4) - K[0, 2]) * z / K[0, 0],
+                      (rng.uniform(5, 370, 4) - K[1, 2]) * z / K[1, 1], z], axis=1)
+        R = synth._rodrigues(rng.normal(0, 0.05, 3))
+        t = np.array([0.0, 0.0, -0.9]) + rng.normal(0, 0.2, 3)
+        C = (R @ P.T).T + t
+        pix = (K @ C.T).T
+        pix = pix[:, :2] / pix[:, 2:3] + rng.normal(0, noise, (4, 2)) if noise else pix[:, :2] / pix[:, 2:3]
+        out.append((P, pix, np.hstack([R, t[:, None]])))
+    return K, out
+
+
+def test_p3p_oracle_vs_ground_truth_and_cv2():
+    import cv2
+    from oracle import p3p_oracle as p3
+    rng = np.random.default_rng(300)
+    K, samples = _pose_samples(rng, 400)
+    gt_ok = cv_ok = cv_n = 0
+    for P, pix, T_gt in samples:
+        T, ok = p3.solve_sample(P, pix, K)
+        assert ok
+        gt_ok += np.abs(T - T_gt).max() < 1e-6
+        s, rv, tv = cv2.solvePnP(P, pix, K, np.zeros((5, 1)), flags=cv2.SOLVEPNP_P3P)
+        if s:
+            cv_n += 1
+            cv_ok += np.abs(T - np.hstack([cv2.Rodrigues(rv)[0], tv])).max() < 1e-5
+    assert gt_ok >= 0.985 * len(samples) and cv_ok >= 0.985 * cv_n and cv_n > 350
+
+
+def test_p3p_host_build_of_product_header(oracle):
+    from oracle import p3p_oracle as p3
+    host = oracle.P3PHost()
+    rng = np.random.default_rng(301)
+    K, samples = _pose_samples(rng, 1500, noise=0.5)
+    both = agree = 0
+    for P, pix, _ in samples:
+        T, ok = host.solve(P, pix, K)
+        To, oko = p3.solve_sample(P, pix, K)
+        if ok and oko:
+            both += 1
+            agree += np.abs(T - To).max() < 1e-6 * max(1.0, np.abs(To).max())
+        if ok:  # a returned pose reproduces the three minimal points exactly and is a rotation
+            c = (T[:, :3] @ P[:3].T).T + T[:, 3]
+            uv = (K @ c.T).T
+            assert np.abs(uv[:, :2] / uv[:, 2:3] - pix[:3]).max() < 1e-3  # px; ill-conditioned samples lose digits
+            assert np.abs(T[:, :3] @ T[:, :3].T - np.eye(3)).max() < 1e-9 and np.linalg.det(T[:, :3]) > 0
+    assert both >= 0.97 * len(samples) and agree >= 0.995 * both
+
+
+def test_quartic_solver_has_no_wrong_roots(oracle):
+    host = oracle.P3PHost()
+    rng = np.random.default_rng(302)
+    missing = 0
+    for _ in range(4000):
+        A = rng.normal(0, 1, 5) * 10 ** rng.uniform(-3, 3, 5)
+        ref = np.roots(A)
+        ref = np.sort(ref[np.abs(ref.imag) < 1e-9 * np.maximum(1, np.abs(ref.real))].real)
+        got = np.sort(host.quartic(A))
+        for g in got:  # every returned root is a true root
+            assert np.min(np.abs(ref - g) / np.maximum(1e-300, np.abs(g))) < 1e-6, (A, g, ref)
+        missing += len(got) < len(ref)
+    assert missing < 0.03 * 4000
+    assert np.allclose(np.sort(host.quartic([1, -10, 35, -50, 24])), [1, 2, 3, 4])
+    assert np.allclose(np.sort(host.quartic([1, 0, -5, 0, 4])), [-2, -1, 1, 2])  # biquadratic branch
+    assert len(host.quartic([1, 0, 2, 0, 5])) == 0
+
+
+def test_sample4_is_a_uniform_distinct_subset(oracle):
+    host = oracle.P3PHost()
+    seen = {}
+    for h in range(8400):
+        s = host.sample4(7, 3, h, 9)
+        assert len(set(s.tolist())) == 4 and s.min() >= 0 and s.max() < 9
+        seen[frozenset(s.tolist())] = seen.get(frozenset(s.tolist()), 0) + 1
+    assert len(seen) == 126 and min(seen.values()) > 30 and max(seen.values()) < 110  # 8400 / 126 = 66.7
+    assert np.array_equal(host.sample4(7, 3, 5, 9), host.sample4(7, 3, 5, 9))
+    assert not np.array_equal(host.sample4(7, 3, 5, 1000), host.sample4(8, 3, 5, 1000))
+    assert sorted(host.sample4(1, 0, 0, 4).tolist()) == [0, 1, 2, 3]
+
+
+def test_ransac_with_minimal_solver_is_statistically_equivalent_to_epnp(oracle):
+    """The contract of the GPU generator: same RANSAC outcome as with cv2 EPnP hypotheses up to the
+    randomness the reference itself has (unseeded sampling): best inlier count within 5 % and the
+    best inlier sets overlap (Jaccard >= 0.9)."""
+    import cv2
+    from slamfe import synth
+    host = oracle.P3PHost()
+    K, M1, M2 = synth.cameras()
+    rng = np.random.default_rng(303)
+    for _ in range(3):
+        _, pts, lp, rp = synth.pnp_problem(rng, 700, 1, outlier_frac=0.4)
+        Te, Tp = [], []
+        for h in range(120):
+            idx = rng.choice(len(pts), 4, replace=False)
+            s, rv, tv = cv2.solvePnP(pts[idx], lp[idx], K, np.zeros((5, 1)), flags=cv2.SOLVEPNP_EPNP)
+            Te.append(np.hstack([cv2.Rodrigues(rv)[0], tv]) if s else np.zeros((3, 4)))
+            Tp.append(host.solve(pts[idx], lp[idx], K)[0])
+        ce, _, me = oracle.score_hypotheses(np.array(Te), pts, lp, rp, K, M1, M2)
+        cp, _, mp = oracle.score_hypotheses(np.array(Tp), pts, lp, rp, K, M1, M2)
+        assert abs(int(ce.max()) - int(cp.max())) <= 0.05 * ce.max()
+        assert (me & mp).sum() / (me | mp).sum() >= 0.9

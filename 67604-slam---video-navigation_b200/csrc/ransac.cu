@@ -40,7 +40,7 @@ struct RansacParams {
     const uint8_t *hyp_valid;
     int H;
     const double *pts, *l_pix, *r_pix;
-    const int32_t *pt_off;
+    const int32_t *pt_off, *pt_cnt;
     int n_points;
     RansacCams cam;
     int32_t *counts, *best, *work;
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_score_kernel(const RansacPa
     const int tid = threadIdx.x, lane = tid & 31;
     const int f = blockIdx.z;
     const int p0 = p.pt_off ? p.pt_off[f] : 0;
-    const int np = p.pt_off ? p.pt_off[f + 1] - p0 : p.n_points;
+    const int np = p.pt_cnt ? p.pt_cnt[f] : (p.pt_off ? p.pt_off[f + 1] - p0 : p.n_points);
     const int h0 = blockIdx.y * RS_HC;
     const int nh = min(RS_HC, p.H - h0);
     const size_t hbase = static_cast<size_t>(f) * p.H;
@@ -269,8 +269,9 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_score_kernel(const RansacPa
 using namespace slamfe;
 
 extern "C" int slamfe_ransac_score(const double *T, const uint8_t *hyp_valid, int H, const double *pts,
-                                   const double *l_pix, const double *r_pix, const int32_t *pt_off, int n_points,
-                                   int n_frames, int max_points, const double *K, const double *M1, const double *M2,
+                                   const double *l_pix, const double *r_pix, const int32_t *pt_off,
+                                   const int32_t *pt_cnt, int n_points, int n_frames, int max_points,
+                                   const double *K, const double *M1, const double *M2,
                                    int32_t *counts, int32_t *best, uint8_t *best_mask, int32_t *work,
                                    slamfe_stream_t stream)
 {
@@ -279,6 +280,7 @@ extern "C" int slamfe_ransac_score(const double *T, const uint8_t *hyp_valid, in
     if (!best || !work || !K || !M1 || !M2) return SLAMFE_EINVAL;
     if (H > 0 && (!T || !counts)) return SLAMFE_EINVAL;
     if (!pt_off && n_frames != 1) return SLAMFE_EINVAL;
+    if (pt_cnt && !pt_off) return SLAMFE_EINVAL;
     if (!pt_off) max_points = n_points;
     if (max_points > 0 && (!pts || !l_pix || !r_pix || !best_mask)) return SLAMFE_EINVAL;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -286,7 +288,7 @@ extern "C" int slamfe_ransac_score(const double *T, const uint8_t *hyp_valid, in
     if (H > 0) SLAMFE_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * static_cast<size_t>(n_frames) * H, s));
     RansacParams p{};
     p.T = T; p.hyp_valid = hyp_valid; p.H = H;
-    p.pts = pts; p.l_pix = l_pix; p.r_pix = r_pix; p.pt_off = pt_off; p.n_points = n_points;
+    p.pts = pts; p.l_pix = l_pix; p.r_pix = r_pix; p.pt_off = pt_off; p.pt_cnt = pt_cnt; p.n_points = n_points;
     for (int k = 0; k < 9; ++k) p.cam.K[k] = K[k];
     for (int k = 0; k < 12; ++k) { p.cam.M1[k] = M1[k]; p.cam.M2[k] = M2[k]; }
     p.counts = counts; p.best = best; p.work = work; p.best_mask = best_mask;

@@ -141,8 +141,11 @@ class FrontEnd:
         from . import utils
         self.P = utils.P if P is None else np.asarray(P, dtype=np.float64)
         self.Q = utils.Q if Q is None else np.asarray(Q, dtype=np.float64)
+        self.K, self.M1, self.M2 = utils.K, utils.M1, utils.M2
         self._out = None
         self._key = None
+        self._trk = None
+        self._trk_key = None
         self._in = None
         self._in_key = None
         self._pinned_out = None
@@ -208,6 +211,56 @@ class FrontEnd:
                              F - 1, max_links, o["fwd_keys"], o["bwd_keys"])
             self.last_launches += 1
         return o
+
+    # -- stages 5-8: the rest of the create_db loop body (database.py:54-85), device resident -----
+    def _track_buffers(self, L, F, h_max, dev):
+        torch = _cabi.require_cuda()
+        key = (L, F, h_max, dev)
+        if self._trk_key != key:
+            i32 = dict(dtype=torch.int32, device=dev)
+            f64 = dict(dtype=torch.float64, device=dev)
+            n = max(F - 1, 1)
+            self._trk = {
+                "good_j": torch.empty((L,), **i32), "good_t": torch.empty((L,), **i32),
+                "n_good": torch.empty((n,), **i32), "n_hyp": torch.empty((n,), **i32),
+                "pts": torch.empty((L, 3), **f64), "lpix": torch.empty((L, 2), **f64),
+                "rpix": torch.empty((L, 2), **f64),
+                "T": torch.empty((n * h_max, 3, 4), **f64), "hyp_valid": torch.empty((n * h_max,), dtype=torch.uint8,
+                                                                                     device=dev),
+                "counts": torch.empty((n, h_max), **i32), "best": torch.empty((n, 2), **i32),
+                "best_mask": torch.empty((L,), dtype=torch.uint8, device=dev), "work": torch.empty((n,), **i32),
+                "inlier_fwd": torch.empty((L,), dtype=torch.uint8, device=dev),
+            }
+            self._trk_key = key
+        return self._trk
+
+    def track(self, ds: DeviceSequence, h_max=256, seed=1):
+        """run(ds) followed by the frame-to-frame tracking of database.py:54-85 for every consecutive
+        pair, without leaving the device: mutual forward/backward check + link gather + fp64
+        triangulation of the previous links (slamfe_track_gather), RANSAC-PnP hypothesis generation
+        (slamfe_ransac_hypotheses; per-pair iteration count from calc_ransac_iteration, capped at
+        h_max), scoring of all hypotheses of all pairs in one launch (slamfe_ransac_score) and the
+        inlier flags per forward match (in_prev_cur, database.py:84-85).  Returns the output dict of
+        run() extended with good_j, good_t, n_good, n_hyp, pts, lpix, rpix, T, hyp_valid, counts, best,
+        best_mask, inlier_fwd."""
+        o = self.run(ds)
+        F = ds.n_frames
+        L = ds.desc_l.shape[0]
+        t = self._track_buffers(L, F, h_max, ds.desc_l.device)
+        out = dict(o)
+        out.update(t)
+        if F < 2:
+            return out
+        n = F - 1
+        ops.track_gather(o, ds.l_off, ds.r_off, ds.pts_l, ds.pts_r, n, self.P, self.Q, h_max, t)
+        ops.ransac_hypotheses(t["pts"], t["lpix"], self.K, h_max, seed=seed, pt_off=ds.l_off, pt_cnt=t["n_good"],
+                              n_frames=n, n_hyp=t["n_hyp"], out=(t["T"], t["hyp_valid"]))
+        ops.ransac_score(t["T"], t["pts"], t["lpix"], t["rpix"], self.K, self.M1, self.M2, hyp_valid=t["hyp_valid"],
+                         pt_off=ds.l_off, pt_cnt=t["n_good"], n_frames=n, max_points=min(ds.max_nl, ds.max_nr),
+                         out=t)
+        ops.scatter_inliers(t["best_mask"], t["good_j"], ds.l_off, t["n_good"], t["best"], n, t["inlier_fwd"])
+        self.last_launches += 4
+        return out
 
     # -- host in, host out ---------------------------------------------------------------------
     def _input_buffers(self, seq: PackedSequence, dev):

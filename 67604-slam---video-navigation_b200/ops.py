@@ -221,7 +221,8 @@ def same_rows_stereo(P, Q) -> bool:
     return bool(np.array_equal(P[1:], Q[1:]))
 
 
-def ransac_score(T, pts, l_pix, r_pix, K, M1, M2, hyp_valid=None, pt_off=None, n_frames=1, max_points=None):
+def ransac_score(T, pts, l_pix, r_pix, K, M1, M2, hyp_valid=None, pt_off=None, n_frames=1, max_points=None,
+                 pt_cnt=None, out=None):
     """All hypotheses x all correspondences (x all frames) in one launch.
 
     T (n_frames*H, 3, 4) or (n_frames, H, 3, 4) float64; pts (Ntot, 3), l_pix / r_pix (Ntot, 2)
@@ -236,33 +237,65 @@ def ransac_score(T, pts, l_pix, r_pix, K, M1, M2, hyp_valid=None, pt_off=None, n
     n_tot = pts.shape[0]
     if max_points is None:
         max_points = n_tot
-    counts = torch.empty((n_frames, H), dtype=torch.int32, device=dev)
-    best = torch.empty((n_frames, 2), dtype=torch.int32, device=dev)
-    mask = torch.empty((n_tot,), dtype=torch.uint8, device=dev)
-    work = torch.empty((n_frames,), dtype=torch.int32, device=dev)
+    if out is None:
+        out = {}
+    counts = out.get("counts")
+    if counts is None or counts.shape != (n_frames, H):
+        counts = torch.empty((n_frames, H), dtype=torch.int32, device=dev)
+    best = out.get("best", torch.empty((n_frames, 2), dtype=torch.int32, device=dev))
+    mask = out.get("best_mask", torch.empty((n_tot,), dtype=torch.uint8, device=dev))
+    work = out.get("work", torch.empty((n_frames,), dtype=torch.int32, device=dev))
     Kb, M1b, M2b = _cabi.host_doubles(K, 9), _cabi.host_doubles(M1, 12), _cabi.host_doubles(M2, 12)
     with torch.cuda.device(dev):
         check(load_library().slamfe_ransac_score(
-            ptr(T), ptr(hyp_valid), H, ptr(pts), ptr(l_pix), ptr(r_pix), ptr(pt_off), n_tot, n_frames, max_points,
+            ptr(T), ptr(hyp_valid), H, ptr(pts), ptr(l_pix), ptr(r_pix), ptr(pt_off), ptr(pt_cnt), n_tot, n_frames,
+            max_points,
             Kb, M1b, M2b, ptr(counts), ptr(best), ptr(mask), ptr(work), stream_handle()), "slamfe_ransac_score")
     return counts, best, mask
 
 
-def ransac_hypotheses(pts, l_pix, K, H, seed=0, pt_off=None, pt_cnt=None, n_frames=1, n_hyp=None, sample_idx=None):
+def ransac_hypotheses(pts, l_pix, K, H, seed=0, pt_off=None, pt_cnt=None, n_frames=1, n_hyp=None, sample_idx=None,
+                      out=None):
     """Pose hypotheses on the GPU (slamfe_ransac_hypotheses): P3P + 4th-point disambiguation on 4
     sampled correspondences per hypothesis.  Returns (T (n_frames*H, 3, 4) float64, valid (n_frames*H,)
     uint8) — directly usable as the T / hyp_valid arguments of ransac_score."""
     torch = _torch()
     dev = pts.device
     pts, l_pix = pts.contiguous(), l_pix.contiguous()
-    T = torch.empty((n_frames * H, 3, 4), dtype=torch.float64, device=dev)
-    valid = torch.empty((n_frames * H,), dtype=torch.uint8, device=dev)
+    if out is not None:
+        T, valid = out
+    else:
+        T = torch.empty((n_frames * H, 3, 4), dtype=torch.float64, device=dev)
+        valid = torch.empty((n_frames * H,), dtype=torch.uint8, device=dev)
     Kb = _cabi.host_doubles(K, 9)
     with torch.cuda.device(dev):
         check(load_library().slamfe_ransac_hypotheses(
             ptr(pts), ptr(l_pix), ptr(pt_off), ptr(pt_cnt), pts.shape[0], n_frames, H, ptr(n_hyp), ptr(sample_idx),
             int(seed) & 0xFFFFFFFFFFFFFFFF, Kb, ptr(T), ptr(valid), stream_handle()), "slamfe_ransac_hypotheses")
     return T, valid
+
+
+def track_gather(o, ds_l_off, ds_r_off, pts_left, pts_right, n_pairs, P, Q, h_max, out):
+    """slamfe_track_gather on the pipeline tables `o` (FrontEnd buffers); fills out[good_j, good_t,
+    n_good, n_hyp, pts, lpix, rpix]."""
+    torch = _torch()
+    Pb, Qb = _cabi.host_doubles(P, 12), _cabi.host_doubles(Q, 12)
+    with torch.cuda.device(pts_left.device):
+        check(load_library().slamfe_track_gather(
+            ptr(o["fwd_keys"]), ptr(o["bwd_keys"]), ptr(ds_l_off), ptr(ds_r_off), ptr(o["n_links"]),
+            ptr(o["n_matches"]), ptr(pts_left), ptr(pts_right), ptr(o["link_src"]), ptr(o["match_t"]), n_pairs,
+            Pb, Qb, int(h_max), ptr(out["good_j"]), ptr(out["good_t"]), ptr(out["n_good"]), ptr(out["n_hyp"]),
+            ptr(out["pts"]), ptr(out["lpix"]), ptr(out["rpix"]), stream_handle()), "slamfe_track_gather")
+    return out
+
+
+def scatter_inliers(best_mask, good_j, l_off, n_good, best, n_pairs, inlier_fwd):
+    torch = _torch()
+    with torch.cuda.device(inlier_fwd.device):
+        check(load_library().slamfe_scatter_inliers(ptr(best_mask), ptr(good_j), ptr(l_off), ptr(n_good), ptr(best),
+                                                    n_pairs, ptr(inlier_fwd), inlier_fwd.numel(), stream_handle()),
+              "slamfe_scatter_inliers")
+    return inlier_fwd
 
 
 def measure_peak(mode: int, iters: int = 4096, ctas_per_sm: int = 8, block: int = 256):

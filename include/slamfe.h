@@ -200,7 +200,9 @@ int slamfe_triangulate_dlt_f64(const double *pxy, const double *qxy, int64_t n,
  * loops ransac.py:94-112 and :155-182), batched over `n_frames` independent problems in ONE
  * launch.  Frame f owns hypotheses T[f*H .. f*H+H) (each 3x4 row-major fp64), and points
  * [pt_off[f], pt_off[f+1]) of pts (.,3) / l_pix (.,2) / r_pix (.,2) (fp64).  pt_off is a DEVICE
- * int32 array of n_frames + 1 entries, or NULL when n_frames == 1 (then n_points is used).
+ * int32 array of n_frames + 1 entries, or NULL when n_frames == 1 (then n_points is used); with
+ * pt_cnt (n_frames,) the frame's point count is pt_cnt[f] instead of the offset difference (ragged
+ * tables with per-frame capacity, as slamfe_track_gather writes them; pt_off then needs n_frames entries).
  *   hyp_valid  (n_frames*H,) uint8 or NULL: 0 = hypothesis skipped (solvePnP failed, ransac.py:101-104)
  *   counts     out (n_frames*H,) int32: inlier count per hypothesis (np.sum, ransac.py:109)
  *   best       out (n_frames, 2) int32: [index of the first hypothesis with the largest count
@@ -212,10 +214,45 @@ int slamfe_triangulate_dlt_f64(const double *pxy, const double *qxy, int64_t n,
  */
 int slamfe_ransac_score(const double *T, const uint8_t *hyp_valid, int H,
                         const double *pts, const double *l_pix, const double *r_pix,
-                        const int32_t *pt_off, int n_points, int n_frames, int max_points,
+                        const int32_t *pt_off, const int32_t *pt_cnt, int n_points, int n_frames, int max_points,
                         const double *K, const double *M1, const double *M2,
                         int32_t *counts, int32_t *best, uint8_t *best_mask, int32_t *work,
                         slamfe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Frame-to-frame tracking glue (the create_db loop body, backend/database/database.py:48-87)
+ * ---------------------------------------------------------------------------------------- */
+
+/*
+ * For every consecutive frame pair (f, f+1), f < n_pairs, from the tables of the sequence pipeline
+ * (slamfe_hamming_top2_batched on the compacted features + slamfe_stereo_links_batched):
+ *   - mutual forward/backward check (database.py:67-77): forward match j kept iff
+ *     bwd[fwd[j]] == j; kept matches in ascending j (== good_idx);
+ *   - link gather + pixel arrays (ransac.py:76-81, :85-88) and fp64 triangulation of the previous
+ *     frame's links (ransac.py:83) from the exact Link values (x float32, y = (yl+yr)/2 in double);
+ *   - n_hyp[f] = min(h_max, calc_ransac_iteration(100 * n_links[f+1] / n_matches[f+1]))
+ *     (ransac.py:59-67, database.py:26,80).
+ * Row-indexed outputs use frame f's row offset l_off[f] as base and hold n_good[f] entries:
+ *   good_j, good_t (L,) int32 link indices in frame f / f+1;  pts (L,3), lpix (L,2), rpix (L,2) fp64.
+ * They are the pts / l_pix / r_pix (pt_off = l_off, pt_cnt = n_good) of slamfe_ransac_hypotheses and
+ * slamfe_ransac_score.  P, Q: HOST 3x4 (shared rows 1, 2 as for slamfe_triangulate_links_*).
+ */
+int slamfe_track_gather(const uint32_t *fwd_keys, const uint32_t *bwd_keys, const int32_t *l_off, const int32_t *r_off,
+                        const int32_t *n_links, const int32_t *n_matches, const float *pts_left,
+                        const float *pts_right, const int32_t *link_src, const int32_t *match_t, int n_pairs,
+                        const double *P, const double *Q, int h_max, int32_t *good_j, int32_t *good_t,
+                        int32_t *n_good, int32_t *n_hyp, double *pts, double *lpix, double *rpix,
+                        slamfe_stream_t stream);
+
+/*
+ * in_prev_cur of database.py:84-85: inlier_fwd[l_off[f] + good_j[k]] = 1 for the mutual matches k of
+ * pair f that the best hypothesis accepts (best_mask from slamfe_ransac_score), 0 elsewhere
+ * (rows_total bytes are cleared first).  When no hypothesis scored > 0 inliers (best[f][0] < 0) every
+ * mutual match is flagged, as good_idx[None] does in the reference (database.py:82).
+ */
+int slamfe_scatter_inliers(const uint8_t *best_mask, const int32_t *good_j, const int32_t *l_off,
+                           const int32_t *n_good, const int32_t *best, int n_pairs, uint8_t *inlier_fwd,
+                           int64_t rows_total, slamfe_stream_t stream);
 
 /*
  * RANSAC-PnP hypothesis generation (the host half of the loops ransac.py:94-104, :155-171:

@@ -68,5 +68,5 @@ def test_argument_errors_do_not_need_a_gpu(slamfe):
     Q = (ctypes.c_double * 12)(*[v + (1 if i >= 4 else 0) for i, v in enumerate(range(12))])
     # rows 1-2 of P and Q differ: the links entry point refuses (general DLT must be used)
     assert lib.slamfe_triangulate_links_f64(p, 4, P, Q, p, None) == EINVAL
-    assert lib.slamfe_ransac_score(None, None, 4, p, p, p, None, 5, 1, 5, None, None, None, p, p, p, p, None) == EINVAL
+    assert lib.slamfe_ransac_score(None, None, 4, p, p, p, None, None, 5, 1, 5, None, None, None, p, p, p, p, None) == EINVAL
     assert lib.slamfe_peak_kernel(9, 0, 1, 1, p, None, 0, None) == EINVAL

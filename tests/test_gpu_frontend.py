@@ -106,3 +106,63 @@ def test_patch_rebinds_reference_style_modules(slamfe):
     assert callable(mods["final_project.algorithms.ransac"].transformation_agreement)
     patch.unpatch(tok)
     assert mods["final_project.algorithms.ransac"].transformation_agreement == "reference"
+
+
+def test_tracking_stages_vs_oracle(slamfe, oracle):
+    """FrontEnd.track: mutual check, link gather, fp64 triangulation, per-pair iteration counts and the
+    scoring of the device-generated hypotheses, against the oracle's restatement of
+    database.py:54-85 / ransac.py:59-113 on the same frames."""
+    from slamfe import frontend, ransac, utils
+    rng = np.random.default_rng(73)
+    frames = make_sequence(rng, [800, 1000, 30, 1200, 700])
+    seq = frontend.pack_sequence(frames)
+    ds = frontend.to_device(seq)
+    fe = frontend.FrontEnd()
+    H = 48
+    out = fe.track(ds, h_max=H, seed=5)
+    out = fe.track(ds, h_max=H, seed=5)      # buffers reused
+    g = {k: v.cpu().numpy() for k, v in out.items() if k in ("good_j", "good_t", "n_good", "n_hyp", "pts", "lpix", "rpix", "T",
+                                                            "hyp_valid", "counts", "best", "best_mask", "inlier_fwd",
+                                                            "n_links", "n_matches")}
+    feats, links = [], []
+    for dl, dr, pl, pr in frames:
+        cq, ct, _ = oracle.match_crosscheck(dl, dr)
+        inl, _ = oracle.extract_inliers_outliers(pl, pr, cq, ct)
+        valid, ln = oracle.create_links(pl, pr, cq[inl], ct[inl])
+        feats.append(dl[valid]); links.append(np.asarray(ln, dtype=np.float64).reshape(-1, 3))
+    K, M1, M2 = utils.K, utils.M1, utils.M2
+    for f in range(len(frames) - 1):
+        lo = seq.l_off[f]
+        fi, fd, good = oracle.mutual_forward_backward(feats[f], feats[f + 1])
+        n = len(good)
+        assert g["n_good"][f] == n
+        assert np.array_equal(g["good_j"][lo:lo + n], good) and np.array_equal(g["good_t"][lo:lo + n], fi[good])
+        cur = links[f + 1][fi[good]]
+        assert np.array_equal(g["lpix"][lo:lo + n], cur[:, [0, 2]]) and np.array_equal(g["rpix"][lo:lo + n], cur[:, [1, 2]])
+        if n:
+            ref = oracle.triangulate_links(links[f][good], ransac.P, ransac.Q)
+            rel = np.linalg.norm(g["pts"][lo:lo + n] - ref, axis=1) / np.linalg.norm(ref, axis=1)
+            assert rel.max() < 1e-11
+        pct = 100 * (g["n_links"][f + 1] / g["n_matches"][f + 1])
+        assert g["n_hyp"][f] == min(H, ransac.calc_ransac_iteration(pct))
+        # scoring of the generated hypotheses: bit-exact against the oracle on the same T and points
+        T = g["T"][f * H:(f + 1) * H]; ok = g["hyp_valid"][f * H:(f + 1) * H].astype(bool)
+        assert not ok[g["n_hyp"][f]:].any()
+        if n >= 4:
+            assert ok[:g["n_hyp"][f]].sum() >= 0.4 * g["n_hyp"][f]  # random geometry: many samples admit no pose
+        pts, lp, rp = g["pts"][lo:lo + n], g["lpix"][lo:lo + n], g["rpix"][lo:lo + n]
+        counts = np.zeros(H, np.int64)
+        masks = {}
+        for h in np.nonzero(ok)[0]:
+            masks[h] = oracle.transformation_agreement(T[h], pts, lp, rp, K, M1, M2)
+            counts[h] = masks[h].sum()
+        assert np.array_equal(g["counts"][f], counts)
+        best = int(np.argmax(counts)) if counts.max() > 0 else -1
+        assert g["best"][f, 0] == best and g["best"][f, 1] == counts.max()
+        flags = np.zeros(len(feats[f]), np.uint8)
+        if best >= 0:
+            assert np.array_equal(g["best_mask"][lo:lo + n].astype(bool), masks[best])
+            flags[good[masks[best]]] = 1
+        else:
+            flags[good] = 1                     # good_idx[None] quirk, database.py:82
+        assert np.array_equal(g["inlier_fwd"][lo:lo + len(feats[f])], flags)

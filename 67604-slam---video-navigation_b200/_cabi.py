@@ -50,7 +50,7 @@ _SIGNATURES = {
     "slamfe_track_gather": (c_int, [c_void_p] * 10 + [c_int, c_void_p, c_void_p, c_int] + [c_void_p] * 8),
     "slamfe_scatter_inliers": (c_int, [c_void_p] * 5 + [c_int, c_void_p, c_int64, c_void_p]),
     "slamfe_ransac_hypotheses": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
-                                         c_void_p, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                         c_void_p, c_uint64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "slamfe_peak_kernel": (c_int, [c_int, c_int, c_int, c_int, c_void_p, POINTER(c_int), c_void_p]),
 }
 

@@ -20,6 +20,7 @@ struct GenParams {
     const int32_t *sample_idx;
     const int32_t *n_hyp;  // per-frame number of hypotheses to generate (<= H), or null = H
     unsigned long long seed;
+    int frame_base;  // global index of frame 0 of this launch (RNG stream id)
     double K[9], Kinv[9];
     double *T;
     uint8_t *valid;
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(GEN_THREADS) ransac_hypotheses_kernel(const Ge
 #pragma unroll
             for (int k = 0; k < 4; ++k) ok = ok && idx[k] >= 0 && idx[k] < np;
         } else {
-            p3p::sample4(p.seed, static_cast<uint32_t>(f), static_cast<uint32_t>(h), np, idx);
+            p3p::sample4(p.seed, static_cast<uint32_t>(p.frame_base + f), static_cast<uint32_t>(h), np, idx);
         }
         if (ok) {
             p3p::Vec3 P[4];
@@ -91,7 +92,8 @@ using namespace slamfe;
 extern "C" int slamfe_ransac_hypotheses(const double *pts, const double *l_pix, const int32_t *pt_off,
                                         const int32_t *pt_cnt, int n_points, int n_frames, int H,
                                         const int32_t *n_hyp, const int32_t *sample_idx, uint64_t seed,
-                                        const double *K, double *T, uint8_t *hyp_valid, slamfe_stream_t stream)
+                                        int frame_index_base, const double *K, double *T, uint8_t *hyp_valid,
+                                        slamfe_stream_t stream)
 {
     if (H < 0 || n_frames < 0 || n_points < 0) return SLAMFE_EINVAL;
     if (H == 0 || n_frames == 0) return 0;
@@ -100,7 +102,8 @@ extern "C" int slamfe_ransac_hypotheses(const double *pts, const double *l_pix, 
     if (pt_cnt && !pt_off) return SLAMFE_EINVAL;
     GenParams p{};
     p.pts = pts; p.l_pix = l_pix; p.pt_off = pt_off; p.pt_cnt = pt_cnt; p.n_points = n_points; p.H = H;
-    p.sample_idx = sample_idx; p.n_hyp = n_hyp; p.seed = seed; p.T = T; p.valid = hyp_valid;
+    p.sample_idx = sample_idx; p.n_hyp = n_hyp; p.seed = seed; p.frame_base = frame_index_base; p.T = T;
+    p.valid = hyp_valid;
     for (int k = 0; k < 9; ++k) p.K[k] = K[k];
     if (!invert3(K, p.Kinv)) return SLAMFE_EINVAL;
     const dim3 grid((H + GEN_THREADS - 1) / GEN_THREADS, n_frames);

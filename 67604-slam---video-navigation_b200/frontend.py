@@ -126,6 +126,7 @@ def to_device(seq: PackedSequence, device="cuda", non_blocking=True) -> DeviceSe
 
 
 RESULT_KEYS = ("match_t", "n_matches", "n_links", "link_src", "links", "xyz", "fwd_keys", "bwd_keys")
+TRACK_KEYS = ("inlier_fwd", "best", "n_good", "n_hyp")
 
 
 class FrontEnd:
@@ -234,6 +235,17 @@ class FrontEnd:
             self._trk_key = key
         return self._trk
 
+    def _track_stages(self, o, t, l_off, r_off, pts_l, pts_r, n_pairs, max_links, h_max, seed, pair_base=0):
+        """Stages 5-8 for n_pairs consecutive pairs; o / t hold (views of) the pipeline and tracking
+        tables whose row 0 is the first row of the first pair's previous frame."""
+        ops.track_gather(o, l_off, r_off, pts_l, pts_r, n_pairs, self.P, self.Q, h_max, t)
+        ops.ransac_hypotheses(t["pts"], t["lpix"], self.K, h_max, seed=seed, pt_off=l_off, pt_cnt=t["n_good"],
+                              n_frames=n_pairs, n_hyp=t["n_hyp"], out=(t["T"], t["hyp_valid"]),
+                              frame_index_base=pair_base)
+        ops.ransac_score(t["T"], t["pts"], t["lpix"], t["rpix"], self.K, self.M1, self.M2, hyp_valid=t["hyp_valid"],
+                         pt_off=l_off, pt_cnt=t["n_good"], n_frames=n_pairs, max_points=max_links, out=t)
+        ops.scatter_inliers(t["best_mask"], t["good_j"], l_off, t["n_good"], t["best"], n_pairs, t["inlier_fwd"])
+
     def track(self, ds: DeviceSequence, h_max=256, seed=1):
         """run(ds) followed by the frame-to-frame tracking of database.py:54-85 for every consecutive
         pair, without leaving the device: mutual forward/backward check + link gather + fp64
@@ -251,14 +263,7 @@ class FrontEnd:
         out.update(t)
         if F < 2:
             return out
-        n = F - 1
-        ops.track_gather(o, ds.l_off, ds.r_off, ds.pts_l, ds.pts_r, n, self.P, self.Q, h_max, t)
-        ops.ransac_hypotheses(t["pts"], t["lpix"], self.K, h_max, seed=seed, pt_off=ds.l_off, pt_cnt=t["n_good"],
-                              n_frames=n, n_hyp=t["n_hyp"], out=(t["T"], t["hyp_valid"]))
-        ops.ransac_score(t["T"], t["pts"], t["lpix"], t["rpix"], self.K, self.M1, self.M2, hyp_valid=t["hyp_valid"],
-                         pt_off=ds.l_off, pt_cnt=t["n_good"], n_frames=n, max_points=min(ds.max_nl, ds.max_nr),
-                         out=t)
-        ops.scatter_inliers(t["best_mask"], t["good_j"], ds.l_off, t["n_good"], t["best"], n, t["inlier_fwd"])
+        self._track_stages(o, t, ds.l_off, ds.r_off, ds.pts_l, ds.pts_r, F - 1, min(ds.max_nl, ds.max_nr), h_max, seed)
         self.last_launches += 4
         return out
 
@@ -278,11 +283,14 @@ class FrontEnd:
             self._pinned_out = None
         return self._in
 
-    def run_host(self, seq: PackedSequence, chunk_frames=576, device="cuda", keys=RESULT_KEYS):
+    def run_host(self, seq: PackedSequence, chunk_frames=576, device="cuda", keys=RESULT_KEYS, track=False,
+                 h_max=256, seed=1):
         """Pinned host inputs -> pinned host result tables, copies overlapped with the kernels.
 
         Returns (dict of numpy views of the pinned result tables, h2d_bytes, d2h_bytes).  The call
-        returns after the last table has landed in host memory."""
+        returns after the last table has landed in host memory.  track=True adds the tracking stages
+        of track() per chunk and the tables TRACK_KEYS (inlier flags per forward match, best
+        hypothesis / inlier count and mutual-match count per pair)."""
         torch = _cabi.require_cuda()
         if seq.tensors is None:
             raise ValueError("run_host needs a pinned PackedSequence (pack_sequence(..., pin=True))")
@@ -293,8 +301,14 @@ class FrontEnd:
         L, R = seq.desc_l.shape[0], seq.desc_r.shape[0]
         din = self._input_buffers(seq, dev)
         o = self._buffers(L, R, F, dev)
-        if self._pinned_out is None:
-            self._pinned_out = {k: torch.empty(o[k].shape, dtype=o[k].dtype, pin_memory=True) for k in RESULT_KEYS}
+        trk = self._track_buffers(L, F, h_max, dev) if track else None
+        if track:
+            keys = tuple(keys) + tuple(k for k in TRACK_KEYS if k not in keys)
+            o = dict(o)
+            o.update(trk)
+        if self._pinned_out is None or any(k not in self._pinned_out or self._pinned_out[k].shape != o[k].shape
+                                           for k in keys):
+            self._pinned_out = {k: torch.empty(o[k].shape, dtype=o[k].dtype, pin_memory=True) for k in keys}
         hout = self._pinned_out
         if self._streams is None:
             self._streams = tuple(torch.cuda.Stream(device=dev) for _ in range(4))
@@ -312,7 +326,8 @@ class FrontEnd:
             f0, f1 = bounds[c], bounds[c + 1]
             p0 = max(f0 - 1, 0)
             tabs = (l_off[f0:f1 + 1] - l_off[f0], r_off[f0:f1 + 1] - r_off[f0],
-                    l_off[p0:f1 - 1] - l_off[p0], l_off[p0 + 1:f1] - l_off[p0 + 1])
+                    l_off[p0:f1 - 1] - l_off[p0], l_off[p0 + 1:f1] - l_off[p0 + 1],
+                    l_off[p0:f1] - l_off[p0], r_off[p0:f1] - r_off[p0])
             loc = []
             for t in tabs:
                 loc.append((pos, pos + len(t)))
@@ -346,7 +361,7 @@ class FrontEnd:
                     h2d += src.numel() * src.element_size()
                 ev_in = torch.cuda.Event()
                 ev_in.record(s_in)
-            (l0, l1), (r0, r1), (q0, q1), (t0, t1) = index[c]
+            (l0, l1), (r0, r1), (q0, q1), (t0, t1), (lp0, lp1), (rp0, rp1) = index[c]
             with torch.cuda.stream(s_cmp):
                 s_cmp.wait_event(ev_in)
                 view = {k: o[k][a:b] for k in ("lr_row_keys", "match_t", "link_src", "links", "feat", "xyz")}
@@ -370,8 +385,23 @@ class FrontEnd:
                                      o["feat"][ta:b], small_dev[t0:t1], o["n_links"][p0 + 1:f1],
                                      n_pairs, max_links, o["fwd_keys"][qa:qb], o["bwd_keys"][ta:b])
                     self.last_launches += 1
+                    if track:  # rows / frames based at frame p0; pairs p0 .. f1-2
+                        ra0 = int(r_off[p0])
+                        ov = {"fwd_keys": o["fwd_keys"][qa:b], "bwd_keys": o["bwd_keys"][qa:b],
+                              "n_links": o["n_links"][p0:f1], "n_matches": o["n_matches"][p0:f1],
+                              "link_src": o["link_src"][qa:b], "match_t": o["match_t"][qa:b]}
+                        tv = {k: trk[k][qa:qb] for k in ("good_j", "good_t", "pts", "lpix", "rpix", "best_mask",
+                                                         "inlier_fwd")}
+                        tv.update({k: trk[k][p0:f1 - 1] for k in ("n_good", "n_hyp", "counts", "best", "work")})
+                        tv["T"] = trk["T"][p0 * h_max:(f1 - 1) * h_max]
+                        tv["hyp_valid"] = trk["hyp_valid"][p0 * h_max:(f1 - 1) * h_max]
+                        self._track_stages(ov, tv, small_dev[lp0:lp1], small_dev[rp0:rp1], din["pts_l"][qa:b],
+                                           din["pts_r"][ra0:rb], n_pairs, max_links, h_max, seed, pair_base=p0)
+                        self.last_launches += 4
                 if f1 == F:  # the last frame has no successor, frame 0 no predecessor
                     o["fwd_keys"][int(l_off[F - 1]):].fill_(-1)
+                    if track:
+                        trk["inlier_fwd"][int(l_off[F - 1]):].zero_()
                 if f0 == 0:
                     o["bwd_keys"][:int(l_off[1])].fill_(-1)
                 ev_cmp = torch.cuda.Event()
@@ -384,7 +414,9 @@ class FrontEnd:
                 for k in keys:
                     if k in ("n_matches", "n_links"):
                         lo, hi = f0, f1
-                    elif k == "fwd_keys":
+                    elif k in ("best", "n_good", "n_hyp"):        # per pair: pairs p0 .. f1-2
+                        lo, hi = max(f0 - 1, 0), f1 - 1
+                    elif k in ("fwd_keys", "inlier_fwd"):
                         lo, hi = fa, fb
                     else:
                         lo, hi = a, b

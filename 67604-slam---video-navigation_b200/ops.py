@@ -255,7 +255,7 @@ def ransac_score(T, pts, l_pix, r_pix, K, M1, M2, hyp_valid=None, pt_off=None, n
 
 
 def ransac_hypotheses(pts, l_pix, K, H, seed=0, pt_off=None, pt_cnt=None, n_frames=1, n_hyp=None, sample_idx=None,
-                      out=None):
+                      out=None, frame_index_base=0):
     """Pose hypotheses on the GPU (slamfe_ransac_hypotheses): P3P + 4th-point disambiguation on 4
     sampled correspondences per hypothesis.  Returns (T (n_frames*H, 3, 4) float64, valid (n_frames*H,)
     uint8) — directly usable as the T / hyp_valid arguments of ransac_score."""
@@ -271,7 +271,8 @@ def ransac_hypotheses(pts, l_pix, K, H, seed=0, pt_off=None, pt_cnt=None, n_fram
     with torch.cuda.device(dev):
         check(load_library().slamfe_ransac_hypotheses(
             ptr(pts), ptr(l_pix), ptr(pt_off), ptr(pt_cnt), pts.shape[0], n_frames, H, ptr(n_hyp), ptr(sample_idx),
-            int(seed) & 0xFFFFFFFFFFFFFFFF, Kb, ptr(T), ptr(valid), stream_handle()), "slamfe_ransac_hypotheses")
+            int(seed) & 0xFFFFFFFFFFFFFFFF, int(frame_index_base), Kb, ptr(T), ptr(valid), stream_handle()),
+            "slamfe_ransac_hypotheses")
     return T, valid
 
 

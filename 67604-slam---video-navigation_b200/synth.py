@@ -163,14 +163,29 @@ def sequence_sizes(n_frames, first_frame=0, seed=1, lo=1000, hi=2500):
                      for f in range(first_frame, first_frame + n_frames)], dtype=np.int32)
 
 
+def frame_motion(seed, f):
+    """World->camera motion from frame f-1 to frame f (pure function of seed and f): small rotation
+    rvec ~ N(0, 0.01), forward translation t = (0, 0, -0.9) +- 0.05 m (KITTI-like)."""
+    rng = np.random.default_rng([seed, f, 23])
+    rvec = rng.normal(0, 0.01, 3)
+    tvec = np.array([0.0, 0.0, -0.9]) + rng.normal(0, 0.05, 3)
+    return _rodrigues(rvec), tvec
+
+
 def torch_sequence(n_frames, first_frame=0, seed=1, device="cuda", lo=1000, hi=2500, row_align=16):
     """Synthetic stereo sequence in the packed layout of frontend.PackedSequence, generated on
     `device`.  Frame f's left descriptors are bit-flipped copies (p = 1/16 per bit) of the
     descriptors frame f-1 introduced plus fresh random ones, row-permuted; its right descriptors
     are flipped copies of 60 % of the left rows (permuted) plus random rows; 1 % exact duplicates
-    force distance ties; right keypoints of true matches satisfy the rectified-stereo geometry
-    except for 15 % gross outliers.  Returns a dict of tensors + numpy offset arrays."""
+    force distance ties.  Geometry is consistent in 3-D: every fresh keypoint gets a pixel and a
+    disparity (i.e. a 3-D point in its frame's camera coordinates, KITTI-00 calibration); in the next
+    frame the carried-over keypoints are those points moved by frame_motion() and re-projected with
+    N(0, 0.5) px noise, so frame-to-frame RANSAC-PnP finds a real consensus set; right keypoints of
+    true stereo matches sit at x_left - disparity except for 15 % gross outliers.
+    Returns a dict of tensors + numpy offset arrays."""
     import torch
+    fx, cx, cy = float(KITTI00_P0[0, 0]), float(KITTI00_P0[0, 2]), float(KITTI00_P0[1, 2])
+    fxb = -float(KITTI00_P1[0, 3])  # fx * baseline
 
     def gen(f, tag):
         g = torch.Generator(device=device)
@@ -189,7 +204,38 @@ def torch_sequence(n_frames, first_frame=0, seed=1, device="cuda", lo=1000, hi=2
         return out
 
     def fresh(f):
-        return rand_desc(_fresh_count(seed, f, lo, hi), gen(f, 1))
+        """Descriptors, left pixels (n, 2) and disparities (n,) of the keypoints frame f introduces."""
+        n = _fresh_count(seed, f, lo, hi)
+        g = gen(f, 1)
+        d = rand_desc(n, g)
+        g3 = gen(f, 3)
+        pix = torch.rand((n, 2), device=device, generator=g3, dtype=torch.float64) * \
+            torch.tensor([1200.0, 365.0], device=device, dtype=torch.float64) + \
+            torch.tensor([20.0, 5.0], device=device, dtype=torch.float64)
+        disp = torch.rand((n,), device=device, generator=g3, dtype=torch.float64) * 117.5 + 2.5
+        return d, pix, disp
+
+    def carry(pix, disp, f, g):
+        """Pixels / disparities in frame f of points seen at (pix, disp) in frame f-1."""
+        R, t = frame_motion(seed, f)
+        R = torch.from_numpy(R).to(device)
+        t = torch.from_numpy(t).to(device)
+        Z = fxb / disp
+        P = torch.stack([(pix[:, 0] - cx) * Z / fx, (pix[:, 1] - cy) * Z / fx, Z], dim=1)
+        Pn = P @ R.T + t
+        ok = Pn[:, 2] > 1.0
+        Zn = torch.where(ok, Pn[:, 2], torch.ones_like(Pn[:, 2]))
+        new_pix = torch.stack([fx * Pn[:, 0] / Zn + cx, fx * Pn[:, 1] / Zn + cy], dim=1) + \
+            0.5 * torch.randn(pix.shape, device=device, generator=g, dtype=torch.float64)
+        new_disp = fxb / Zn
+        # points that passed the camera (or would have an absurd disparity) become unrelated keypoints
+        ok = ok & (new_disp < 400.0)
+        rnd = torch.rand(pix.shape, device=device, generator=g, dtype=torch.float64) * \
+            torch.tensor([1200.0, 365.0], device=device, dtype=torch.float64) + \
+            torch.tensor([20.0, 5.0], device=device, dtype=torch.float64)
+        new_pix = torch.where(ok[:, None], new_pix, rnd)
+        new_disp = torch.where(ok, new_disp, torch.full_like(new_disp, 30.0))
+        return new_pix, new_disp
 
     sizes = sequence_sizes(n_frames, first_frame, seed, lo, hi)
     off = np.zeros(n_frames + 1, dtype=np.int64)
@@ -203,9 +249,20 @@ def torch_sequence(n_frames, first_frame=0, seed=1, device="cuda", lo=1000, hi=2
     for i in range(n_frames):
         f = first_frame + i
         g = gen(f, 2)
-        cur_fresh = fresh(f)
-        old = flip(prev_fresh, g) if prev_fresh is not None else rand_desc(cur_fresh.shape[0], g)
-        left = torch.cat([old, cur_fresh])[torch.randperm(int(sizes[i]), device=device, generator=g)]
+        cur_d, cur_pix, cur_disp = fresh(f)
+        if prev_fresh is not None:
+            old_d = flip(prev_fresh[0], g)
+            old_pix, old_disp = carry(prev_fresh[1], prev_fresh[2], f, g)
+        else:
+            old_d = rand_desc(cur_d.shape[0], g)
+            old_pix = torch.rand((cur_d.shape[0], 2), device=device, generator=g, dtype=torch.float64) * \
+                torch.tensor([1200.0, 365.0], device=device, dtype=torch.float64) + \
+                torch.tensor([20.0, 5.0], device=device, dtype=torch.float64)
+            old_disp = torch.rand((cur_d.shape[0],), device=device, generator=g, dtype=torch.float64) * 117.5 + 2.5
+        perm = torch.randperm(int(sizes[i]), device=device, generator=g)
+        left = torch.cat([old_d, cur_d])[perm]
+        pl = torch.cat([old_pix, cur_pix])[perm].to(torch.float32)
+        disp = torch.cat([old_disp, cur_disp])[perm]
         n = left.shape[0]
         assert n == int(sizes[i])
         n_match = int(0.6 * n)
@@ -217,11 +274,9 @@ def torch_sequence(n_frames, first_frame=0, seed=1, device="cuda", lo=1000, hi=2
         a = torch.randint(0, n, (n_dup,), device=device, generator=g)
         b = torch.randint(0, n, (n_dup,), device=device, generator=g)
         right[a] = right[b]
-        pl = torch.rand((n, 2), device=device, generator=g) * torch.tensor([1200.0, 365.0], device=device) \
-            + torch.tensor([20.0, 5.0], device=device)
         pr = torch.rand((n, 2), device=device, generator=g) * torch.tensor([1200.0, 365.0], device=device) \
             + torch.tensor([20.0, 5.0], device=device)
-        d = torch.rand((n_match,), device=device, generator=g) * 117.5 + 2.5
+        d = disp[src].to(torch.float32)
         bad = torch.rand((n_match,), device=device, generator=g) < 0.15
         xr = pl[src, 0] - torch.where(bad, -torch.ones_like(d), d)
         yr = pl[src, 1] + 0.5 * torch.randn((n_match,), device=device, generator=g)
@@ -232,7 +287,7 @@ def torch_sequence(n_frames, first_frame=0, seed=1, device="cuda", lo=1000, hi=2
         desc_r[o:o + n] = right
         pts_l[o:o + n] = pl
         pts_r[o:o + n] = pr
-        prev_fresh = cur_fresh
+        prev_fresh = (cur_d, cur_pix, cur_disp)
     off32 = off.astype(np.int32)
     return {"desc_l": desc_l, "desc_r": desc_r, "pts_l": pts_l, "pts_r": pts_r,
             "l_off": off32, "r_off": off32.copy(), "n_l": sizes, "n_r": sizes.copy()}

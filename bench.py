@@ -35,7 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "frame pairs/s (stereo + consecutive-frame Hamming matching, row filter, triangulation)"
+METRIC = "frame pairs/s (stereo + consecutive-frame Hamming matching, row filter, triangulation, RANSAC-PnP)"
 UNIT = "frame_pairs/s"
 
 
@@ -52,6 +52,9 @@ def parse_args():
                     help="sequence = BASELINE configs[1] (the headline line); the others are configs[2..4], see "
                          "bench_extra.py")
     ap.add_argument("--keyframes", type=int, default=450, help="--workload loop: number of keyframes")
+    ap.add_argument("--h-max", type=int, default=128,
+                    help="cap of RANSAC-PnP hypotheses per frame pair (calc_ransac_iteration gives ~57 at the "
+                         "workload's 76 %% stereo inlier rate)")
     ap.add_argument("--cpu-sample-frames", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -120,14 +123,17 @@ class ClockSampler:
 # CPU path of the reference on host cores (oracle = checker / baseline only)
 # --------------------------------------------------------------------------------------------
 def cpu_frames_pass(frames, P, Q, collect=False):
-    """The reference's per-frame work (database.py:12-27, :54-77; ransac.py:83) on the CPU:
+    """The reference's per-frame work (database.py:12-27, :54-85; ransac.py:70-113) on the CPU:
     cv2 crossCheck match, row filter, create_links, np.linalg.svd triangulation per link,
-    forward+backward cv2 matches + mutual check.  Returns per-frame results when collect=True."""
+    forward+backward cv2 matches, mutual check, RANSAC-PnP (cv2 EPnP hypotheses + NumPy scoring).
+    Returns per-frame results when collect=True."""
     import cv2
     from oracle import ref_oracle as ora
     lr = cv2.BFMatcher(normType=cv2.NORM_HAMMING, crossCheck=True)
     mm = cv2.BFMatcher(normType=cv2.NORM_HAMMING, crossCheck=False)
-    out, prev_feat = [], None
+    from slamfe import utils as _u
+    K, M1, M2 = _u.K, _u.M1, _u.M2
+    out, prev_feat, prev_links = [], None, None
     for dl, dr, pl, pr in frames:
         ms = lr.match(dl, dr)
         mq = np.fromiter((m.queryIdx for m in ms), np.int32, len(ms))
@@ -143,10 +149,17 @@ def cpu_frames_pass(frames, P, Q, collect=False):
             fwd_t = np.fromiter((m.trainIdx for m in fwd), np.int32, len(fwd))
             fwd_d = np.fromiter((m.distance for m in fwd), np.int32, len(fwd))
             bwd_t = np.fromiter((m.trainIdx for m in bwd), np.int32, len(bwd))
+        good = best_idx = None
+        if fwd_t is not None:
+            # database.py:67-85: mutual check, then ransac_pnp_for_tracking_db with the frame's stereo inlier rate
+            good = np.nonzero(bwd_t[fwd_t] == np.arange(len(fwd_t)))[0]
+            if len(good) >= 4:
+                pct = 100 * (len(inl) / len(ms))
+                best_idx = ora.ransac_pnp_for_tracking_db(good, fwd_t[good], prev_links, links, pct, K, M1, M2)
         if collect:
             out.append({"mq": mq, "mt": mt, "inl": inl, "links": links, "xyz": xyz, "fwd_t": fwd_t, "fwd_d": fwd_d,
-                        "bwd_t": bwd_t})
-        prev_feat = feat
+                        "bwd_t": bwd_t, "good": good, "ransac_inliers": None if best_idx is None else len(best_idx)})
+        prev_feat, prev_links = feat, links
     return out
 
 
@@ -199,7 +212,7 @@ def run_reference(args, rank):
 
 def workload_config(args, world):
     return {"workload": "configs[1]: synthetic 4541-frame KITTI-00-shaped stereo sequence per GPU "
-                        "(stereo + consecutive-frame matching + triangulation)",
+                        "(stereo + consecutive-frame matching + triangulation + RANSAC-PnP per frame pair)",
             "frames_per_gpu": args.frames, "frames_total": args.frames * world,
             "keypoints_per_image": "2000-5000 (mean 3500)", "descriptor_bytes": 61, "image": "1241x376",
             "l2_policy": "inputs (~2 GB/GPU) are larger than L2; no flush needed", "seed": args.seed,
@@ -265,7 +278,7 @@ def main():
         return g_rows, g_frames
 
     def step():
-        o = fe.run(ds)
+        o = fe.track(ds, h_max=args.h_max, seed=args.seed)
         gather_tables(o)
         return o
 
@@ -312,7 +325,8 @@ def main():
 
         def e2e_step():
             nonlocal h2d, d2h
-            _, h2d, d2h = fe2.run_host(host_seq, chunk_frames=args.chunk_frames, device=dev)
+            _, h2d, d2h = fe2.run_host(host_seq, chunk_frames=args.chunk_frames, device=dev, track=True,
+                                       h_max=args.h_max, seed=args.seed)
             gather_tables(fe2._out)
 
         for _ in range(2):
@@ -328,7 +342,7 @@ def main():
         e2e = {"value": pairs_total / (float(e_ms.item()) / args.steps * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": float(e_ms.item()) / args.steps,
-               "api": f"FrontEnd.run_host(PackedSequence, chunk_frames={args.chunk_frames})",
+               "api": f"FrontEnd.run_host(PackedSequence, chunk_frames={args.chunk_frames}, track=True)",
                "gpu_launches_per_step": fe2.last_launches}
         del pinned_in, host_seq, fe2
 
@@ -406,7 +420,8 @@ def main():
                             "sample": f"first {n} frames of the workload ({dt:.1f} s): cv2 {cv2.__version__} "
                                       f"BFMatcher crossCheck + fwd/bwd match with all host threads, oracle "
                                       f"restatement of the reference's Python row filter / create_links / "
-                                      f"per-link np.linalg.svd triangulation (single thread, as the reference)"}
+                                      f"per-link np.linalg.svd triangulation / mutual check / RANSAC-PnP loop with "
+                                      f"cv2 EPnP (single thread, as the reference)"}
             host, _, _ = frontend.results_to_host(out)
             ok, worst = True, 0.0
             for f, r in enumerate(res):
@@ -425,8 +440,30 @@ def main():
                     lo1, k1n = int(seq_t["l_off"][f + 1]), len(nxt["inl"])
                     bi, _ = ops.keys_to_numpy(host["bwd_keys"][lo1:lo1 + k1n])
                     ok &= bool(np.array_equal(bi, nxt["bwd_t"]))
+            # tracking stages: mutual matches bit-exact; RANSAC consensus statistically equal (the
+            # reference samples with an unseeded RNG and cv2 EPnP, the GPU with P3P: DESIGN.md 2.6)
+            trk = {k: out[k].cpu().numpy() for k in ("good_j", "n_good", "best")}
+            mutual_ok, ratios = True, []
+            for f in range(n - 1):
+                nxt = res[f + 1]
+                if nxt["good"] is None:
+                    continue
+                lo = int(seq_t["l_off"][f])
+                mutual_ok &= bool(trk["n_good"][f] == len(nxt["good"]) and
+                                  np.array_equal(trk["good_j"][lo:lo + len(nxt["good"])], nxt["good"]))
+                if nxt["ransac_inliers"]:
+                    ratios.append(float(trk["best"][f, 1]) / nxt["ransac_inliers"])
             parity = {"frames_checked": n, "match_tables_bit_exact": ok, "xyz_max_rel_err": worst,
-                      "xyz_tolerance": 1e-5}
+                      "xyz_tolerance": 1e-5, "mutual_matches_bit_exact": mutual_ok,
+                      "ransac_inlier_count_ratio_gpu_over_cpu": {"median": float(np.median(ratios)) if ratios else None,
+                                                                 "min": min(ratios) if ratios else None,
+                                                                 "max": max(ratios) if ratios else None,
+                                                                 "frac_within_10pct": float(np.mean(
+                                                                     np.abs(np.array(ratios) - 1) <= 0.1))
+                                                                 if ratios else None,
+                                                                 "note": "both sides are randomised RANSAC runs with "
+                                                                         "the reference's own iteration count (~57): "
+                                                                         "either can miss the consensus on a pair"}}
 
     if rank == 0:
         line = {
@@ -436,7 +473,7 @@ def main():
             "config": workload_config(args, world),
             "descriptor_pairs_per_s": desc_pairs_total / (ms_per_step * 1e-3),
             "descriptor_pairs_per_step": desc_pairs_total,
-            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": fe.launches_per_run * args.steps,
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": fe.last_launches * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
         }
         print(json.dumps(line))

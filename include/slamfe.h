@@ -264,6 +264,8 @@ int slamfe_scatter_inliers(const uint8_t *best_mask, const int32_t *good_j, cons
  * solver, pinned against cv2.SOLVEPNP_P3P and ground truth.
  *   pts (.,3), l_pix (.,2) fp64 DEVICE; frame f owns points [pt_off[f], pt_off[f] + n_f) with
  *   n_f = pt_cnt ? pt_cnt[f] : pt_off[f+1] - pt_off[f]  (pt_off NULL: one frame of n_points points)
+ *   seed, frame_index_base: the sample of hypothesis h of frame f is a pure function of
+ *            (seed, frame_index_base + f, h), so a sequence processed in chunks draws the same samples
  *   n_hyp    (n_frames,) int32 DEVICE or NULL: hypotheses wanted for frame f (<= H); the rest of the
  *            frame's H slots are marked invalid (calc_ransac_iteration differs per frame, ransac.py:59-67)
  *   T        out (n_frames*H, 12) fp64 row-major [R|t], zero where invalid
@@ -272,7 +274,8 @@ int slamfe_scatter_inliers(const uint8_t *best_mask, const int32_t *good_j, cons
  */
 int slamfe_ransac_hypotheses(const double *pts, const double *l_pix, const int32_t *pt_off, const int32_t *pt_cnt,
                              int n_points, int n_frames, int H, const int32_t *n_hyp, const int32_t *sample_idx,
-                             uint64_t seed, const double *K, double *T, uint8_t *hyp_valid, slamfe_stream_t stream);
+                             uint64_t seed, int frame_index_base, const double *K, double *T, uint8_t *hyp_valid,
+                             slamfe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Roofline micro-benchmarks (measure the pipe peaks the matcher / scorer are bound by)

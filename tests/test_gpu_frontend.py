@@ -85,6 +85,16 @@ def test_host_pipeline_equals_resident_run(slamfe, chunk):
             for key in ("link_src", "links", "xyz", "fwd_keys", "bwd_keys"):
                 assert np.array_equal(got[key][lo:lo + k], ref[key][lo:lo + k]), (key, f)
     torch.cuda.synchronize()
+    # with the tracking stages: same samples (RNG keyed by global pair index), same tables
+    trk = fe.track(frontend.to_device(seq), h_max=40, seed=9)
+    ref_t = {k: trk[k].cpu().numpy() for k in frontend.TRACK_KEYS}
+    got, _, _ = fe2.run_host(seq, chunk_frames=chunk, track=True, h_max=40, seed=9)
+    n_pairs = seq.n_frames - 1
+    for key in ("best", "n_good", "n_hyp"):
+        assert np.array_equal(got[key][:n_pairs], ref_t[key][:n_pairs]), key
+    for f in range(seq.n_frames):
+        lo, k = seq.l_off[f], ref["n_links"][f]
+        assert np.array_equal(got["inlier_fwd"][lo:lo + k], ref_t["inlier_fwd"][lo:lo + k]), f
 
 
 def test_patch_rebinds_reference_style_modules(slamfe):

@@ -383,10 +383,17 @@ def main():
         sm_mhz = clocks.summary()["sm_mhz"] or 1965.0
         xu_clk, alu_clk = 7.0 / 16.0, 30.0 / 64.0
         pipe_bound_pairs = sms * sm_mhz * 1e6 / max(xu_clk, alu_clk)
+        traffic = None  # dram__bytes_read+write of this launch from the committed ncu capture (full size only)
+        try:
+            if F == 4541 and world == 1:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_matcher_traffic.json")))[
+                    "dram_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {
             "kernel": "hamming_top2_kernel<256,2,COL,best-only,9 adders> (stereo L<->R launch, all frames)",
             "bound": "popc", "achieved": achieved, "peak": peak_popc, "unit": "Gpopc32/s",
-            "frac": achieved / peak_popc if peak_popc else None, "traffic": None,
+            "frac": achieved / peak_popc if peak_popc else None, "traffic": traffic,
             "note": "achieved counts the ALGORITHMIC 16 popc32 per descriptor pair (SURVEY 8d); the kernel's "
                     "prefix-XOR carry-save adders execute only 7 POPC per pair, so frac > 1 against the plain "
                     "POPC-pipe peak is expected; frac_of_executed_pipe_bound is the utilisation of the pipes "

@@ -12,7 +12,7 @@ python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench
 kill $SMI
 BENCH_SMALL="python bench.py --frames 512 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
 $BENCH_SMALL > gpurun_out/plain_small.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"hamming|stereo_|triangulate|ransac|peak_|unpack_keys|merge_top2|cross_check|ratio_test|nccl" -c 400 --csv --log-file gpurun_out/launches.csv $BENCH_SMALL > gpurun_out/ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"hamming|stereo_|triangulate|ransac|track_gather|scatter_inliers|peak_|unpack_keys|merge_top2|cross_check|ratio_test|nccl" -c 400 --csv --log-file gpurun_out/launches.csv $BENCH_SMALL > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
 $BENCH_SMALL > gpurun_out/plain_small2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:hamming_top2 -s 4 -c 2 -f -o gpurun_out/prof_hamming $BENCH_SMALL > gpurun_out/ncu_full.log 2>&1

@@ -97,8 +97,17 @@ def require_cuda():
 
 
 def ptr(t) -> int:
-    """Device (or host) address of a torch tensor, 0 for None."""
-    return 0 if t is None else t.data_ptr()
+    """Device (or host) address of a torch tensor, 0 for None.  An EMPTY view (zero rows of a larger
+    table, e.g. the rows of a frame without keypoints) still gets the address it would start at —
+    torch reports 0 for it, which the C-ABI would reject as a missing argument."""
+    if t is None:
+        return 0
+    p = t.data_ptr()
+    if p == 0 and t.numel() == 0:
+        st = t.untyped_storage()
+        if st.nbytes() > 0:
+            p = st.data_ptr() + t.storage_offset() * t.element_size()
+    return p
 
 
 def host_doubles(a, n: int):

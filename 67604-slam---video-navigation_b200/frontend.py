@@ -261,7 +261,9 @@ class FrontEnd:
         t = self._track_buffers(L, F, h_max, ds.desc_l.device)
         out = dict(o)
         out.update(t)
-        if F < 2:
+        if F < 2 or L == 0:  # nothing to track: report "no mutual matches, no hypothesis" for every pair
+            t["n_good"].zero_(); t["n_hyp"].zero_(); t["best"].fill_(-1); t["best"][:, 1].zero_()
+            t["inlier_fwd"].zero_()
             return out
         self._track_stages(o, t, ds.l_off, ds.r_off, ds.pts_l, ds.pts_r, F - 1, min(ds.max_nl, ds.max_nr), h_max, seed)
         self.last_launches += 4

@@ -176,3 +176,36 @@ def test_tracking_stages_vs_oracle(slamfe, oracle):
         else:
             flags[good] = 1                     # good_idx[None] quirk, database.py:82
         assert np.array_equal(g["inlier_fwd"][lo:lo + len(feats[f])], flags)
+
+
+def test_tracking_edge_cases(slamfe):
+    """Empty frames, frames with fewer than 4 links, a single-frame sequence: no crash, invalid
+    pairs report best = -1 / zero flags, and the chunked host pipeline agrees with the resident one."""
+    from slamfe import frontend, synth
+    rng = np.random.default_rng(74)
+    empty = (np.zeros((0, 61), np.uint8), np.zeros((0, 61), np.uint8), np.zeros((0, 2), np.float32),
+             np.zeros((0, 2), np.float32))
+    frames = [empty, synth.stereo_frame(rng, 40), synth.stereo_frame(rng, 3), empty, synth.stereo_frame(rng, 500),
+              synth.stereo_frame(rng, 450)]
+    seq = frontend.pack_sequence(frames)
+    fe = frontend.FrontEnd()
+    out = fe.track(frontend.to_device(seq), h_max=16, seed=3)
+    host = {k: out[k].cpu().numpy() for k in ("n_links", "n_matches", "n_good", "n_hyp", "best", "inlier_fwd", "hyp_valid")}
+    assert host["n_links"][0] == 0 and host["n_links"][3] == 0 and host["n_matches"][0] == 0
+    n_pairs = len(frames) - 1
+    for f in range(n_pairs):
+        if host["n_good"][f] < 4:
+            assert host["best"][f, 0] == -1 and host["best"][f, 1] == 0
+            assert not host["hyp_valid"][f * 16:(f + 1) * 16].any()
+    assert host["n_hyp"][2] == 0            # frame 3 has no stereo matches: no iteration count
+    got, _, _ = frontend.FrontEnd().run_host(seq, chunk_frames=2, track=True, h_max=16, seed=3)
+    assert np.array_equal(got["best"][:n_pairs], host["best"][:n_pairs])
+    assert np.array_equal(got["n_good"][:n_pairs], host["n_good"][:n_pairs])
+    for f in range(len(frames)):
+        lo, k = seq.l_off[f], host["n_links"][f]
+        assert np.array_equal(got["inlier_fwd"][lo:lo + k], host["inlier_fwd"][lo:lo + k])
+    one = frontend.pack_sequence([synth.stereo_frame(rng, 300)])
+    o1 = frontend.FrontEnd().track(frontend.to_device(one), h_max=8)
+    assert int(o1["n_links"][0]) > 0
+    g1, _, _ = frontend.FrontEnd().run_host(one, track=True, h_max=8)
+    assert g1["n_links"][0] == int(o1["n_links"][0])

@@ -71,13 +71,24 @@ def test_no_cpu_fallback(slamfe):
 
 
 def test_product_does_not_import_oracle(slamfe):
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/: not the package,
+    not the C sources, not the development scripts."""
     import os
     import re
     pkg = slamfe.__path__[0]
-    for fn in os.listdir(pkg):
-        if fn.endswith(".py"):
-            src = open(os.path.join(pkg, fn)).read()
-            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+    root = os.path.dirname(pkg)
+    files = [os.path.join(pkg, fn) for fn in os.listdir(pkg) if fn.endswith(".py")]
+    files += [os.path.join(pkg, "csrc", fn) for fn in os.listdir(os.path.join(pkg, "csrc"))]
+    files += [os.path.join(root, "scripts", fn) for fn in os.listdir(os.path.join(root, "scripts")) if fn.endswith(".py")]
+    files += [os.path.join(root, "slamfe.py")]
+    for path in files:
+        src = open(path).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), path
+        assert "liboracle" not in src and "libp3p_host" not in src, path
+    # and the library itself must not depend on the oracle's shared objects
+    import subprocess
+    deps = subprocess.run(["ldd", os.path.join(pkg, "libslamfe.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in deps and "p3p_host" not in deps
 
 
 def test_offsets_are_tma_aligned(slamfe):

@@ -13,6 +13,7 @@ Layout
     _cabi.py         ctypes binding, ops.py  tensor-level operators
     matching.py / triangulation.py / ransac.py / utils.py   mirrors of the reference modules
     frontend.py      device-resident batched sequence pipeline (frame pairs per launch)
+    loop.py          batched loop-closure candidate verification (match + RANSAC-PnP per candidate)
     dist.py          one-process-per-GPU sharding + NCCL all-gather of result tables
     patch.py         rebinding of the reference's module attributes (the "plugin" hook)
     synth.py         seeded synthetic KITTI-shaped inputs
@@ -23,11 +24,11 @@ from ._cabi import EXPORTED_SYMBOLS, KEY_IDX_BITS, KEY_IDX_MASK, KEY_NONE, Slamf
 __version__ = "0.1.0"
 
 __all__ = ["EXPORTED_SYMBOLS", "KEY_IDX_BITS", "KEY_IDX_MASK", "KEY_NONE", "SlamfeError", "load_library",
-           "matching", "triangulation", "ransac", "utils", "ops", "frontend", "dist", "patch", "synth"]
+           "matching", "triangulation", "ransac", "utils", "ops", "frontend", "loop", "dist", "patch", "synth"]
 
 
 def __getattr__(name):
-    if name in ("matching", "triangulation", "ransac", "utils", "ops", "frontend", "dist", "patch", "synth",
+    if name in ("matching", "triangulation", "ransac", "utils", "ops", "frontend", "loop", "dist", "patch", "synth",
                 "build"):
         import importlib
         return importlib.import_module("." + name, __name__)

@@ -48,6 +48,7 @@ _SIGNATURES = {
                                     c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "slamfe_track_gather": (c_int, [c_void_p] * 10 + [c_int, c_void_p, c_void_p, c_int] + [c_void_p] * 8),
+    "slamfe_pairs_gather": (c_int, [c_void_p] * 5 + [c_int, c_int] + [c_void_p] * 6),
     "slamfe_scatter_inliers": (c_int, [c_void_p] * 5 + [c_int, c_void_p, c_int64, c_void_p]),
     "slamfe_ransac_hypotheses": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                          c_void_p, c_uint64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

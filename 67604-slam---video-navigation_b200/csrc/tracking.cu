@@ -130,10 +130,57 @@ __global__ void scatter_inliers_kernel(const uint8_t *__restrict__ best_mask, co
         if (none || best_mask[l0 + k]) inlier_fwd[l0 + good_j[l0 + k]] = 1;
 }
 
+// Loop-closure candidate form of the gather (backend/loop/loop_closure.py:405-436 -> ransac.py:132-146):
+// candidate p matches ALL links of keyframe A (queries, in order) against keyframe B; the 3-D points
+// are keyframe A's triangulated links, the pixel arrays keyframe B's links at trainIdx.
+__global__ void pairs_gather_kernel(const uint32_t *__restrict__ keys, const int32_t *__restrict__ q_off,
+                                    const int32_t *__restrict__ q_cnt, const int32_t *__restrict__ t_off,
+                                    const int32_t *__restrict__ out_off, const double *__restrict__ kf_pts,
+                                    const double *__restrict__ kf_links, double *__restrict__ pts,
+                                    double *__restrict__ lpix, double *__restrict__ rpix)
+{
+    const int p = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= q_cnt[p]) return;
+    const size_t o = static_cast<size_t>(out_off[p]) + j;
+    const size_t a = static_cast<size_t>(q_off[p]) + j;
+    pts[3 * o] = kf_pts[3 * a];
+    pts[3 * o + 1] = kf_pts[3 * a + 1];
+    pts[3 * o + 2] = kf_pts[3 * a + 2];
+    const uint32_t k = keys[o];
+    double xl, xr, y;
+    if (k == KEY_NONE) {  // empty train keyframe: a correspondence that can never agree
+        xl = xr = y = __longlong_as_double(0x7FF8000000000000ll);
+    } else {
+        const size_t b = static_cast<size_t>(t_off[p]) + (k & KEY_IDX_MASK);
+        xl = kf_links[3 * b];
+        xr = kf_links[3 * b + 1];
+        y = kf_links[3 * b + 2];
+    }
+    lpix[2 * o] = xl; lpix[2 * o + 1] = y;
+    rpix[2 * o] = xr; rpix[2 * o + 1] = y;
+}
+
 }  // namespace
 }  // namespace slamfe
 
 using namespace slamfe;
+
+extern "C" int slamfe_pairs_gather(const uint32_t *keys, const int32_t *q_off, const int32_t *q_cnt,
+                                   const int32_t *t_off, const int32_t *out_off, int n_problems, int max_nq,
+                                   const double *kf_pts, const double *kf_links, double *pts, double *lpix,
+                                   double *rpix, slamfe_stream_t stream)
+{
+    if (n_problems < 0 || max_nq < 0) return SLAMFE_EINVAL;
+    if (n_problems == 0 || max_nq == 0) return 0;
+    if (!keys || !q_off || !q_cnt || !t_off || !out_off || !kf_pts || !kf_links || !pts || !lpix || !rpix)
+        return SLAMFE_EINVAL;
+    if (n_problems > 65535) return SLAMFE_ERANGE;
+    const dim3 grid((max_nq + 255) / 256, n_problems);
+    pairs_gather_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(keys, q_off, q_cnt, t_off, out_off, kf_pts,
+                                                                             kf_links, pts, lpix, rpix);
+    return launch_status();
+}
 
 extern "C" int slamfe_track_gather(const uint32_t *fwd_keys, const uint32_t *bwd_keys, const int32_t *l_off,
                                    const int32_t *r_off, const int32_t *n_links, const int32_t *n_matches,

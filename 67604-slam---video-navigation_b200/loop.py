@@ -1,0 +1,131 @@
+"""Batched loop-closure candidate verification — the hot half of backend/loop/loop_closure.py.
+
+The reference verifies one candidate at a time (`check_candidate_match`, loop_closure.py:405-436):
+`MATCHER.match(kf1_features, kf2_features)` (:422, crossCheck=False) followed by
+`ransac_pnp(matches, kf1_links, kf2_links, inliers_percent=40)` (:425 -> ransac.py:116-204: 888
+iterations of sample / EPnP / transformation_agreement), and accepts the first candidate with more
+than INLIERS_THRESHOLD = 120 inliers (`consensus_matches`, :572-599).  Here a whole block of
+(keyframe, candidate) pairs goes through each stage in one launch, device resident:
+
+    slamfe_hamming_top2_pairs -> slamfe_pairs_gather -> slamfe_ransac_hypotheses -> slamfe_ransac_score
+
+Candidate gating (Mahalanobis distance on the pose graph), the final refit and the GTSAM bundle stay
+with the reference (out of scope).  Hypotheses come from the GPU generator
+(DESIGN.md section 2.6), so inlier counts are statistically — not bit-wise — equal to a run of the
+reference, which is itself unseeded.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _cabi, ops
+from .ransac import calc_ransac_iteration
+
+INLIERS_THRESHOLD = 120   # loop_closure.py:17
+LOOP_INLIERS_PERCENT = 40  # loop_closure.py:425
+
+
+class CandidateVerifier:
+    """Owns the device buffers of one block of candidates and reuses them across calls."""
+
+    def __init__(self, K=None, M1=None, M2=None, block_pairs=8192):
+        from . import utils
+        self.K = utils.K if K is None else np.asarray(K, float)
+        self.M1 = utils.M1 if M1 is None else np.asarray(M1, float)
+        self.M2 = utils.M2 if M2 is None else np.asarray(M2, float)
+        self.P, self.Q = self.K @ self.M1, self.K @ self.M2
+        self.block_pairs = int(block_pairs)
+        self._buf = None
+        self._key = None
+        self.last_launches = 0
+
+    def _buffers(self, rows, n_pairs, H, dev):
+        torch = _cabi.require_cuda()
+        key = (rows, n_pairs, H, dev)
+        if self._key != key:
+            f64 = dict(dtype=torch.float64, device=dev)
+            i32 = dict(dtype=torch.int32, device=dev)
+            self._buf = {
+                "keys": torch.empty((rows,), **i32), "pts": torch.empty((rows, 3), **f64),
+                "lpix": torch.empty((rows, 2), **f64), "rpix": torch.empty((rows, 2), **f64),
+                "T": torch.empty((n_pairs * H, 3, 4), **f64),
+                "hyp_valid": torch.empty((n_pairs * H,), dtype=torch.uint8, device=dev),
+                "counts": torch.empty((n_pairs, H), **i32), "best": torch.empty((n_pairs, 2), **i32),
+                "best_mask": torch.empty((rows,), dtype=torch.uint8, device=dev), "work": torch.empty((n_pairs,), **i32),
+            }
+            self._key = key
+        return self._buf
+
+    def verify(self, pool_desc, pool_links, kf_off, kf_cnt, pairs, inliers_percent=LOOP_INLIERS_PERCENT, n_iter=None,
+               seed=1, want_masks=False, pair_base=0, key_table=None, sync=True):
+        """pool_desc (R, 61|64) uint8 CUDA: filtered features of all keyframes; pool_links (R, 3) float64
+        CUDA [x_left, x_right, y] of the same rows; kf_off / kf_cnt: row offset / link count per keyframe
+        (numpy int); pairs (P, 2) numpy: (reference keyframe, candidate keyframe).
+        Returns a dict of numpy arrays per pair: n_matches, inliers (best count), best_hyp, percentage
+        (= inliers / n_matches, loop_closure.py:429), accepted (inliers > 120); with want_masks also
+        `keys` (best match key per query row) and `mask` (inlier flag per match) as ragged lists.
+        key_table: optional (sum of n_matches,) int32 CUDA tensor that receives the best-match keys of
+        all pairs (pair-major), e.g. for the multi-GPU all-gather of match tables.  sync=False leaves
+        the per-pair [best_hyp, inliers] table on the device (res["best_dev"], (P, 2) int32) and skips
+        the host copies."""
+        torch = _cabi.require_cuda()
+        dev = pool_desc.device
+        pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
+        kf_off = np.asarray(kf_off, dtype=np.int64)
+        kf_cnt = np.asarray(kf_cnt, dtype=np.int64)
+        H = int(n_iter) if n_iter is not None else calc_ransac_iteration(inliers_percent)
+        kf_pts = ops.triangulate_links(pool_links, self.P, self.Q)       # once per keyframe pool
+        res = {"n_matches": kf_cnt[pairs[:, 0]].copy(), "inliers": np.zeros(len(pairs), np.int64),
+               "best_hyp": np.full(len(pairs), -1, np.int64)}
+        best_dev = torch.empty((len(pairs), 2), dtype=torch.int32, device=dev)
+        row0 = 0
+        keys_out, mask_out = [], []
+        self.last_launches = 1
+        max_n = int(kf_cnt.max()) if len(kf_cnt) else 0
+        blk = max(1, min(self.block_pairs, 65535))
+        rows_cap = blk * max_n
+        for b0 in range(0, len(pairs), blk):
+            pb = pairs[b0:b0 + blk]
+            n = len(pb)
+            q_cnt_h = kf_cnt[pb[:, 0]]
+            out_off_h = np.zeros(n + 1, np.int64)
+            np.cumsum(q_cnt_h, out=out_off_h[1:])
+            rows = int(out_off_h[-1])
+            buf = self._buffers(rows_cap, blk, H, dev)
+            small = np.concatenate([kf_off[pb[:, 0]], q_cnt_h, kf_off[pb[:, 1]], kf_cnt[pb[:, 1]], out_off_h[:-1]])
+            sd = torch.from_numpy(small.astype(np.int32)).to(dev, non_blocking=True)
+            q_off, q_cnt, t_off, t_cnt, out_off = (sd[i * n:(i + 1) * n] for i in range(5))
+            v = {k: buf[k][:rows] for k in ("keys", "pts", "lpix", "rpix", "best_mask")}
+            if key_table is not None:
+                v["keys"] = key_table[row0:row0 + rows]
+            row0 += rows
+            ops.hamming_pairs(pool_desc, q_off, q_cnt, pool_desc, t_off, t_cnt, out_off, n, max_n, max_n,
+                              row_keys=v["keys"], out_rows_total=rows, best_only=True, compact=True)
+            ops.pairs_gather(v["keys"], q_off, q_cnt, t_off, out_off, n, max_n, kf_pts, pool_links, v["pts"],
+                             v["lpix"], v["rpix"])
+            T, valid = buf["T"][:n * H], buf["hyp_valid"][:n * H]
+            ops.ransac_hypotheses(v["pts"], v["lpix"], self.K, H, seed=seed, pt_off=out_off, pt_cnt=q_cnt, n_frames=n,
+                                  out=(T, valid), frame_index_base=pair_base + b0)
+            out = {"counts": buf["counts"][:n], "best": best_dev[b0:b0 + n], "best_mask": v["best_mask"],
+                   "work": buf["work"][:n]}
+            ops.ransac_score(T, v["pts"], v["lpix"], v["rpix"], self.K, self.M1, self.M2, hyp_valid=valid,
+                             pt_off=out_off, pt_cnt=q_cnt, n_frames=n, max_points=max_n, out=out)
+            self.last_launches += 4
+            if want_masks:
+                kh = v["keys"].cpu().numpy().view(np.uint32)
+                mh = v["best_mask"].cpu().numpy().astype(bool)
+                for p in range(n):
+                    keys_out.append(kh[out_off_h[p]:out_off_h[p + 1]].copy())
+                    mask_out.append(mh[out_off_h[p]:out_off_h[p + 1]].copy())
+        res["best_dev"] = best_dev
+        if not sync:
+            return res
+        best = best_dev.cpu().numpy()
+        res["best_hyp"][:] = best[:, 0]
+        res["inliers"][:] = best[:, 1]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            res["percentage"] = np.where(res["n_matches"] > 0, res["inliers"] / np.maximum(res["n_matches"], 1), 0.0)
+        res["accepted"] = res["inliers"] > INLIERS_THRESHOLD
+        if want_masks:
+            res["keys"], res["mask"] = keys_out, mask_out
+        return res

@@ -290,6 +290,15 @@ def track_gather(o, ds_l_off, ds_r_off, pts_left, pts_right, n_pairs, P, Q, h_ma
     return out
 
 
+def pairs_gather(keys, q_off, q_cnt, t_off, out_off, n_problems, max_nq, kf_pts, kf_links, pts, lpix, rpix):
+    """slamfe_pairs_gather: RANSAC inputs of loop-closure candidates from the compact match keys."""
+    torch = _torch()
+    with torch.cuda.device(keys.device):
+        check(load_library().slamfe_pairs_gather(ptr(keys), ptr(q_off), ptr(q_cnt), ptr(t_off), ptr(out_off),
+                                                 n_problems, max_nq, ptr(kf_pts), ptr(kf_links), ptr(pts), ptr(lpix),
+                                                 ptr(rpix), stream_handle()), "slamfe_pairs_gather")
+
+
 def scatter_inliers(best_mask, good_j, l_off, n_good, best, n_pairs, inlier_fwd):
     torch = _torch()
     with torch.cuda.device(inlier_fwd.device):

@@ -52,6 +52,7 @@ def parse_args():
                     help="sequence = BASELINE configs[1] (the headline line); the others are configs[2..4], see "
                          "bench_extra.py")
     ap.add_argument("--keyframes", type=int, default=450, help="--workload loop: number of keyframes")
+    ap.add_argument("--loop-block", type=int, default=8192, help="--workload loop: candidate pairs per launch")
     ap.add_argument("--h-max", type=int, default=128,
                     help="cap of RANSAC-PnP hypotheses per frame pair (calc_ransac_iteration gives ~57 at the "
                          "workload's 76 %% stereo inlier rate)")

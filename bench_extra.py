@@ -128,80 +128,113 @@ class RansacWorkload(Workload):
 
 # ------------------------------------------------------------------------------------------------
 class LoopWorkload(Workload):
-    metric = "candidate keyframe pairs/s (loop-closure matching: every keyframe vs all prior keyframes)"
+    metric = ("candidate keyframe pairs/s (loop-closure verification: every keyframe vs all prior keyframes, "
+              "match + 888-iteration RANSAC-PnP per candidate)")
     unit = "candidate_pairs/s"
     scaling = "strong"
 
     def __init__(self, args, rank, world, dev):
         import torch
-        from slamfe import dist as sdist
+        from slamfe import dist as sdist, loop, synth, utils
         self.torch, self.dev, self.world, self.rank = torch, dev, world, rank
         self.K, self.n = args.keyframes, 2000
+        n = self.n
         g = torch.Generator(device=dev).manual_seed(args.seed + 3)
-        pool = torch.randint(0, 256, (self.K * self.n, 61), dtype=torch.uint8, device=dev, generator=g)
+        pool = torch.randint(0, 256, (self.K * n, 61), dtype=torch.uint8, device=dev, generator=g)
         pool[:, 60] &= 0x3F
-        # planted revisits (cf. project.py:109-119): keyframe a re-observes keyframe b
-        for a, b in ((self.K - 3, 5), (self.K // 2, 11), (self.K - 40, self.K // 3), (self.K // 3 + 7, 2)):
-            if 0 <= b < a < self.K:
-                flip = (torch.rand((self.n, 61, 8), device=dev, generator=g) < 0.06)
-                bits = (flip * (2 ** torch.arange(8, device=dev))).sum(-1).to(torch.uint8)
-                pool[a * self.n:(a + 1) * self.n] = pool[b * self.n:(b + 1) * self.n] ^ bits
-                pool[a * self.n:(a + 1) * self.n, 60] &= 0x3F
+        rng = np.random.default_rng(args.seed + 3)
+        Kc = utils.K
+        fx, cx, cy, fxb = Kc[0, 0], Kc[0, 2], Kc[1, 2], -synth.KITTI00_P1[0, 3]
+        f32 = lambda a: a.astype(np.float32).astype(np.float64)
+        xl = f32(rng.uniform(20, 1220, self.K * n))
+        links = np.stack([xl, f32(xl - rng.uniform(2.5, 120, self.K * n)), f32(rng.uniform(5, 370, self.K * n))], axis=1)
+        # planted revisits (cf. project.py:109-119): keyframe a re-observes keyframe b from a nearby pose
+        self.revisits = [(a, b) for a, b in ((self.K - 3, 5), (self.K // 2, 11), (self.K - 40, self.K // 3),
+                                             (self.K // 3 + 7, 2)) if 0 <= b < a < self.K]
+        for a, b in self.revisits:
+            flip = (torch.rand((n, 61, 8), device=dev, generator=g) < 0.06)
+            bits = (flip * (2 ** torch.arange(8, device=dev))).sum(-1).to(torch.uint8)
+            perm = torch.randperm(n, device=dev, generator=g)
+            pool[a * n:(a + 1) * n] = pool[b * n:(b + 1) * n][perm] ^ bits
+            pool[a * n:(a + 1) * n, 60] &= 0x3F
+            lb = links[b * n:(b + 1) * n][perm.cpu().numpy()]
+            Z = fxb / (lb[:, 0] - lb[:, 1])
+            P3 = np.stack([(lb[:, 0] - cx) * Z / fx, (lb[:, 2] - cy) * Z / fx, Z], axis=1)
+            R = synth._rodrigues(rng.normal(0, 0.02, 3))
+            t = np.array([0.3, -0.05, -0.6]) + rng.normal(0, 0.05, 3)
+            Pa = (P3 - t) @ R
+            ok = Pa[:, 2] > 2.0
+            xa = fx * Pa[:, 0] / Pa[:, 2] + cx + rng.normal(0, 0.3, n)
+            ya = fx * Pa[:, 1] / Pa[:, 2] + cy + rng.normal(0, 0.3, n)
+            la = f32(np.stack([xa, xa - fxb / Pa[:, 2], ya], axis=1))
+            blk_l = links[a * n:(a + 1) * n]
+            blk_l[ok] = la[ok]
+        self.links_host = links
         self.pool = pool
+        self.links = torch.from_numpy(links).to(dev)
         self.pool_pinned = torch.empty(pool.shape, dtype=torch.uint8, pin_memory=True).copy_(pool)
+        self.links_pinned = torch.from_numpy(links).pin_memory()
         pairs = sdist.candidate_pairs(self.K)
         self.pairs = pairs
-        b = sdist.candidate_blocks(pairs, np.full(self.K, self.n), world)
+        b = sdist.candidate_blocks(pairs, np.full(self.K, n), world)
         self.lo, self.hi = int(b[rank]), int(b[rank + 1])
-        self.lengths = (b[1:] - b[:-1]) * self.n
-        mine = pairs[self.lo:self.hi]
-        self.q_off = torch.from_numpy((mine[:, 0].astype(np.int64) * self.n).astype(np.int32)).to(dev)
-        self.t_off = torch.from_numpy((mine[:, 1].astype(np.int64) * self.n).astype(np.int32)).to(dev)
-        self.cnt = torch.full((len(mine),), self.n, dtype=torch.int32, device=dev)
-        self.blk = 32768
-        self.out_off = torch.arange(0, self.blk, dtype=torch.int32, device=dev) * self.n
-        self.table = torch.empty((len(mine) * self.n,), dtype=torch.int32, device=dev)
+        self.lengths = (b[1:] - b[:-1]) * n
+        self.pair_lengths = b[1:] - b[:-1]
+        self.kf_off = np.arange(self.K, dtype=np.int64) * n
+        self.kf_cnt = np.full(self.K, n, dtype=np.int64)
+        self.H = 888  # calc_ransac_iteration(40), loop_closure.py:425
+        self.ver = loop.CandidateVerifier(block_pairs=args.loop_block)
+        self.table = torch.empty(((self.hi - self.lo) * n,), dtype=torch.int32, device=dev)
         self.units_total = len(pairs)
-        self.launches_per_step = -(-len(mine) // self.blk)
-        self.desc_pairs_total = float(len(pairs)) * self.n * self.n
-        self.config = {"workload": "configs[3]: loop-closure candidate matching, each keyframe vs all prior keyframes",
-                       "keyframes": self.K, "descriptors_per_keyframe": self.n, "candidate_pairs": len(pairs),
+        self.launches_per_step = 1 + 4 * -(-(self.hi - self.lo) // args.loop_block)
+        self.desc_pairs_total = float(len(pairs)) * n * n
+        self.config = {"workload": "configs[3]: loop-closure candidate verification, each keyframe vs all prior "
+                                   "keyframes: Hamming match + RANSAC-PnP (888 hypotheses) per candidate",
+                       "keyframes": self.K, "descriptors_per_keyframe": n, "candidate_pairs": len(pairs),
+                       "ransac_iterations": self.H, "planted_revisits": self.revisits,
                        "l2_policy": "keyframe pool 55 MB is L2-resident by design (every keyframe is re-read ~K/2 "
-                                    "times); result tables (808 MB total) stream to HBM",
+                                    "times); match tables (808 MB total) and RANSAC inputs stream through HBM",
                        "sharding": f"candidate blocks balanced by Nq*Nt, {world} rank(s), pool replicated"}
 
-    def _run(self, pool):
-        from slamfe import ops, dist as sdist
-        n_mine = self.hi - self.lo
-        for p0 in range(0, n_mine, self.blk):
-            p1 = min(n_mine, p0 + self.blk)
-            ops.hamming_pairs(pool, self.q_off[p0:p1], self.cnt[p0:p1], pool, self.t_off[p0:p1], self.cnt[p0:p1],
-                              self.out_off, p1 - p0, self.n, self.n, 61, row_keys=self.table[p0 * self.n:p1 * self.n],
-                              out_rows_total=(p1 - p0) * self.n, best_only=True, compact=True)
-        if self.world > 1:
+    def _run(self, pool, links):
+        from slamfe import dist as sdist
+        res = self.ver.verify(pool, links, self.kf_off, self.kf_cnt, self.pairs[self.lo:self.hi], n_iter=self.H,
+                              seed=1, pair_base=self.lo, key_table=self.table, sync=False)
+        self.best = res["best_dev"]
+        if self.world > 1:  # the path's only collectives: best-match tables and inlier tables
             self.gathered, _ = sdist.all_gather_padded(self.table, lengths=self.lengths)
-        return self.table
+            self.gathered_best, _ = sdist.all_gather_padded(self.best, lengths=self.pair_lengths)
+        return self.best
 
     def step(self):
-        return self._run(self.pool)
+        return self._run(self.pool, self.links)
 
     def e2e_step(self):
         torch = self.torch
         self.pool.copy_(self.pool_pinned, non_blocking=True)
-        table = self._run(self.pool)
+        self.links.copy_(self.links_pinned, non_blocking=True)
+        best = self._run(self.pool, self.links)
         if not hasattr(self, "host_table"):
-            self.host_table = torch.empty(table.shape, dtype=table.dtype, pin_memory=True)
-        self.host_table.copy_(table, non_blocking=True)
+            self.host_table = torch.empty(self.table.shape, dtype=self.table.dtype, pin_memory=True)
+            self.host_best = torch.empty(best.shape, dtype=best.dtype, pin_memory=True)
+        self.host_table.copy_(self.table, non_blocking=True)
+        self.host_best.copy_(best, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return self.pool_pinned.numel(), table.numel() * 4
+        return self.pool_pinned.numel() + self.links_pinned.numel() * 8, self.table.numel() * 4 + best.numel() * 4
 
     def time_kernel(self):
         from slamfe import ops
-        n_mine = min(self.hi - self.lo, self.blk)
+        torch = self.torch
+        n_mine = min(self.hi - self.lo, 16384)
+        mine = self.pairs[self.lo:self.lo + n_mine]
+        dev = self.dev
+        q_off = torch.from_numpy((mine[:, 0].astype(np.int64) * self.n).astype(np.int32)).to(dev)
+        t_off = torch.from_numpy((mine[:, 1].astype(np.int64) * self.n).astype(np.int32)).to(dev)
+        cnt = torch.full((n_mine,), self.n, dtype=torch.int32, device=dev)
+        out_off = torch.arange(0, n_mine, dtype=torch.int32, device=dev) * self.n
 
         def fn():
-            ops.hamming_pairs(self.pool, self.q_off[:n_mine], self.cnt[:n_mine], self.pool, self.t_off[:n_mine],
-                              self.cnt[:n_mine], self.out_off, n_mine, self.n, self.n, 61,
+            ops.hamming_pairs(self.pool, q_off, cnt, self.pool, t_off, cnt, out_off, n_mine, self.n, self.n, 61,
                               row_keys=self.table[:n_mine * self.n], out_rows_total=n_mine * self.n, best_only=True,
                               compact=True)
         self._kernel_pairs = float(n_mine) * self.n * self.n
@@ -212,32 +245,50 @@ class LoopWorkload(Workload):
         return {"kernel": "hamming_top2_kernel<256,2,rows only,best-only,9 adders> via slamfe_hamming_top2_pairs",
                 "bound": "popc", "achieved": ach, "peak": peak_popc, "unit": "Gpopc32/s", "frac": ach / peak_popc,
                 "traffic": None, "launch_ms": launch_ms,
-                "note": "algorithmic 16 popc32 per descriptor pair; carry-save adders execute 7 (DESIGN.md 2.1)",
+                "note": "algorithmic 16 popc32 per descriptor pair; carry-save adders execute 7 (DESIGN.md 2.1); the "
+                        "RANSAC stages (hypotheses + scoring, fp64-bound) are the other ~40 % of a step",
                 "gdesc_pairs_per_s": self._kernel_pairs / launch_ms / 1e6}
 
     def cpu_baseline(self):
         import cv2
         from oracle import ref_oracle as ora
+        from slamfe import utils
         cv2.setNumThreads(os.cpu_count() or 1)
         mm = cv2.BFMatcher(normType=cv2.NORM_HAMMING, crossCheck=False)
         pool = self.pool_pinned.numpy()
-        sample = self.pairs[self.lo:self.lo + 48]
-        kf = lambda i: pool[i * self.n:(i + 1) * self.n]
+        n = self.n
+        kf = lambda i: pool[i * n:(i + 1) * n]
+        lk = lambda i: self.links_host[i * n:(i + 1) * n]
+        sample = [tuple(p) for p in self.pairs[self.lo:self.lo + 6].tolist()]
+        if self.rank == 0 and self.world == 1:
+            sample += [r for r in self.revisits][:2]
         mm.match(kf(1), kf(0))
         t0 = time.perf_counter()
-        res = [mm.match(kf(i), kf(j)) for i, j in sample]
+        out = []
+        for i, j in sample:  # check_candidate_match, loop_closure.py:405-436
+            ms = mm.match(kf(i), kf(j))
+            ti = np.fromiter((m.trainIdx for m in ms), np.int64, n)
+            idx = ora.ransac_pnp_for_tracking_db(np.arange(n), ti, lk(i), lk(j), 40, utils.K, utils.M1, utils.M2)
+            out.append((ti, np.fromiter((int(m.distance) for m in ms), np.int64, n), 0 if idx is None else len(idx)))
         dt = time.perf_counter() - t0
-        table = self.table[: len(sample) * self.n].cpu().numpy().view(np.uint32).reshape(len(sample), self.n)
-        ok = True
-        for p, ms in enumerate(res):
-            ok &= bool(np.array_equal(table[p] & 0x3FFFFF, np.fromiter((m.trainIdx for m in ms), np.uint32, self.n)))
-            ok &= bool(np.array_equal(table[p] >> 22, np.fromiter((int(m.distance) for m in ms), np.uint32, self.n)))
-        oi, od = ora.match(kf(sample[0][0]), kf(sample[0][1]))
-        ok &= bool(np.array_equal(table[0] & 0x3FFFFF, oi.astype(np.uint32)))
-        return ({"value": len(sample) / dt, "unit": self.unit, "cores": cv2.getNumThreads(), "kind": "reference",
-                 "sample": f"{len(sample)} candidate pairs ({dt:.2f} s): cv2 {cv2.__version__} "
-                           f"BFMatcher(NORM_HAMMING).match as loop_closure.py:422 calls it, all host threads"},
-                {"pairs_checked": len(sample), "match_tables_bit_exact": ok})
+        table = self.table.cpu().numpy().view(np.uint32)
+        best = self.best.cpu().numpy()
+        index = {tuple(p): k for k, p in enumerate(self.pairs[self.lo:self.hi].tolist())}
+        ok, ratios = True, []
+        for (i, j), (ti, td, cnt) in zip(sample, out):
+            k = index[(i, j)]
+            row = table[k * n:(k + 1) * n]
+            ok &= bool(np.array_equal(row & 0x3FFFFF, ti.astype(np.uint32)) and np.array_equal(row >> 22, td.astype(np.uint32)))
+            ratios.append((int(best[k, 1]), cnt))
+        accepted = {tuple(r): int(best[index[tuple(r)], 1]) for r in self.revisits if tuple(r) in index}
+        n_acc = int((best[:, 1] > 120).sum())
+        return ({"value": len(sample) / dt, "unit": self.unit, "cores": cv2.getNumThreads(), "kind": "port",
+                 "sample": f"{len(sample)} candidate pairs ({dt:.1f} s): cv2 {cv2.__version__} BFMatcher.match "
+                           f"(all host threads) + the oracle's restatement of ransac_pnp's 888-iteration loop with "
+                           f"cv2 EPnP (single thread, as the reference), loop_closure.py:405-436"},
+                {"pairs_checked": len(sample), "match_tables_bit_exact": ok,
+                 "inliers_gpu_vs_cpu": ratios, "planted_revisit_inliers": {str(k): v for k, v in accepted.items()},
+                 "candidates_accepted_over_120_inliers": n_acc, "planted": len(self.revisits)})
 
 
 # ------------------------------------------------------------------------------------------------

@@ -245,6 +245,19 @@ int slamfe_track_gather(const uint32_t *fwd_keys, const uint32_t *bwd_keys, cons
                         slamfe_stream_t stream);
 
 /*
+ * Loop-closure candidate gather (check_candidate_match, backend/loop/loop_closure.py:405-436, feeding
+ * ransac_pnp, ransac.py:132-146): candidate p = (keyframe A at rows q_off[p], q_cnt[p] links; keyframe B
+ * at rows t_off[p]); keys = compact best keys of slamfe_hamming_top2_pairs (one per query, at
+ * out_off[p] + i).  kf_pts (.,3): triangulated links of every keyframe (slamfe_triangulate_links_f64),
+ * kf_links (.,3) fp64 [x_left, x_right, y].  Writes pts / lpix / rpix rows at out_off[p] + i:
+ * A's 3-D point i and B's link pixels at trainIdx — the inputs of slamfe_ransac_hypotheses /
+ * slamfe_ransac_score with pt_off = out_off, pt_cnt = q_cnt.
+ */
+int slamfe_pairs_gather(const uint32_t *keys, const int32_t *q_off, const int32_t *q_cnt, const int32_t *t_off,
+                        const int32_t *out_off, int n_problems, int max_nq, const double *kf_pts,
+                        const double *kf_links, double *pts, double *lpix, double *rpix, slamfe_stream_t stream);
+
+/*
  * in_prev_cur of database.py:84-85: inlier_fwd[l_off[f] + good_j[k]] = 1 for the mutual matches k of
  * pair f that the best hypothesis accepts (best_mask from slamfe_ransac_score), 0 elsewhere
  * (rows_total bytes are cleared first).  When no hypothesis scored > 0 inliers (best[f][0] < 0) every

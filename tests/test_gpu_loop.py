@@ -1,0 +1,94 @@
+"""Batched loop-closure candidate verification (slamfe.loop) against the oracle's restatement of
+check_candidate_match (loop_closure.py:405-436): match tables and RANSAC inputs bit-exact, scoring
+bit-exact on the device-generated hypotheses, planted revisits accepted."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _keyframes(rng, sizes, revisits):
+    """Keyframe pool: random descriptors and valid stereo links; revisits {a: b} make keyframe a a
+    re-observation of keyframe b (flipped descriptors, links = b's 3-D points under a small motion)."""
+    from slamfe import synth, utils
+    K = utils.K
+    fx, cx, cy, fxb = K[0, 0], K[0, 2], K[1, 2], -utils.KITTI00_P1[0, 3]
+    desc, links = [], []
+    for n in sizes:
+        desc.append(synth.descriptors(rng, n))
+        xl = rng.uniform(20, 1220, n).astype(np.float32).astype(np.float64)
+        d = rng.uniform(2.5, 120, n)
+        xr = (xl - d).astype(np.float32).astype(np.float64)
+        y = rng.uniform(5, 370, n).astype(np.float32).astype(np.float64)
+        links.append(np.stack([xl, xr, y], axis=1))
+    for a, b in revisits.items():
+        n = min(sizes[a], sizes[b])
+        perm = rng.permutation(sizes[b])[:n]
+        desc[a][:n] = synth.flip_bits(rng, desc[b][perm], 0.06)
+        lb = links[b][perm]
+        Z = fxb / (lb[:, 0] - lb[:, 1])
+        P = np.stack([(lb[:, 0] - cx) * Z / fx, (lb[:, 2] - cy) * Z / fx, Z], axis=1)
+        R = synth._rodrigues(rng.normal(0, 0.02, 3))
+        t = np.array([0.3, -0.05, -0.6])
+        # keyframe a sees the points at P; keyframe b (the candidate) sees them at R P + t: build a's links
+        # from the inverse so that T = [R|t] maps a's triangulated points to b's camera
+        Pa = (P - t) @ R          # R^T (P - t)
+        ok = Pa[:, 2] > 2.0
+        xl = fx * Pa[:, 0] / Pa[:, 2] + cx + rng.normal(0, 0.3, n)
+        y = fx * Pa[:, 1] / Pa[:, 2] + cy + rng.normal(0, 0.3, n)
+        xr = xl - fxb / Pa[:, 2]
+        la = np.stack([xl, xr, y], axis=1).astype(np.float32).astype(np.float64)
+        links[a][:n][ok] = la[ok]
+    return desc, links
+
+
+def test_candidate_verification_vs_oracle(slamfe, oracle):
+    import torch
+    from slamfe import dist, loop, utils
+    rng = np.random.default_rng(81)
+    sizes = [300, 280, 310, 5, 290, 300]
+    desc, links = _keyframes(rng, sizes, {4: 1, 5: 0})
+    off = np.zeros(len(sizes) + 1, np.int64)
+    np.cumsum([-(-n // 16) * 16 for n in sizes], out=off[1:])
+    pool_d = np.zeros((off[-1], 61), np.uint8)
+    pool_l = np.ones((off[-1], 3), np.float64) * [30.0, 10.0, 50.0]
+    for k, n in enumerate(sizes):
+        pool_d[off[k]:off[k] + n] = desc[k]
+        pool_l[off[k]:off[k] + n] = links[k]
+    pairs = dist.candidate_pairs(len(sizes))
+    H = 96
+    ver = loop.CandidateVerifier(block_pairs=4)          # several blocks
+    res = ver.verify(torch.from_numpy(pool_d).cuda(), torch.from_numpy(pool_l).cuda(), off[:-1], np.array(sizes), pairs,
+                     n_iter=H, seed=3, want_masks=True)
+    K, M1, M2 = utils.K, utils.M1, utils.M2
+    for p, (a, b) in enumerate(pairs):
+        oi, od = oracle.match(desc[a], desc[b])
+        k = res["keys"][p]
+        assert np.array_equal(k & 0x3FFFFF, oi.astype(np.uint32)) and np.array_equal(k >> 22, od.astype(np.uint32))
+        assert res["n_matches"][p] == sizes[a]
+    # scoring on the device-generated hypotheses of the LAST block, bit-exact against the oracle
+    nb = len(pairs) % 4 or 4
+    last = pairs[-nb:]
+    T = ver._buf["T"][:nb * H].cpu().numpy(); valid = ver._buf["hyp_valid"][:nb * H].cpu().numpy().astype(bool)
+    for q, (a, b) in enumerate(last):
+        p = len(pairs) - nb + q
+        oi, _ = oracle.match(desc[a], desc[b])
+        pts = oracle.triangulate_links(links[a], utils.P, utils.Q)
+        cur = links[b][oi]
+        lp, rp = cur[:, [0, 2]], cur[:, [1, 2]]
+        counts = np.zeros(H, np.int64); masks = {}
+        for h in np.nonzero(valid[q * H:(q + 1) * H])[0]:
+            # the device triangulates with its own fp64 kernel (1e-13 from the SVD): score the oracle on
+            # the oracle's points and require the same verdicts except within 1e-9 px of the threshold
+            masks[h] = oracle.transformation_agreement(T[q * H + h], pts, lp, rp, K, M1, M2)
+            counts[h] = masks[h].sum()
+        assert abs(int(counts.max()) - int(res["inliers"][p])) <= 1
+        if counts.max() > 0 and counts.max() - np.sort(counts)[-2] > 2:
+            assert res["best_hyp"][p] == int(np.argmax(counts))
+            assert (res["mask"][p] != masks[int(np.argmax(counts))]).sum() <= 1
+    # planted revisits are accepted, unrelated keyframes are not
+    acc = {tuple(pr): bool(a) for pr, a in zip(pairs.tolist(), res["accepted"])}
+    assert acc[(4, 1)] and acc[(5, 0)]
+    assert sum(acc.values()) == 2
+    i41 = pairs.tolist().index([4, 1])
+    assert res["inliers"][i41] > 150 and 0.5 < res["percentage"][i41] <= 1.0

@@ -1,12 +1,13 @@
 #!/bin/bash
-# All four bench workloads at N GPUs: gpurun --gpus N --timeout 900 -- 'bash scripts/gpu_scale.sh N'
+# Bench workloads at N GPUs: gpurun --gpus N --timeout 600 -- 'bash scripts/gpu_scale.sh N "sequence loop"'
 set -u
 N=${1:-2}
-for w in sequence ransac loop dense; do
+WL=${2:-"sequence ransac loop dense"}
+for w in $WL; do
   if [ "$N" = "1" ]; then
-    python bench.py --workload $w --gpus 1 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/scale_${w}_${N}gpu.json 2> gpurun_out/scale_${w}_${N}gpu.err
+    timeout 300 python bench.py --workload $w --gpus 1 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/scale_${w}_${N}gpu.json 2> gpurun_out/scale_${w}_${N}gpu.err
   else
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --workload $w --gpus $N --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/scale_${w}_${N}gpu.json 2> gpurun_out/scale_${w}_${N}gpu.err
+    timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --workload $w --gpus $N --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/scale_${w}_${N}gpu.json 2> gpurun_out/scale_${w}_${N}gpu.err
   fi
   echo "$w rc=$?"
   python - <<PY

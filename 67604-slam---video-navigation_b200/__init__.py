@@ -14,6 +14,7 @@ Layout
     matching.py / triangulation.py / ransac.py / utils.py   mirrors of the reference modules
     frontend.py      device-resident batched sequence pipeline (frame pairs per launch)
     loop.py          batched loop-closure candidate verification (match + RANSAC-PnP per candidate)
+    database.py      batched drop-in for the reference's create_db loop (feeds TrackingDB.add_frame)
     dist.py          one-process-per-GPU sharding + NCCL all-gather of result tables
     patch.py         rebinding of the reference's module attributes (the "plugin" hook)
     synth.py         seeded synthetic KITTI-shaped inputs
@@ -24,12 +25,12 @@ from ._cabi import EXPORTED_SYMBOLS, KEY_IDX_BITS, KEY_IDX_MASK, KEY_NONE, Slamf
 __version__ = "0.1.0"
 
 __all__ = ["EXPORTED_SYMBOLS", "KEY_IDX_BITS", "KEY_IDX_MASK", "KEY_NONE", "SlamfeError", "load_library",
-           "matching", "triangulation", "ransac", "utils", "ops", "frontend", "loop", "dist", "patch", "synth"]
+           "matching", "triangulation", "ransac", "utils", "ops", "frontend", "loop", "database", "dist", "patch", "synth"]
 
 
 def __getattr__(name):
-    if name in ("matching", "triangulation", "ransac", "utils", "ops", "frontend", "loop", "dist", "patch", "synth",
-                "build"):
+    if name in ("matching", "triangulation", "ransac", "utils", "ops", "frontend", "loop", "database", "dist", "patch",
+                "synth", "build"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

@@ -209,3 +209,39 @@ def test_tracking_edge_cases(slamfe):
     assert int(o1["n_links"][0]) > 0
     g1, _, _ = frontend.FrontEnd().run_host(one, track=True, h_max=8)
     assert g1["n_links"][0] == int(o1["n_links"][0])
+
+
+def test_create_db_adapter_on_the_gpu(slamfe, oracle):
+    """slamfe.database.create_db: the add_frame arguments built from the GPU tables equal the oracle's
+    restatement of database.py:12-27,54-66 (links, features, forward matches); the conversion itself is
+    checked against the real reference TrackingDB by tests/test_reference_db.py on the CPU."""
+    from slamfe import database as sdb
+
+    class FakeDB:
+        def __init__(self):
+            self.calls, self.frameID_to_inliers_percent = [], {}
+
+        def add_frame(self, links, left_features, matches_to_previous_left=None, inliers=None):
+            self.calls.append((links, left_features, matches_to_previous_left, inliers))
+
+    rng = np.random.default_rng(75)
+    frames = make_sequence(rng, [600, 750, 500, 640])
+    db = sdb.create_db([(pl, pr, dl, dr) for dl, dr, pl, pr in frames], FakeDB(), chunk_frames=2, h_max=32)
+    assert len(db.calls) == len(frames)
+    prev_feat = None
+    for f, ((dl, dr, pl, pr), (links, feats, ms, inl)) in enumerate(zip(frames, db.calls)):
+        cq, ct, _ = oracle.match_crosscheck(dl, dr)
+        ii, _ = oracle.extract_inliers_outliers(pl, pr, cq, ct)
+        valid, ref_links = oracle.create_links(pl, pr, cq[ii], ct[ii])
+        assert np.array_equal(np.array([(l.x_left, l.x_right, l.y) for l in links]).reshape(-1, 3),
+                              np.asarray(ref_links, dtype=np.float64).reshape(-1, 3))
+        assert np.array_equal(feats, dl[valid])
+        assert db.frameID_to_inliers_percent[f] == 100 * (len(ii) / len(cq))
+        if f == 0:
+            assert ms is None and inl is None
+        else:
+            fi, fd = oracle.match(prev_feat, dl[valid])
+            assert [m.queryIdx for m in ms] == list(range(len(prev_feat))) and all(m.imgIdx == 0 for m in ms)
+            assert np.array_equal([m.trainIdx for m in ms], fi) and np.array_equal([int(m.distance) for m in ms], fd)
+            assert inl.dtype == bool and len(inl) == len(ms)
+        prev_feat = dl[valid]

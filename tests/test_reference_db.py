@@ -1,0 +1,129 @@
+"""The batched create_db adapter (slamfe.database) against the UNMODIFIED reference's create_db +
+TrackingDB (backend/database/database.py:30-89, tracking_database.py), run through oracle/refshim.py.
+
+CPU only; skipped where /root/reference is absent (the GPU box).  The reference runs with its own
+cv2 path on synthetic frames (its image reader and AKAZE detector are replaced by a provider of
+synthetic keypoints / descriptors — inputs, not code under test); every `add_frame` call is
+recorded.  The adapter is fed host tables in the exact format FrontEnd.run_host(track=True) returns,
+built here from the oracle (the product's CUDA path cannot run in this container; the same tables
+are checked against the oracle on the GPU by tests/test_gpu_frontend.py), with the reference's own
+inlier flags, and must drive a fresh reference TrackingDB into an identical state."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import refshim  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+
+
+def _synthetic_frames(n):
+    from slamfe import synth
+    seq = synth.torch_sequence(n, first_frame=3, seed=5, device="cpu", lo=150, hi=260)
+    frames = []
+    for f in range(n):
+        lo, k = int(seq["l_off"][f]), int(seq["n_l"][f])
+        frames.append((seq["pts_l"][lo:lo + k].numpy(), seq["pts_r"][lo:lo + k].numpy(),
+                       seq["desc_l"][lo:lo + k].numpy(), seq["desc_r"][lo:lo + k].numpy()))
+    return frames
+
+
+def _oracle_tables(seq, frames, oracle, inlier_flags):
+    """Host tables in FrontEnd.run_host(track=True) format from the oracle."""
+    from slamfe import _cabi
+    L, F = seq.desc_l.shape[0], seq.n_frames
+    t = {"match_t": np.full(L, -1, np.int32), "n_matches": np.zeros(F, np.int32), "n_links": np.zeros(F, np.int32),
+         "link_src": np.full(L, -1, np.int32), "fwd_keys": np.full((L, 2), -1, np.int32),
+         "inlier_fwd": np.zeros(L, np.uint8)}
+    feats = []
+    for f, (pl, pr, dl, dr) in enumerate(frames):
+        lo = int(seq.l_off[f])
+        cq, ct, _ = oracle.match_crosscheck(dl, dr)
+        inl, _ = oracle.extract_inliers_outliers(pl, pr, cq, ct)
+        t["match_t"][lo + cq] = ct
+        t["n_matches"][f], t["n_links"][f] = len(cq), len(inl)
+        t["link_src"][lo:lo + len(inl)] = cq[inl]
+        feats.append(dl[cq[inl]])
+    for f in range(F - 1):
+        lo, k = int(seq.l_off[f]), len(feats[f])
+        fi, fd = oracle.match(feats[f], feats[f + 1])
+        t["fwd_keys"][lo:lo + k, 0] = ((fd.astype(np.uint32) << _cabi.KEY_IDX_BITS) | fi.astype(np.uint32)).view(np.int32)
+        t["inlier_fwd"][lo:lo + k] = inlier_flags[f + 1]
+    return t
+
+
+def test_adapter_drives_the_reference_tracking_db_identically(oracle):
+    import cv2
+    ref = refshim.load()
+    from slamfe import database as sdb
+    frames = _synthetic_frames(5)
+
+    class Provider:  # stands in for cv2.AKAZE: keypoints / descriptors of the synthetic frame
+        def detectAndCompute(self, token, mask):
+            side, f = token
+            pts = frames[f][0 if side == "L" else 1]
+            desc = frames[f][2 if side == "L" else 3]
+            return tuple(cv2.KeyPoint(float(x), float(y), 1.0) for x, y in pts), desc
+
+    old_feature, old_reader = ref.matching.FEATURE, ref.inputs.read_images
+    ref.matching.FEATURE = Provider()
+    ref.inputs.read_images = lambda idx: (("L", idx), ("R", idx))
+    calls = []
+    try:
+        db_ref = ref.tracking_database.TrackingDB()
+        real_add = db_ref.add_frame
+
+        def spy(links, left_features, matches_to_previous_left=None, inliers=None):
+            calls.append((links, left_features, matches_to_previous_left, inliers))
+            return real_add(links, left_features, matches_to_previous_left, inliers)
+
+        db_ref.add_frame = spy
+        np.random.seed(3)
+        ref.database.create_db(start_frame=0, num_frames=len(frames), db=db_ref)
+    finally:
+        ref.matching.FEATURE, ref.inputs.read_images = old_feature, old_reader
+    assert len(calls) == len(frames)
+
+    seq = sdb.pack_frames([(pl, pr, dl, dr) for pl, pr, dl, dr in frames], pin=False)
+    flags = [None] + [np.asarray(c[3], dtype=bool) for c in calls[1:]]
+    tables = _oracle_tables(seq, frames, oracle, flags)
+    db_new = ref.tracking_database.TrackingDB()
+    replay = []
+    real_add2 = db_new.add_frame
+    db_new.add_frame = lambda links, left_features, matches_to_previous_left=None, inliers=None: (
+        replay.append((links, left_features, matches_to_previous_left, inliers)),
+        real_add2(links, left_features, matches_to_previous_left, inliers))[1]
+    for fr in sdb.frames_from_tables(seq, tables):  # what create_db() does after run_host()
+        links = [ref.tracking_database.Link(float(a), float(b), float(c)) for a, b, c in fr["links"]]
+        db_new.frameID_to_inliers_percent[fr["frame"]] = fr["inliers_percent"]
+        if fr["frame"] == 0:
+            db_new.add_frame(links=links, left_features=fr["features"], matches_to_previous_left=None, inliers=None)
+            continue
+        n = len(fr["fwd_idx"])
+        ms = np.empty(n, dtype=object)
+        ms[:] = list(map(cv2.DMatch, range(n), fr["fwd_idx"].tolist(), [0] * n, fr["fwd_dist"].tolist()))
+        db_new.add_frame(links, fr["features"], ms, fr["inliers"])
+
+    # every add_frame argument equals the reference's own
+    for (l0, f0, m0, i0), (l1, f1, m1, i1) in zip(calls, replay):
+        assert [(a.x_left, a.x_right, a.y) for a in l0] == [(a.x_left, a.x_right, a.y) for a in l1]
+        assert np.array_equal(f0, f1)
+        if m0 is None:
+            assert m1 is None
+        else:
+            assert [(m.queryIdx, m.trainIdx, m.imgIdx, m.distance) for m in m0] == \
+                   [(m.queryIdx, m.trainIdx, m.imgIdx, m.distance) for m in m1]
+            assert np.array_equal(np.asarray(i0, bool), np.asarray(i1, bool))
+    # ... and so does the resulting database
+    assert db_ref.frameID_to_inliers_percent == db_new.frameID_to_inliers_percent
+    assert db_ref.trackId_to_frames == db_new.trackId_to_frames and len(db_ref.trackId_to_frames) > 20
+    assert db_ref.frameId_to_trackIds_list == db_new.frameId_to_trackIds_list
+    assert sorted(db_ref.linkId_to_link) == sorted(db_new.linkId_to_link)
+    for k, ln in db_ref.linkId_to_link.items():
+        other = db_new.linkId_to_link[k]
+        assert (ln.x_left, ln.x_right, ln.y) == (other.x_left, other.x_right, other.y)
+    db_new._check_consistency() if hasattr(db_new, "_check_consistency") else None

@@ -9,7 +9,8 @@ import os
 from ctypes import c_char_p, c_int, c_int32, c_int64, c_uint64, c_void_p, POINTER
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libslamfe.so")
+# SLAMFE_LIBRARY overrides the in-tree build (development: A/B timing of two builds on one box)
+LIB_PATH = os.environ.get("SLAMFE_LIBRARY") or os.path.join(PKG_DIR, "libslamfe.so")
 
 KEY_IDX_BITS = 22
 KEY_IDX_MASK = (1 << KEY_IDX_BITS) - 1

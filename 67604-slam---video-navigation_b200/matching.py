@@ -184,7 +184,29 @@ def get_akaze_matcher_lr_matcher():
     return feature, matcher_left_right, matcher
 
 
-_filter_staging = _Staging()
+class _ThreadLocalStaging:
+    """One _Staging per Python thread: the module-level entry points (extract_inliers_outliers,
+    triangulate_links, transformation_agreement, ...) may be called from several threads, each on its
+    own CUDA stream, and must not share pinned buffers."""
+
+    def __init__(self):
+        import threading
+        self._tls = threading.local()
+
+    def _get(self):
+        st = getattr(self._tls, "st", None)
+        if st is None:
+            st = self._tls.st = _Staging()
+        return st
+
+    def to_device(self, key, arr):
+        return self._get().to_device(key, arr)
+
+    def to_host(self, key, t):
+        return self._get().to_host(key, t)
+
+
+_filter_staging = _ThreadLocalStaging()
 
 
 def extract_inliers_outliers(kp_left, kp_right, matches):

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import ops
 from . import utils as _utils
-from .matching import _Staging
+from .matching import _ThreadLocalStaging
 from .triangulation import links_to_array, triangulate_link_array
 from .utils import rodriguez_to_mat
 
@@ -22,7 +22,7 @@ SUCCESS_PROBABILITY = 0.9999999999  # ransac.py:9
 K, M1, M2 = _utils.K, _utils.M1, _utils.M2  # ransac.py:11
 P, Q = K @ M1, K @ M2                        # ransac.py:12
 
-_st = _Staging()
+_st = _ThreadLocalStaging()
 
 
 def set_cameras(k, m1, m2):

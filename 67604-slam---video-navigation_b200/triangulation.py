@@ -8,9 +8,9 @@ from __future__ import annotations
 import numpy as np
 
 from . import ops
-from .matching import _Staging
+from .matching import _ThreadLocalStaging
 
-_st = _Staging()
+_st = _ThreadLocalStaging()
 
 
 def links_to_array(links) -> np.ndarray:

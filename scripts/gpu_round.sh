@@ -22,8 +22,8 @@ BENCH_FULL="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e"
 $BENCH_FULL > gpurun_out/plain_full.log 2>&1 &&
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:hamming_top2 -s 6 -c 2 --csv --log-file gpurun_out/traffic_full.csv $BENCH_FULL > gpurun_out/ncu_traffic.log 2>&1
 echo "ncu traffic rc=$?"
-# full captures of the other kernels on their own benchmark (ransac scorer, triangulation, stereo epilogue)
-python scripts/kernel_bench.py > gpurun_out/kernel_bench.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"ransac_score|triangulate_links|ransac_hypotheses" -c 4 -f -o gpurun_out/prof_other python scripts/kernel_bench.py > gpurun_out/ncu_other.log 2>&1
+# full captures of the other kernels of a step (scorer, generator, gather, stereo epilogue, triangulation)
+$BENCH_SMALL > gpurun_out/plain_small3.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"ransac_score|ransac_hypotheses|track_gather|stereo_links|triangulate_links" -s 15 -c 5 -f -o gpurun_out/prof_other $BENCH_SMALL > gpurun_out/ncu_other.log 2>&1
 echo "ncu other rc=$?"
 tail -3 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log; cat gpurun_out/bench.json; cat gpurun_out/bench_ref.json

@@ -16,11 +16,7 @@
 #include <math.h>
 #include <stdint.h>
 
-#ifdef __CUDACC__
-#define SLAMFE_HD __host__ __device__ __forceinline__
-#else
-#define SLAMFE_HD inline
-#endif
+#include "hd.cuh"
 
 namespace slamfe {
 namespace p3p {

@@ -1,0 +1,110 @@
+// Arithmetic core of the RANSAC-PnP scorer (used by ransac.cu; plain C++ under the SLAMFE_HD macros so
+// that oracle/ransac_host_shim.cpp can compile the very same code for the host and the CPU test suite
+// can fuzz it against the reference formula — millions of borderline cases, no GPU needed).
+// Every multiply-add that must be fused is an explicit fma(); nothing else relies on contraction, so
+// the host build (-ffp-contract=off) and the device build produce identical bits.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "hd.cuh"
+
+namespace slamfe {
+
+struct RansacCams {
+    double K[9];
+    double M1[12];
+    double M2[12];
+};
+
+// out (3x4) = (K @ T) @ [M; 0 0 0 1], each dot product = sequential FMA over k (dgemm order).
+SLAMFE_HD_PLAIN void hypothesis_matrices(const RansacCams &c, const double *T, double *PL, double *PR)
+{
+    double KT[12];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double acc = c.K[3 * i] * T[j];
+            acc = fma(c.K[3 * i + 1], T[4 + j], acc);
+            acc = fma(c.K[3 * i + 2], T[8 + j], acc);
+            KT[4 * i + j] = acc;
+        }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double h3 = (j == 3) ? 1.0 : 0.0;  // last row of [M; 0 0 0 1]
+            double a = KT[4 * i] * c.M1[j];
+            a = fma(KT[4 * i + 1], c.M1[4 + j], a);
+            a = fma(KT[4 * i + 2], c.M1[8 + j], a);
+            a = fma(KT[4 * i + 3], h3, a);
+            PL[4 * i + j] = a;
+            double b = KT[4 * i] * c.M2[j];
+            b = fma(KT[4 * i + 1], c.M2[4 + j], b);
+            b = fma(KT[4 * i + 2], c.M2[8 + j], b);
+            b = fma(KT[4 * i + 3], h3, b);
+            PR[4 * i + j] = b;
+        }
+}
+
+SLAMFE_HD double project_row(const double *m, double x, double y, double z)
+{
+    double acc = m[0] * x;
+    acc = fma(m[1], y, acc);
+    acc = fma(m[2], z, acc);
+    return acc + m[3];  // fma(m[3], 1.0, acc)
+}
+
+// ransac.py:38-56 for one (hypothesis, correspondence), exactly as the reference evaluates it:
+// IEEE division, subtraction, strict < 2.  M = PL (12) followed by PR (12).
+SLAMFE_HD_NOINLINE bool agrees_exact(const double *M, double x, double y, double z, double lx, double ly,
+                                          double rx, double ry)
+{
+    const double l0 = project_row(M + 0, x, y, z), l1 = project_row(M + 4, x, y, z), l2 = project_row(M + 8, x, y, z);
+    const double r0 = project_row(M + 12, x, y, z), r1 = project_row(M + 16, x, y, z),
+                 r2 = project_row(M + 20, x, y, z);
+    const double ul = l0 / l2, vl = l1 / l2, ur = r0 / r2, vr = r1 / r2;
+    return (fabs(vl - ly) < 2.0) && (fabs(ul - lx) < 2.0) && (fabs(vr - ry) < 2.0) && (fabs(ur - rx) < 2.0);
+}
+
+// Division-free evaluation of  |num/den - pix| < 2  with a certificate.
+// With w = num/den - pix in exact arithmetic, the reference's rounded result t = fl(fl(num/den) - pix)
+// satisfies |t - w| <= (|pix| + 2|w|) * 2^-52, so its verdict equals (|w| < 2) whenever
+// ||w| - 2| exceeds that.  Here e = fma(-pix, den, num) = w*den (one rounding), diff = |e| - 2|den|
+// and the verdict (diff < 0) is certified when  |diff| > (|pix| + 8) * |den| * 2^-49:
+//   * |e| <= 4|den|: the reference's error, scaled by |den|, is <= (|pix| + 8)|den| 2^-52 and the
+//     roundings of e and diff add <= 4|den| 2^-52 — together < 1/8 of the bound;
+//   * |e| >  4|den|: |diff| >= |e|/2, far above 2|e| 2^-52, and the bound covers the |pix| term.
+// NaN and 0/0 never certify and take the exact path.  The fp64 divider sequences (~25
+// instructions each, 4 per pair) were 3/4 of the kernel; a test now costs 3 fp64 operations.
+// cert = (|pix| + 8) * 2^-49 is hoisted out of the hypothesis loop.
+SLAMFE_HD double cert_of(double pix) { return (fabs(pix) + 8.0) * 0x1p-49; }
+
+struct RatioTest {
+    double diff, bound;
+    SLAMFE_HD RatioTest(double num, double den, double pix, double cert)
+    {
+        const double e = fma(-pix, den, num);
+        const double ad = fabs(den);
+        diff = fma(-2.0, ad, fabs(e));
+        bound = cert * ad;
+    }
+    SLAMFE_HD bool surely_outside() const { return diff > bound; }
+    SLAMFE_HD bool surely_inside() const { return diff < -bound; }
+};
+
+SLAMFE_HD bool agrees(const double *M, double x, double y, double z, double lx, double ly, double rx,
+                                       double ry)
+{
+    const double l0 = project_row(M + 0, x, y, z), l1 = project_row(M + 4, x, y, z), l2 = project_row(M + 8, x, y, z);
+    const double r0 = project_row(M + 12, x, y, z), r1 = project_row(M + 16, x, y, z),
+                 r2 = project_row(M + 20, x, y, z);
+    const RatioTest t0(l1, l2, ly, cert_of(ly)), t1(l0, l2, lx, cert_of(lx));
+    const RatioTest t2(r1, r2, ry, cert_of(ry)), t3(r0, r2, rx, cert_of(rx));
+    if (t0.surely_outside() | t1.surely_outside() | t2.surely_outside() | t3.surely_outside()) return false;
+    if (t0.surely_inside() & t1.surely_inside() & t2.surely_inside() & t3.surely_inside()) return true;
+    return agrees_exact(M, x, y, z, lx, ly, rx, ry);
+}
+
+}  // namespace slamfe

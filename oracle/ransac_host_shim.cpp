@@ -1,0 +1,45 @@
+// TEST INFRASTRUCTURE ONLY.  Compiles the product's scorer arithmetic (csrc/ransac_core.cuh) for the
+// HOST so that the CPU test suite (-m "not gpu") can fuzz the certified division-free inlier test
+// against the reference formula (ransac.py:38-56 in numpy) on millions of borderline cases.
+// Build with -ffp-contract=off: every fused multiply-add in the header is an explicit fma(), so the
+// host build computes exactly what the device does.  The product never loads this library.
+#include "../67604-slam---video-navigation_b200/csrc/ransac_core.cuh"
+
+using namespace slamfe;
+
+// For n points and ONE hypothesis T (3x4): out_agrees = agrees() (certified test + exact fallback),
+// out_exact = agrees_exact(), out_fast = the division-free verdict alone, out_cert = 1 where the
+// certificate decided (no fallback needed).
+extern "C" void ransac_host_score(const double *K, const double *M1, const double *M2, const double *T,
+                                  const double *pts, const double *lpix, const double *rpix, long n,
+                                  unsigned char *out_agrees, unsigned char *out_exact, unsigned char *out_fast,
+                                  unsigned char *out_cert)
+{
+    RansacCams c;
+    for (int k = 0; k < 9; ++k) c.K[k] = K[k];
+    for (int k = 0; k < 12; ++k) { c.M1[k] = M1[k]; c.M2[k] = M2[k]; }
+    double M[24];
+    hypothesis_matrices(c, T, M, M + 12);
+    for (long i = 0; i < n; ++i) {
+        const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+        const double lx = lpix[2 * i], ly = lpix[2 * i + 1], rx = rpix[2 * i], ry = rpix[2 * i + 1];
+        out_agrees[i] = agrees(M, x, y, z, lx, ly, rx, ry);
+        out_exact[i] = agrees_exact(M, x, y, z, lx, ly, rx, ry);
+        const double l0 = project_row(M + 0, x, y, z), l1 = project_row(M + 4, x, y, z), l2 = project_row(M + 8, x, y, z);
+        const double r0 = project_row(M + 12, x, y, z), r1 = project_row(M + 16, x, y, z), r2 = project_row(M + 20, x, y, z);
+        const RatioTest t0(l1, l2, ly, cert_of(ly)), t1(l0, l2, lx, cert_of(lx));
+        const RatioTest t2(r1, r2, ry, cert_of(ry)), t3(r0, r2, rx, cert_of(rx));
+        const bool out = t0.surely_outside() | t1.surely_outside() | t2.surely_outside() | t3.surely_outside();
+        const bool in = t0.surely_inside() & t1.surely_inside() & t2.surely_inside() & t3.surely_inside();
+        out_cert[i] = out | in;
+        out_fast[i] = (t0.diff < 0) & (t1.diff < 0) & (t2.diff < 0) & (t3.diff < 0);
+    }
+}
+
+extern "C" void ransac_host_matrices(const double *K, const double *M1, const double *M2, const double *T, double *PLPR)
+{
+    RansacCams c;
+    for (int k = 0; k < 9; ++k) c.K[k] = K[k];
+    for (int k = 0; k < 12; ++k) { c.M1[k] = M1[k]; c.M2[k] = M2[k]; }
+    hypothesis_matrices(c, T, PLPR, PLPR + 12);
+}

@@ -84,6 +84,83 @@ class P3PHost:
         return np.array(list(idx), dtype=np.int32)
 
 
+_RANSAC_LIB_PATH = os.path.join(_HERE, "libransac_host.so")
+_ransac_lib = None
+
+
+def build_ransac_shim(force: bool = False) -> str:
+    """Compile oracle/ransac_host_shim.cpp (the product's csrc/ransac_core.cuh, built for the HOST
+    with -ffp-contract=off) -> oracle/libransac_host.so."""
+    src = os.path.join(_HERE, "ransac_host_shim.cpp")
+    csrc = os.path.join(os.path.dirname(_HERE), "67604-slam---video-navigation_b200", "csrc")
+    newest = max(os.path.getmtime(src), os.path.getmtime(os.path.join(csrc, "ransac_core.cuh")),
+                 os.path.getmtime(os.path.join(csrc, "hd.cuh")))
+    if force or not os.path.exists(_RANSAC_LIB_PATH) or os.path.getmtime(_RANSAC_LIB_PATH) < newest:
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++", src, "-o",
+                               _RANSAC_LIB_PATH])
+    return _RANSAC_LIB_PATH
+
+
+class ScorerHost:
+    """ctypes view of the host build of csrc/ransac_core.cuh (test infrastructure)."""
+
+    def __init__(self):
+        global _ransac_lib
+        if _ransac_lib is None:
+            build_ransac_shim()
+            _ransac_lib = ctypes.CDLL(_RANSAC_LIB_PATH)
+        self.lib = _ransac_lib
+
+    def score(self, T, pts, l_pix, r_pix, K, M1, M2):
+        """Returns bool arrays (agrees, exact, fast, certified) for one hypothesis."""
+        dp, up = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ubyte)
+        c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        arrs = [c(K), c(M1), c(M2), c(T), c(pts), c(l_pix), c(r_pix)]
+        n = arrs[4].shape[0]
+        outs = [np.zeros(n, np.uint8) for _ in range(4)]
+        self.lib.ransac_host_score(*[a.ctypes.data_as(dp) for a in arrs], ctypes.c_long(n),
+                                   *[o.ctypes.data_as(up) for o in outs])
+        return tuple(o.astype(bool) for o in outs)
+
+    def matrices(self, T, K, M1, M2):
+        dp = ctypes.POINTER(ctypes.c_double)
+        c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        out = np.zeros(24)
+        self.lib.ransac_host_matrices(c(K).ctypes.data_as(dp), c(M1).ctypes.data_as(dp), c(M2).ctypes.data_as(dp),
+                                      c(T).ctypes.data_as(dp), out.ctypes.data_as(dp))
+        return out[:12].reshape(3, 4), out[12:].reshape(3, 4)
+
+
+_TRI_LIB_PATH = os.path.join(_HERE, "libtriangulate_host.so")
+_tri_lib = None
+
+
+def build_triangulate_shim(force: bool = False) -> str:
+    """Compile oracle/triangulate_host_shim.cpp (csrc/triangulate_core.cuh for the HOST)."""
+    src = os.path.join(_HERE, "triangulate_host_shim.cpp")
+    csrc = os.path.join(os.path.dirname(_HERE), "67604-slam---video-navigation_b200", "csrc")
+    newest = max(os.path.getmtime(src), os.path.getmtime(os.path.join(csrc, "triangulate_core.cuh")))
+    if force or not os.path.exists(_TRI_LIB_PATH) or os.path.getmtime(_TRI_LIB_PATH) < newest:
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=fast", "-shared", "-fPIC", "-x", "c++", src, "-o",
+                               _TRI_LIB_PATH])
+    return _TRI_LIB_PATH
+
+
+def triangulate_links_host_build(links, P, Q):
+    """(M, 3) links -> (M, 3) points through the HOST build of the product's triangulation core."""
+    global _tri_lib
+    if _tri_lib is None:
+        build_triangulate_shim()
+        _tri_lib = ctypes.CDLL(_TRI_LIB_PATH)
+    dp = ctypes.POINTER(ctypes.c_double)
+    c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    links, Pc, Qc = c(links).reshape(-1, 3), c(P), c(Q)
+    out = np.zeros_like(links)
+    _tri_lib.triangulate_host_links(links.ctypes.data_as(dp), ctypes.c_long(len(links)), Pc.ctypes.data_as(dp),
+                                    Qc.ctypes.data_as(dp), out.ctypes.data_as(dp))
+    return out
+
+
 def _load():
     global _lib
     if _lib is None:

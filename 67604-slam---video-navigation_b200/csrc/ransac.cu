@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_score_kernel(const RansacPa
     __shared__ alignas(16) double sM[RS_HC][24];
     __shared__ int s_cnt[RS_HC];
     __shared__ uint8_t s_valid[RS_HC];
+    __shared__ uint8_t s_shared[RS_HC];  // hypothesis' left/right matrices share their first three columns
     __shared__ unsigned long long s_red[RS_THREADS / 32];
     __shared__ int s_last, s_best;
 
@@ -64,7 +65,12 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_score_kernel(const RansacPa
             bool ok = tid < nh;
             if (ok && p.hyp_valid) ok = p.hyp_valid[hbase + h0 + tid] != 0;
             s_valid[tid] = ok;
-            if (ok) hypothesis_matrices(p.cam, p.T + (hbase + h0 + tid) * 12, &sM[tid][0], &sM[tid][12]);
+            bool shared = false;
+            if (ok) {
+                hypothesis_matrices(p.cam, p.T + (hbase + h0 + tid) * 12, &sM[tid][0], &sM[tid][12]);
+                shared = shares_rotation_columns(&sM[tid][0], &sM[tid][12]);
+            }
+            s_shared[tid] = shared;
         }
         // RS_PP correspondences per thread, in registers for the whole hypothesis sweep
         double x[RS_PP], y[RS_PP], z[RS_PP], lx[RS_PP], ly[RS_PP], rx[RS_PP], ry[RS_PP];
@@ -89,12 +95,16 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_score_kernel(const RansacPa
             const double *M = &sM[h][0];
             // left camera first: most hypotheses of a RANSAC run are bad, and a warp whose points
             // are all certainly outside on the left image skips the right camera altogether
+            const bool shared = s_shared[h];  // CTA-uniform
             bool maybe[RS_PP], left_in[RS_PP];
+            double acc[RS_PP][3];
             bool any = false;
 #pragma unroll
             for (int k = 0; k < RS_PP; ++k) {
-                const double l0 = project_row(M + 0, x[k], y[k], z[k]), l1 = project_row(M + 4, x[k], y[k], z[k]),
-                             l2 = project_row(M + 8, x[k], y[k], z[k]);
+                acc[k][0] = project_acc(M + 0, x[k], y[k], z[k]);
+                acc[k][1] = project_acc(M + 4, x[k], y[k], z[k]);
+                acc[k][2] = project_acc(M + 8, x[k], y[k], z[k]);
+                const double l0 = acc[k][0] + M[3], l1 = acc[k][1] + M[7], l2 = acc[k][2] + M[11];
                 const RatioTest tv(l1, l2, ly[k], cly[k]), tu(l0, l2, lx[k], clx[k]);
                 maybe[k] = have[k] && !(tv.surely_outside() | tu.surely_outside());
                 left_in[k] = tv.surely_inside() & tu.surely_inside();
@@ -103,8 +113,13 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_score_kernel(const RansacPa
             if (!__any_sync(0xFFFFFFFFu, any)) continue;  // warp-uniform
 #pragma unroll
             for (int k = 0; k < RS_PP; ++k) {
-                const double r0 = project_row(M + 12, x[k], y[k], z[k]), r1 = project_row(M + 16, x[k], y[k], z[k]),
-                             r2 = project_row(M + 20, x[k], y[k], z[k]);
+                double r0, r1, r2;
+                if (shared) {  // same bits as the full rows: identical accumulators, right fourth column
+                    r0 = acc[k][0] + M[15]; r1 = acc[k][1] + M[19]; r2 = acc[k][2] + M[23];
+                } else {
+                    r0 = project_row(M + 12, x[k], y[k], z[k]); r1 = project_row(M + 16, x[k], y[k], z[k]);
+                    r2 = project_row(M + 20, x[k], y[k], z[k]);
+                }
                 const RatioTest tv(r1, r2, ry[k], cry[k]), tu(r0, r2, rx[k], crx[k]);
                 bool in = false;
                 if (maybe[k] && !(tv.surely_outside() | tu.surely_outside())) {

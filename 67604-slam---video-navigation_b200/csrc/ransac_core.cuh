@@ -48,12 +48,32 @@ SLAMFE_HD_PLAIN void hypothesis_matrices(const RansacCams &c, const double *T, d
         }
 }
 
-SLAMFE_HD double project_row(const double *m, double x, double y, double z)
+// One row of a 3x4 projection times [x y z 1]: the dgemm accumulation order of numpy's matmul.
+// project_acc is the part that does not involve the fourth column.
+SLAMFE_HD double project_acc(const double *m, double x, double y, double z)
 {
     double acc = m[0] * x;
     acc = fma(m[1], y, acc);
     acc = fma(m[2], z, acc);
-    return acc + m[3];  // fma(m[3], 1.0, acc)
+    return acc;
+}
+SLAMFE_HD double project_row(const double *m, double x, double y, double z)
+{
+    return project_acc(m, x, y, z) + m[3];  // fma(m[3], 1.0, acc)
+}
+
+// Rectified rigs (M1 = [I|0], M2 = [I|t]): the left and right projection matrices of a hypothesis
+// share their first three columns BIT FOR BIT, so the right camera's rows are the left camera's
+// accumulators plus the right fourth column — the same bits as the full evaluation at a quarter
+// of the cost.  Checked per hypothesis; NaN entries compare unequal and take the general path.
+SLAMFE_HD bool shares_rotation_columns(const double *PL, const double *PR)
+{
+    bool same = true;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) same = same && (PL[4 * i + j] == PR[4 * i + j]);
+    return same;
 }
 
 // ransac.py:38-56 for one (hypothesis, correspondence), exactly as the reference evaluates it:

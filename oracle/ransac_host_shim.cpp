@@ -13,13 +13,14 @@ using namespace slamfe;
 extern "C" void ransac_host_score(const double *K, const double *M1, const double *M2, const double *T,
                                   const double *pts, const double *lpix, const double *rpix, long n,
                                   unsigned char *out_agrees, unsigned char *out_exact, unsigned char *out_fast,
-                                  unsigned char *out_cert)
+                                  unsigned char *out_cert, unsigned char *out_shared_rows_equal)
 {
     RansacCams c;
     for (int k = 0; k < 9; ++k) c.K[k] = K[k];
     for (int k = 0; k < 12; ++k) { c.M1[k] = M1[k]; c.M2[k] = M2[k]; }
     double M[24];
     hypothesis_matrices(c, T, M, M + 12);
+    const bool shared = shares_rotation_columns(M, M + 12);
     for (long i = 0; i < n; ++i) {
         const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
         const double lx = lpix[2 * i], ly = lpix[2 * i + 1], rx = rpix[2 * i], ry = rpix[2 * i + 1];
@@ -32,6 +33,12 @@ extern "C" void ransac_host_score(const double *K, const double *M1, const doubl
         const bool out = t0.surely_outside() | t1.surely_outside() | t2.surely_outside() | t3.surely_outside();
         const bool in = t0.surely_inside() & t1.surely_inside() & t2.surely_inside() & t3.surely_inside();
         out_cert[i] = out | in;
+        // the kernel's shortcut for rectified rigs: right rows = left accumulators + right 4th column
+        const double a0 = project_acc(M + 0, x, y, z), a1 = project_acc(M + 4, x, y, z), a2 = project_acc(M + 8, x, y, z);
+        const bool lsame = (a0 + M[3] == l0 || l0 != l0) && (a1 + M[7] == l1 || l1 != l1) && (a2 + M[11] == l2 || l2 != l2);
+        const double s0 = a0 + M[15], s1 = a1 + M[19], s2 = a2 + M[23];
+        const bool rsame = (s0 == r0 || r0 != r0) && (s1 == r1 || r1 != r1) && (s2 == r2 || r2 != r2);
+        out_shared_rows_equal[i] = shared ? (lsame && rsame && (s0 != s0) == (r0 != r0) && (s2 != s2) == (r2 != r2)) : 2;
         out_fast[i] = (t0.diff < 0) & (t1.diff < 0) & (t2.diff < 0) & (t3.diff < 0);
     }
 }

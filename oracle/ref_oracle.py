@@ -112,15 +112,17 @@ class ScorerHost:
         self.lib = _ransac_lib
 
     def score(self, T, pts, l_pix, r_pix, K, M1, M2):
-        """Returns bool arrays (agrees, exact, fast, certified) for one hypothesis."""
+        """Returns bool arrays (agrees, exact, fast, certified) for one hypothesis, plus `shared`: uint8 per
+        point, 1 = the rectified-rig shortcut reproduces the full right-camera rows bit for bit, 0 = it
+        does not (a bug), 2 = the hypothesis does not qualify for the shortcut."""
         dp, up = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ubyte)
         c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         arrs = [c(K), c(M1), c(M2), c(T), c(pts), c(l_pix), c(r_pix)]
         n = arrs[4].shape[0]
-        outs = [np.zeros(n, np.uint8) for _ in range(4)]
+        outs = [np.zeros(n, np.uint8) for _ in range(5)]
         self.lib.ransac_host_score(*[a.ctypes.data_as(dp) for a in arrs], ctypes.c_long(n),
                                    *[o.ctypes.data_as(up) for o in outs])
-        return tuple(o.astype(bool) for o in outs)
+        return tuple(o.astype(bool) for o in outs[:4]) + (outs[4],)
 
     def matrices(self, T, K, M1, M2):
         dp = ctypes.POINTER(ctypes.c_double)

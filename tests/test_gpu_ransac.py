@@ -239,3 +239,24 @@ def test_device_resident_ransac_matches_the_cv2_path_statistically(slamfe, golde
     ref_pose = g["pnp_pose"]
     assert np.abs(pose.matrix()[:3, 3] - ref_pose[:3, 3]).max() < 0.05   # metres
     assert np.abs(pose.matrix()[:3, :3] - ref_pose[:3, :3]).max() < 0.01
+
+
+def test_non_rectified_rig_takes_the_general_path(slamfe, oracle):
+    """The scorer reuses the left camera's accumulators for the right camera when a hypothesis' two
+    projection matrices share their first three columns bit for bit (rectified rigs).  A rig with a
+    rotated right camera must take the general path and still match the reference exactly."""
+    from slamfe import ransac, synth
+    rng = np.random.default_rng(93)
+    K, M1, M2 = synth.cameras()
+    M2r = np.hstack([synth._rodrigues(np.array([0.0, 0.02, 0.01])), M2[:, 3:4]])
+    Ts, pts, lp, rp = synth.pnp_problem(rng, 1500, 70)
+    try:
+        ransac.set_cameras(K, M1, M2r)
+        counts, best, cnt, mask = ransac.score_hypotheses(Ts, pts, lp, rp)
+        oc, ob, om = oracle.score_hypotheses(Ts, pts, lp, rp, K, M1, M2r)
+        assert np.array_equal(counts, oc) and best == ob and np.array_equal(mask, om)
+    finally:
+        ransac.set_cameras(K, M1, M2)
+    counts, best, cnt, mask = ransac.score_hypotheses(Ts, pts, lp, rp)
+    oc, ob, om = oracle.score_hypotheses(Ts, pts, lp, rp, K, M1, M2)
+    assert np.array_equal(counts, oc) and best == ob and np.array_equal(mask, om) and counts.max() > 100

@@ -69,10 +69,11 @@ def test_certified_scoring_equals_reference_on_borderline_cases(oracle, scale):
         for col, (arr, c) in enumerate(((lp, 0), (lp, 1), (rp, 0), (rp, 1))):
             m = (which == col) | (which == 4)
             arr[m, c] = _nudge(arr[m, c] + sign[m, col], ulps[m, col])
-        a, e, f, cert = host.score(T, pts, lp, rp, K, M1, M2)
+        a, e, f, cert, shared = host.score(T, pts, lp, rp, K, M1, M2)
         ref = _ref(oracle, T, pts, lp, rp, K, M1, M2)
         assert np.array_equal(a, ref) and np.array_equal(e, ref)
         assert np.array_equal(f[cert], ref[cert])            # the certificate is sound
+        assert (shared == 1).all()                           # KITTI rig: the shared-accumulator shortcut is exact
         total += n
         uncert += int((~cert).sum())
     assert uncert > 0.2 * total                              # the borderline cases really hit the fallback
@@ -94,10 +95,16 @@ def test_certified_scoring_random_magnitudes_and_degenerates(oracle):
         rp = np.nan_to_num(uvr, nan=0.0, posinf=1e300, neginf=-1e300) + jit[:, ::-1]
         pts[:5] = [[0, 0, 0], [1, 2, 0], [np.nan, 1, 5], [np.inf, 1, 5], [1e308, 1e308, 1e308]]
         lp[5:10, 0] = [np.nan, np.inf, -np.inf, 1e308, -1e308]
-        a, e, f, cert = host.score(T, pts, lp, rp, K, M1, M2)
+        a, e, f, cert, shared = host.score(T, pts, lp, rp, K, M1, M2)
         ref = _ref(oracle, T, pts, lp, rp, K, M1, M2)
         assert np.array_equal(a, ref) and np.array_equal(e, ref)
         assert np.array_equal(f[cert], ref[cert])
+        assert (shared == 1).all()
+    # a non-rectified rig (rotated right camera) does not qualify for the shortcut and stays exact
+    M2r = np.hstack([synth._rodrigues(np.array([0.0, 0.02, 0.0])), M2[:, 3:4]])
+    Ts, pts, lp, rp = synth.pnp_problem(rng, 20000, 1)
+    a, e, f, cert, shared = host.score(Ts[0], pts, lp, rp, K, M1, M2r)
+    assert (shared == 2).all() and np.array_equal(a, _ref(oracle, Ts[0], pts, lp, rp, K, M1, M2r))
 
 
 def test_triangulation_core_vs_svd_on_extreme_links(oracle):

@@ -310,7 +310,9 @@ class FrontEnd:
             o.update(trk)
         if self._pinned_out is None or any(k not in self._pinned_out or self._pinned_out[k].shape != o[k].shape
                                            for k in keys):
-            self._pinned_out = {k: torch.empty(o[k].shape, dtype=o[k].dtype, pin_memory=True) for k in keys}
+            self._pinned_out = {k: torch.zeros(o[k].shape, dtype=o[k].dtype, pin_memory=True) for k in keys}
+            if "best" in self._pinned_out:  # pairs that are never computed (single-frame sequence) read "no hypothesis"
+                self._pinned_out["best"][:, 0] = -1
         hout = self._pinned_out
         if self._streams is None:
             self._streams = tuple(torch.cuda.Stream(device=dev) for _ in range(4))

@@ -199,6 +199,58 @@ def golden_database(ref):
                         bwd_t=np.array([m.trainIdx for m in bwd], np.int32), good_idx=np.array(good))
 
 
+def golden_create_db(ref):
+    """The UNMODIFIED reference's create_db (database.py:30-89) + TrackingDB on 5 synthetic frames
+    (3-D-consistent motion), with its image reader / AKAZE detector replaced by a provider of the
+    synthetic keypoints and descriptors (inputs, not code under test) and np.random seeded.  Every
+    add_frame call is recorded: links, features, forward matches, inlier flags."""
+    import torch  # noqa: F401  (synth.torch_sequence)
+    n = 5
+    seq = synth.torch_sequence(n, first_frame=3, seed=5, device="cpu", lo=150, hi=260)
+    frames = []
+    for f in range(n):
+        lo, k = int(seq["l_off"][f]), int(seq["n_l"][f])
+        frames.append((seq["pts_l"][lo:lo + k].numpy(), seq["pts_r"][lo:lo + k].numpy(),
+                       seq["desc_l"][lo:lo + k].numpy(), seq["desc_r"][lo:lo + k].numpy()))
+
+    class Provider:
+        def detectAndCompute(self, token, mask):
+            side, f = token
+            pts = frames[f][0 if side == "L" else 1]
+            return tuple(cv2.KeyPoint(float(x), float(y), 1.0) for x, y in pts), frames[f][2 if side == "L" else 3]
+
+    old_feature, old_reader = ref.matching.FEATURE, ref.inputs.read_images
+    ref.matching.FEATURE = Provider()
+    ref.inputs.read_images = lambda idx: (("L", idx), ("R", idx))
+    calls = []
+    try:
+        db = ref.tracking_database.TrackingDB()
+        real_add = db.add_frame
+
+        def spy(links, left_features, matches_to_previous_left=None, inliers=None):
+            calls.append((links, left_features, matches_to_previous_left, inliers))
+            return real_add(links, left_features, matches_to_previous_left, inliers)
+
+        db.add_frame = spy
+        np.random.seed(3)
+        ref.database.create_db(start_frame=0, num_frames=n, db=db)
+    finally:
+        ref.matching.FEATURE, ref.inputs.read_images = old_feature, old_reader
+    out = {"n_frames": np.array(n)}
+    for f, (pl, pr, dl, dr) in enumerate(frames):
+        out[f"pts_l{f}"], out[f"pts_r{f}"], out[f"desc_l{f}"], out[f"desc_r{f}"] = pl, pr, dl, dr
+    for f, (links, feats, ms, inl) in enumerate(calls):
+        out[f"links{f}"] = np.array([(l.x_left, l.x_right, l.y) for l in links], np.float64).reshape(-1, 3)
+        out[f"features{f}"] = feats
+        out[f"inliers_percent{f}"] = np.array(db.frameID_to_inliers_percent[f])
+        if ms is not None:
+            out[f"match_t{f}"] = np.array([m.trainIdx for m in ms], np.int32)
+            out[f"match_d{f}"] = np.array([m.distance for m in ms], np.float32)
+            out[f"inliers{f}"] = np.asarray(inl, dtype=bool)
+    out["n_tracks"] = np.array(len(db.trackId_to_frames))
+    np.savez_compressed(os.path.join(OUT, "create_db.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = refshim.load()
@@ -207,6 +259,7 @@ def main():
     golden_triangulation(ref)
     golden_ransac(ref)
     golden_database(ref)
+    golden_create_db(ref)
     print("golden vectors written to", OUT, "cv2", cv2.__version__, "numpy", np.__version__)
     for f in sorted(os.listdir(OUT)):
         print(" ", f, os.path.getsize(os.path.join(OUT, f)), "bytes")

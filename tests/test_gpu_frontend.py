@@ -245,3 +245,44 @@ def test_create_db_adapter_on_the_gpu(slamfe, oracle):
             assert np.array_equal([m.trainIdx for m in ms], fi) and np.array_equal([int(m.distance) for m in ms], fd)
             assert inl.dtype == bool and len(inl) == len(ms)
         prev_feat = dl[valid]
+
+
+def test_create_db_against_the_reference_golden(slamfe, golden):
+    """tests/golden/create_db.npz holds every add_frame call of the UNMODIFIED reference's create_db on 5
+    synthetic frames (oracle/make_golden.py: golden_create_db).  slamfe.database.create_db on the same
+    frames must pass identical links, features and forward matches; the inlier flags come from a
+    randomised RANSAC on both sides (the reference's run is seeded, ~20-60 iterations) and must agree
+    as consensus sets."""
+    from slamfe import database as sdb
+    g = golden("create_db")
+    n = int(g["n_frames"])
+    frames = [(g[f"pts_l{f}"], g[f"pts_r{f}"], g[f"desc_l{f}"], g[f"desc_r{f}"]) for f in range(n)]
+
+    class FakeDB:
+        def __init__(self):
+            self.calls, self.frameID_to_inliers_percent = [], {}
+
+        def add_frame(self, links, left_features, matches_to_previous_left=None, inliers=None):
+            self.calls.append((links, left_features, matches_to_previous_left, inliers))
+
+    db = sdb.create_db(frames, FakeDB(), chunk_frames=3, h_max=128, seed=2)
+    assert len(db.calls) == n
+    jac = []
+    for f, (links, feats, ms, inl) in enumerate(db.calls):
+        assert np.array_equal(np.array([(l.x_left, l.x_right, l.y) for l in links], np.float64).reshape(-1, 3),
+                              g[f"links{f}"])
+        assert np.array_equal(feats, g[f"features{f}"])
+        assert db.frameID_to_inliers_percent[f] == float(g[f"inliers_percent{f}"])
+        if f == 0:
+            assert ms is None
+            continue
+        assert np.array_equal([m.trainIdx for m in ms], g[f"match_t{f}"])
+        assert np.array_equal(np.array([m.distance for m in ms], np.float32), g[f"match_d{f}"])
+        a, b = np.asarray(inl, bool), g[f"inliers{f}"]
+        assert a.shape == b.shape
+        # the reference's seeded run missed the consensus on one pair (3 inliers); the GPU run (128
+        # exact minimal solutions instead of ~25 EPnP ones) must find at least what the reference found
+        assert a.sum() >= 0.8 * b.sum(), (f, int(a.sum()), int(b.sum()))
+        if b.sum() >= 20:  # ... and its consensus set contains the reference's
+            jac.append((a & b).sum() / b.sum())
+    assert len(jac) >= 3 and min(jac) >= 0.75, jac

@@ -249,6 +249,27 @@ def golden_create_db(ref):
             out[f"inliers{f}"] = np.asarray(inl, dtype=bool)
     out["n_tracks"] = np.array(len(db.trackId_to_frames))
     np.savez_compressed(os.path.join(OUT, "create_db.npz"), **out)
+    return db
+
+
+def golden_loop_candidates(db):
+    """The UNMODIFIED reference's check_candidate_match (backend/loop/loop_closure.py:405-436:
+    MATCHER.match at :422 + ransac_pnp(..., inliers_percent=40) at :425, 888 iterations) on keyframes of
+    the TrackingDB built by golden_create_db: four overlapping pairs and one unrelated pair."""
+    lc = refshim.load_loop_closure().loop_closure
+    pairs = [(1, 0), (2, 1), (3, 2), (4, 3), (4, 1)]
+    out = {"pairs": np.array(pairs, np.int32)}
+    for k, (a, b) in enumerate(pairs):
+        np.random.seed(20 + k)
+        fa, fb = db.features(a), db.features(b)
+        ms = lc.MATCHER.match(fa, fb)
+        inl, pct, pose = lc.check_candidate_match(a, b, db)
+        out[f"match_t{k}"] = np.array([m.trainIdx for m in ms], np.int32)
+        out[f"match_d{k}"] = np.array([m.distance for m in ms], np.float32)
+        out[f"inlier_q{k}"] = np.array([m.queryIdx for m in inl], np.int32)
+        out[f"percentage{k}"] = np.array(float(pct))
+        out[f"pose{k}"] = pose.matrix() if pose is not None else np.zeros((0, 0))
+    np.savez_compressed(os.path.join(OUT, "loop_candidates.npz"), **out)
 
 
 def main():
@@ -259,7 +280,7 @@ def main():
     golden_triangulation(ref)
     golden_ransac(ref)
     golden_database(ref)
-    golden_create_db(ref)
+    golden_loop_candidates(golden_create_db(ref))
     print("golden vectors written to", OUT, "cv2", cv2.__version__, "numpy", np.__version__)
     for f in sorted(os.listdir(OUT)):
         print(" ", f, os.path.getsize(os.path.join(OUT, f)), "bytes")

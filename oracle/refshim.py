@@ -187,3 +187,34 @@ def load(data_dir: str | None = None, n_frames: int = 4):
         data_dir=data_dir, arguments=args)
     _loaded = ns
     return ns
+
+
+def load_loop_closure():
+    """Additionally import the reference's `backend/loop/loop_closure.py` (for
+    `check_candidate_match`, :405-436).  Its import chain pulls in the GTSAM back-end modules
+    (bundle.py, pose_graph.py, gtsam_utils.py), whose module-level code only needs gtsam NAMES to
+    exist: the gtsam stub gets a permissive module `__getattr__` (any other attribute is a MagicMock).
+    Nothing GTSAM-dependent is ever called through this shim."""
+    from unittest.mock import MagicMock
+    ns = load()
+    if getattr(ns, "loop_closure", None) is not None:
+        return ns
+    for name in ("gtsam", "gtsam.utils", "gtsam.utils.plot", "gtsam.symbol_shorthand"):
+        mod = sys.modules[name]
+        if "__getattr__" not in mod.__dict__:
+            mod.__dict__["__getattr__"] = lambda attr, _m=mod: MagicMock(name=f"{_m.__name__}.{attr}")
+    real_open = builtins.open
+
+    def redirected_open(path, *a, **k):
+        if isinstance(path, str) and path.startswith(_MAC_PREFIX):
+            path = ns.data_dir + path[len(_MAC_PREFIX):]
+        return real_open(path, *a, **k)
+
+    builtins.open = redirected_open
+    try:
+        import final_project.backend.loop.loop_closure as loop_closure
+    finally:
+        builtins.open = real_open
+    loop_closure.MATCHER = ns.matching.MATCHER   # imported by value (loop_closure.py:12)
+    ns.loop_closure = loop_closure
+    return ns

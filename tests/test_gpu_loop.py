@@ -92,3 +92,46 @@ def test_candidate_verification_vs_oracle(slamfe, oracle):
     assert sum(acc.values()) == 2
     i41 = pairs.tolist().index([4, 1])
     assert res["inliers"][i41] > 150 and 0.5 < res["percentage"][i41] <= 1.0
+
+
+def test_candidates_against_the_reference_golden(slamfe, golden):
+    """tests/golden/loop_candidates.npz: the UNMODIFIED reference's check_candidate_match
+    (loop_closure.py:405-436) on keyframes of the TrackingDB its own create_db built
+    (tests/golden/create_db.npz).  Match tables must be identical; where the reference's randomised
+    888-iteration RANSAC found a consensus, the GPU verifier's consensus contains it; the unrelated
+    pair stays far below the acceptance threshold on both sides."""
+    import torch
+    from slamfe import loop
+    db, g = golden("create_db"), golden("loop_candidates")
+    n = int(db["n_frames"])
+    feats = [db[f"features{f}"] for f in range(n)]
+    links = [db[f"links{f}"] for f in range(n)]
+    sizes = [len(x) for x in feats]
+    off = np.zeros(n + 1, np.int64)
+    np.cumsum([-(-s // 16) * 16 for s in sizes], out=off[1:])
+    pool_d = np.zeros((off[-1], 61), np.uint8)
+    pool_l = np.ones((off[-1], 3)) * [30.0, 10.0, 50.0]
+    for f in range(n):
+        pool_d[off[f]:off[f] + sizes[f]] = feats[f]
+        pool_l[off[f]:off[f] + sizes[f]] = links[f]
+    pairs = g["pairs"]
+    res = loop.CandidateVerifier().verify(torch.from_numpy(pool_d).cuda(), torch.from_numpy(pool_l).cuda(), off[:-1],
+                                          np.array(sizes), pairs, inliers_percent=40, seed=4, want_masks=True)
+    found = 0
+    for k, (a, b) in enumerate(pairs):
+        keys = res["keys"][k]
+        assert np.array_equal(keys & 0x3FFFFF, g[f"match_t{k}"].astype(np.uint32))
+        assert np.array_equal((keys >> 22).astype(np.float32), g[f"match_d{k}"])
+        ref_in = np.zeros(sizes[a], bool)
+        ref_in[g[f"inlier_q{k}"]] = True
+        got_in = res["mask"][k]
+        assert got_in.sum() == res["inliers"][k] and res["n_matches"][k] == sizes[a]
+        assert got_in.sum() >= 0.8 * ref_in.sum()
+        if ref_in.sum() >= 20:
+            found += 1
+            assert (got_in & ref_in).sum() / ref_in.sum() >= 0.75
+            assert abs(res["percentage"][k] - float(g[f"percentage{k}"])) < 0.1
+    assert found >= 2
+    unrelated = [k for k, (a, b) in enumerate(pairs) if abs(int(a) - int(b)) > 1]
+    assert all(res["inliers"][k] < 15 and len(g[f"inlier_q{k}"]) < 15 for k in unrelated)
+    assert not res["accepted"].any()       # tiny keyframes: nobody reaches the 120-inlier threshold

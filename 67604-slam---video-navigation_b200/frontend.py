@@ -129,6 +129,35 @@ RESULT_KEYS = ("match_t", "n_matches", "n_links", "link_src", "links", "xyz", "f
 TRACK_KEYS = ("inlier_fwd", "best", "n_good", "n_hyp")
 
 
+def chunk_bounds(n_frames, chunk_frames):
+    """Frame boundaries of the host pipeline's chunks.  The first chunk's H2D copy and the last chunk's
+    D2H copy are the only transfers that cannot hide behind kernels, so the sequence starts (and ends)
+    with small chunks — chunk/8, chunk/4, chunk/2 — and runs at full size in between."""
+    c = max(1, int(chunk_frames))
+    ramp = [s for s in (c // 8, c // 4, c // 2) if s >= 16]
+    bounds = [0]
+    for s in ramp:
+        if bounds[-1] + s + sum(ramp) + c > n_frames:   # keep at least one full chunk and the ramp-down
+            break
+        bounds.append(bounds[-1] + s)
+    tail = []
+    end = n_frames
+    if len(bounds) > 1:
+        for s in ramp:
+            tail.append(end)
+            end -= s
+    pos = bounds[-1]
+    while pos + c < end:
+        pos += c
+        bounds.append(pos)
+    if end > bounds[-1] and end != n_frames:
+        bounds.append(end)
+    bounds += sorted(tail)
+    if bounds[-1] != n_frames:
+        bounds.append(n_frames)
+    return sorted(set(bounds))
+
+
 class FrontEnd:
     """Runs the four batched stages over a DeviceSequence; owns (and reuses) the output buffers.
 
@@ -323,7 +352,7 @@ class FrontEnd:
         l_off, r_off = seq.l_off.astype(np.int64), seq.r_off.astype(np.int64)
         max_nl, max_nr = int(seq.n_l.max()), int(seq.n_r.max())
         max_links = min(max_nl, max_nr)
-        bounds = list(range(0, F, max(1, int(chunk_frames)))) + [F]
+        bounds = chunk_bounds(F, chunk_frames)
         # chunk-relative offset tables for every chunk, one small upload
         parts, index, pos = [], [], 0
         for c in range(len(bounds) - 1):

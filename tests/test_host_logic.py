@@ -122,3 +122,15 @@ def test_merge_top2_host(slamfe):
     merged = dist.merge_top2_host(keys)
     flat = np.sort(keys.transpose(1, 0, 2).reshape(50, 8), axis=1)
     assert np.array_equal(merged, flat[:, :2])
+
+
+def test_chunk_schedule_of_the_host_pipeline(slamfe):
+    from slamfe import frontend
+    for F in (0, 1, 2, 7, 100, 599, 600, 2000, 4541, 20000):
+        for c in (1, 2, 16, 100, 576, 5000):
+            b = frontend.chunk_bounds(F, c)
+            assert b[0] == 0 and b[-1] == F if F else b == [0]
+            sizes = np.diff(b)
+            assert (sizes > 0).all() and sizes.max(initial=0) <= max(c, 1)
+    sizes = np.diff(frontend.chunk_bounds(4541, 576))
+    assert sizes[0] == 72 and sizes[-1] == 72 and (sizes == 576).sum() >= 4   # ramp up, full speed, ramp down

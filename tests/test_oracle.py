@@ -263,3 +263,33 @@ def test_ransac_with_minimal_solver_is_statistically_equivalent_to_epnp(oracle):
         cp, _, mp = oracle.score_hypotheses(np.array(Tp), pts, lp, rp, K, M1, M2)
         assert abs(int(ce.max()) - int(cp.max())) <= 0.05 * ce.max()
         assert (me & mp).sum() / (me | mp).sum() >= 0.9
+
+
+def test_p3p_degenerate_samples_never_yield_invalid_poses(oracle):
+    """Collinear / coincident / behind-camera / non-finite samples: the solver either reports failure or
+    returns a finite proper rotation that reproduces the minimal points — never NaN flagged as valid."""
+    host = oracle.P3PHost()
+    rng = np.random.default_rng(304)
+    K, samples = _pose_samples(rng, 300, noise=0.3)
+    checked = valid = 0
+    for P, pix, _ in samples:
+        cases = []
+        Pc = P.copy(); Pc[2] = Pc[0] + 2.0 * (Pc[1] - Pc[0]); cases.append((Pc, pix))        # collinear 3-D points
+        Pd = P.copy(); Pd[1] = Pd[0]; cases.append((Pd, pix))                                   # coincident points
+        px = pix.copy(); px[1] = px[0]; cases.append((P, px))                                   # coincident pixels
+        Pn = P.copy(); Pn[0, 0] = np.nan; cases.append((Pn, pix))                               # NaN
+        pi_ = pix.copy(); pi_[2, 1] = np.inf; cases.append((P, pi_))                            # inf pixel
+        cases.append((P * 1e-9, pix))                                                           # tiny scene
+        cases.append((P * 1e9, pix))                                                            # huge scene
+        cases.append((P, pix[::-1].copy()))                                                     # mismatched pixels
+        for Pq, pq in cases:
+            with np.errstate(all="ignore"):
+                T, ok = host.solve(Pq, pq, K)
+            checked += 1
+            if not ok:
+                continue
+            valid += 1
+            assert np.isfinite(T).all()
+            R = T[:, :3]
+            assert np.abs(R @ R.T - np.eye(3)).max() < 1e-6 and np.linalg.det(R) > 0
+    assert checked == 300 * 8 and valid > 0

@@ -163,6 +163,38 @@ def triangulate_links_host_build(links, P, Q):
     return out
 
 
+_HAM_LIB_PATH = os.path.join(_HERE, "libhamming_host.so")
+_ham_lib = None
+
+
+def build_hamming_shim(force: bool = False) -> str:
+    """Compile oracle/hamming_host_shim.cpp (csrc/hamming_core.cuh for the HOST)."""
+    src = os.path.join(_HERE, "hamming_host_shim.cpp")
+    root = os.path.dirname(_HERE)
+    csrc = os.path.join(root, "67604-slam---video-navigation_b200", "csrc")
+    newest = max(os.path.getmtime(src), os.path.getmtime(os.path.join(csrc, "hamming_core.cuh")))
+    if force or not os.path.exists(_HAM_LIB_PATH) or os.path.getmtime(_HAM_LIB_PATH) < newest:
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-I", os.path.join(root, "include"), src,
+                               "-o", _HAM_LIB_PATH])
+    return _HAM_LIB_PATH
+
+
+def hamming_keys_host_build(q, t, desc_bytes=None, cs=9):
+    """Row-wise distances of q[i], t[i] through the HOST build of the matcher's carry-save arithmetic.
+    Returns the keys (distance << 22) exactly as the kernel forms them."""
+    global _ham_lib
+    if _ham_lib is None:
+        build_hamming_shim()
+        _ham_lib = ctypes.CDLL(_HAM_LIB_PATH)
+    q, qp = _u8(q)
+    t, tp = _u8(t)
+    desc_bytes = q.shape[1] if desc_bytes is None else desc_bytes
+    keys = np.zeros(q.shape[0], dtype=np.uint32)
+    _ham_lib.hamming_host_keys(qp, tp, ctypes.c_long(q.shape[0]), int(q.shape[1]), int(desc_bytes), int(cs),
+                               keys.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
+    return keys
+
+
 def _load():
     global _lib
     if _lib is None:

@@ -135,3 +135,38 @@ def test_triangulation_core_vs_svd_on_extreme_links(oracle):
         ref = oracle.triangulate_links(lk, P, Q)
         rel = np.linalg.norm(got - ref, axis=1) / np.linalg.norm(ref, axis=1)
         assert rel.max() < 1e-10, rel.max()
+
+
+@pytest.mark.parametrize("cs", [7, 8, 9, 10])
+def test_carry_save_distance_equals_popcount(oracle, cs):
+    """csrc/hamming_core.cuh (host build): prefix form + full-adder chain + weighted popcount
+    accumulation == popcount(q XOR t), for every single-bit and adjacent/arbitrary double-bit pattern of
+    a 64-byte row, the extremes, random rows and every descriptor width 1..64 (zero padded)."""
+    rng = np.random.default_rng(500 + cs)
+    bits = np.arange(512)
+    single = np.zeros((512, 64), np.uint8)
+    single[bits, bits // 8] = 1 << (bits % 8)
+    zero = np.zeros_like(single)
+    assert np.array_equal(oracle.hamming_keys_host_build(single, zero, cs=cs) >> 22, np.ones(512))
+    assert np.array_equal(oracle.hamming_keys_host_build(zero, single, cs=cs) >> 22, np.ones(512))
+    i, j = np.triu_indices(512, k=1)                       # all 130 816 two-bit patterns
+    double = np.zeros((len(i), 64), np.uint8)
+    np.bitwise_or.at(double, (np.arange(len(i)), i // 8), (1 << (i % 8)).astype(np.uint8))
+    np.bitwise_or.at(double, (np.arange(len(j)), j // 8), (1 << (j % 8)).astype(np.uint8))
+    base = rng.integers(0, 256, (len(i), 64), dtype=np.uint8)
+    assert np.array_equal(oracle.hamming_keys_host_build(base, base ^ double, cs=cs) >> 22, np.full(len(i), 2))
+    ones = np.full((3, 64), 255, np.uint8)
+    assert (oracle.hamming_keys_host_build(ones, np.zeros((3, 64), np.uint8), cs=cs) >> 22).tolist() == [512] * 3
+    assert (oracle.hamming_keys_host_build(ones, ones, cs=cs)).tolist() == [0] * 3
+    popc = np.array([bin(v).count("1") for v in range(256)], np.int64)
+    for width in list(range(1, 65)):
+        q = rng.integers(0, 256, (400, 64), dtype=np.uint8)
+        t = rng.integers(0, 256, (400, 64), dtype=np.uint8)
+        k = oracle.hamming_keys_host_build(q, t, desc_bytes=width, cs=cs)
+        assert (k & 0x3FFFFF == 0).all()
+        assert np.array_equal(k >> 22, popc[q[:, :width] ^ t[:, :width]].sum(axis=1))
+    # correlated rows (true matches: few differing bits) and heavy rows
+    q = rng.integers(0, 256, (20000, 64), dtype=np.uint8)
+    flips = (rng.random((20000, 64, 8)) < rng.uniform(0, 1, (20000, 1, 1))).astype(np.uint8)
+    t = q ^ np.packbits(flips, axis=2, bitorder="little")[:, :, 0]
+    assert np.array_equal(oracle.hamming_keys_host_build(q, t, cs=cs) >> 22, popc[q ^ t].sum(axis=1))

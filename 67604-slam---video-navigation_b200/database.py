@@ -102,3 +102,44 @@ def create_db(frames, db, link_factory=None, chunk_frames=576, h_max=256, seed=1
         matches[:] = list(map(cv2.DMatch, range(n), fr["fwd_idx"].tolist(), [0] * n, fr["fwd_dist"].tolist()))
         db.add_frame(links, fr["features"], matches, fr["inliers"])
     return db
+
+
+def make_reference_create_db(reference_database_module, inputs_module=None, matching_module=None, **pipeline_kw):
+    """A function with the signature of the reference's `create_db(start_frame=0, num_frames=200, db=None)`
+    (database.py:30) that reads and describes the frames exactly as `first_operation` does
+    (`Inputs.read_images`, `FEATURE.detectAndCompute`, database.py:17-18 / matching.py:42-43 — CPU work that
+    stays with OpenCV) and then runs everything else of the loop as ONE batched GPU pipeline
+    (`create_db` above).  `patch.patch(batched_db=True)` binds it to `database.create_db`, so
+    `database.run(path)` / `project.run_project` build the TrackingDB through it.
+
+    A resumed build (start_frame != 0, database.py:46-47) needs the previous frame from `db` and is handed
+    to the reference's own loop (which, once patched, still uses the GPU matchers frame by frame)."""
+    ref_create_db = reference_database_module.create_db
+    inputs = inputs_module or reference_database_module.Inputs
+    if matching_module is None:
+        import sys
+        matching_module = sys.modules.get("final_project.algorithms.matching")
+    tracking_db_cls = reference_database_module.TrackingDB
+    link_cls = None
+    try:
+        import sys
+        link_cls = sys.modules[tracking_db_cls.__module__].Link
+    except Exception:
+        link_cls = None
+
+    def create_db_batched(start_frame=0, num_frames=200, db=None):
+        if start_frame != 0:
+            return ref_create_db(start_frame=start_frame, num_frames=num_frames, db=db)
+        if db is None:
+            db = tracking_db_cls()
+        feature = matching_module.FEATURE
+        frames = []
+        for idx in range(num_frames):
+            img_l, img_r = inputs.read_images(idx)
+            kp_l, desc_l = feature.detectAndCompute(img_l, None)
+            kp_r, desc_r = feature.detectAndCompute(img_r, None)
+            frames.append((kp_l, kp_r, desc_l, desc_r))
+        return create_db(frames, db, link_factory=link_cls, **pipeline_kw)
+
+    create_db_batched.__wrapped__ = ref_create_db
+    return create_db_batched

@@ -47,10 +47,15 @@ def replacements():
     }
 
 
-def patch(modules=None):
+def patch(modules=None, batched_db=False, **pipeline_kw):
     """Rebind every already-imported reference module (or the given {name: module} mapping).
     Also copies the reference's cameras into slamfe.ransac so both sides score with the same
-    K, M1, M2.  Returns {module_name: [rebound attribute names]}; `unpatch(token)` restores."""
+    K, M1, M2.  Returns {module_name: [rebound attribute names]}; `unpatch(token)` restores.
+
+    batched_db=True additionally replaces `database.create_db` (database.py:30, called by
+    `database.run`, :92-98) with the batched whole-sequence builder of slamfe.database: frames are
+    still read and described on the CPU exactly as the reference does, everything else of the loop
+    runs as one GPU pipeline (hypotheses from the GPU generator)."""
     from . import ransac
     rep = replacements()
     mods = modules if modules is not None else sys.modules
@@ -67,6 +72,14 @@ def patch(modules=None):
                 saved.append((mod, a, getattr(mod, a)))
                 setattr(mod, a, rep[a])
                 done.setdefault(mod_name, []).append(a)
+    if batched_db:
+        dbm = mods.get("final_project.backend.database.database")
+        if dbm is not None and hasattr(dbm, "create_db"):
+            from . import database as sdb
+            saved.append((dbm, "create_db", dbm.create_db))
+            dbm.create_db = sdb.make_reference_create_db(dbm, matching_module=mods.get(
+                "final_project.algorithms.matching"), **pipeline_kw)
+            done.setdefault("final_project.backend.database.database", []).append("create_db")
     done["_saved"] = saved
     return done
 

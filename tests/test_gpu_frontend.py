@@ -286,3 +286,49 @@ def test_create_db_against_the_reference_golden(slamfe, golden):
         if b.sum() >= 20:  # ... and its consensus set contains the reference's
             jac.append((a & b).sum() / b.sum())
     assert len(jac) >= 3 and min(jac) >= 0.75, jac
+
+
+def test_batched_create_db_through_patch(slamfe, golden):
+    """patch(batched_db=True) on a reference-shaped module tree (the real tree is not on the GPU box; the
+    wiring against the real one is tested on the CPU by tests/test_reference_db.py): `database.create_db`
+    reads / describes the frames through the tree's Inputs + FEATURE and builds the DB with the GPU
+    pipeline — same add_frame arguments as the reference's own run frozen in tests/golden/create_db.npz."""
+    import types
+    import cv2
+    from slamfe import patch
+    g = golden("create_db")
+    n = int(g["n_frames"])
+
+    class Provider:
+        def detectAndCompute(self, token, mask):
+            side, f = token
+            pts = g[f"pts_{'l' if side == 'L' else 'r'}{f}"]
+            return tuple(cv2.KeyPoint(float(x), float(y), 1.0) for x, y in pts), g[f"desc_{'l' if side == 'L' else 'r'}{f}"]
+
+    class TrackingDB:
+        def __init__(self):
+            self.calls, self.frameID_to_inliers_percent = [], {}
+
+        def add_frame(self, links, left_features, matches_to_previous_left=None, inliers=None):
+            self.calls.append((links, left_features, matches_to_previous_left, inliers))
+
+    matching = types.ModuleType("final_project.algorithms.matching")
+    matching.FEATURE = Provider()
+    database = types.ModuleType("final_project.backend.database.database")
+    database.Inputs = types.SimpleNamespace(read_images=lambda idx: (("L", idx), ("R", idx)))
+    database.TrackingDB = TrackingDB
+    database.create_db = lambda start_frame=0, num_frames=200, db=None: "reference loop"
+    mods = {matching.__name__: matching, database.__name__: database}
+    tok = patch.patch(mods, batched_db=True, h_max=64, chunk_frames=2)
+    try:
+        db = database.create_db(num_frames=n)
+        assert database.create_db(start_frame=2, num_frames=n, db=db) == "reference loop"   # resumed build
+    finally:
+        patch.unpatch(tok)
+    assert len(db.calls) == n
+    for f, (links, feats, ms, inl) in enumerate(db.calls):
+        assert np.array_equal(np.array([(l.x_left, l.x_right, l.y) for l in links], np.float64).reshape(-1, 3),
+                              g[f"links{f}"])
+        assert np.array_equal(feats, g[f"features{f}"])
+        if f:
+            assert np.array_equal([m.trainIdx for m in ms], g[f"match_t{f}"]) and len(inl) == len(ms)

@@ -127,3 +127,52 @@ def test_adapter_drives_the_reference_tracking_db_identically(oracle):
         other = db_new.linkId_to_link[k]
         assert (ln.x_left, ln.x_right, ln.y) == (other.x_left, other.x_right, other.y)
     db_new._check_consistency() if hasattr(db_new, "_check_consistency") else None
+
+
+def test_patch_batched_db_rebinds_create_db_on_the_real_reference(monkeypatch):
+    """patch(batched_db=True) on the real reference module tree: `database.create_db` becomes the batched
+    builder, which reads and describes the frames through the reference's own `Inputs.read_images` /
+    `FEATURE.detectAndCompute` in order and hands them to slamfe.database.create_db (stubbed here: the
+    CUDA pipeline cannot run in this container); a resumed build goes to the reference's loop; unpatch
+    restores everything."""
+    import sys
+    import cv2
+    ref = refshim.load()
+    from slamfe import database as sdb, patch
+    frames = _synthetic_frames(3)
+
+    class Provider:
+        def detectAndCompute(self, token, mask):
+            side, f = token
+            pts = frames[f][0 if side == "L" else 1]
+            return tuple(cv2.KeyPoint(float(x), float(y), 1.0) for x, y in pts), frames[f][2 if side == "L" else 3]
+
+    seen = {}
+
+    def fake_create_db(frs, db, link_factory=None, **kw):
+        seen["frames"], seen["db"], seen["link"], seen["kw"] = frs, db, link_factory, kw
+        return db
+
+    monkeypatch.setattr(sdb, "create_db", fake_create_db)
+    monkeypatch.setattr(patch, "replacements", lambda: {})      # the GPU objects cannot be built here
+    monkeypatch.setattr(ref.matching, "FEATURE", Provider())
+    monkeypatch.setattr(ref.inputs, "read_images", lambda idx: (("L", idx), ("R", idx)))
+    original = ref.database.create_db
+    mods = {k: v for k, v in sys.modules.items() if k.startswith("final_project")}
+    # only the batched_db part of patch() is exercised: the per-attribute rebinding needs the GPU objects
+    monkeypatch.setattr(patch, "_REBINDS", {})
+    tok = patch.patch(mods, batched_db=True, h_max=64)
+    try:
+        assert ref.database.create_db is not original and ref.database.create_db.__wrapped__ is original
+        db = ref.database.create_db(start_frame=0, num_frames=3, db=None)
+        assert isinstance(db, ref.tracking_database.TrackingDB) and seen["db"] is db
+        assert seen["link"] is ref.tracking_database.Link and seen["kw"] == {"h_max": 64}
+        assert len(seen["frames"]) == 3
+        for f, (kl, kr, dl, dr) in enumerate(seen["frames"]):
+            assert np.array_equal(dl, frames[f][2]) and np.array_equal(dr, frames[f][3])
+            assert np.allclose([k.pt for k in kl], frames[f][0]) and np.allclose([k.pt for k in kr], frames[f][1])
+        seq = sdb.pack_frames(seen["frames"], pin=False)     # what the batched builder packs for the GPU
+        assert seq.n_frames == 3 and np.array_equal(seq.pts_l[:len(frames[0][0])], frames[0][0])
+    finally:
+        patch.unpatch(tok)
+    assert ref.database.create_db is original

@@ -129,3 +129,97 @@ class CandidateVerifier:
         if want_masks:
             res["keys"], res["mask"] = keys_out, mask_out
         return res
+
+
+# ------------------------------------------------------------------------------------------------
+# Drop-ins for the two callers in backend/loop/loop_closure.py (same names, signatures, returns)
+# ------------------------------------------------------------------------------------------------
+_default_verifier = None
+
+
+def _verifier():
+    global _default_verifier
+    if _default_verifier is None:
+        from . import ransac
+        _default_verifier = CandidateVerifier(K=ransac.K, M1=ransac.M1, M2=ransac.M2, block_pairs=64)
+    return _default_verifier
+
+
+def _keyframe_pool(db, frames):
+    """Features and links of the given keyframes of a TrackingDB as one padded pool (host arrays)."""
+    from .triangulation import links_to_array
+    feats = [np.ascontiguousarray(db.features(f), dtype=np.uint8) for f in frames]
+    links = [links_to_array(db.all_frame_links(f)) for f in frames]
+    cnt = np.array([len(x) for x in feats], dtype=np.int64)
+    off = np.zeros(len(frames) + 1, dtype=np.int64)
+    np.cumsum((cnt + 15) // 16 * 16, out=off[1:])
+    width = feats[0].shape[1] if len(feats) and feats[0].ndim == 2 else 61
+    pool_d = np.zeros((max(int(off[-1]), 1), width), dtype=np.uint8)
+    pool_l = np.tile(np.array([[30.0, 10.0, 50.0]]), (max(int(off[-1]), 1), 1))
+    for k in range(len(frames)):
+        pool_d[off[k]:off[k] + cnt[k]] = feats[k]
+        pool_l[off[k]:off[k] + cnt[k]] = links[k]
+    return pool_d, pool_l, off[:-1], cnt, links
+
+
+def _verify_from_db(reference_key_frame, candidates, db, seed=None):
+    torch = _cabi.require_cuda()
+    frames = [reference_key_frame] + list(candidates)
+    pool_d, pool_l, off, cnt, links = _keyframe_pool(db, frames)
+    pairs = np.array([(0, k + 1) for k in range(len(candidates))], dtype=np.int64)
+    ver = _verifier()
+    if seed is None:
+        seed = int(np.random.randint(0, 2 ** 31 - 1))   # follows np.random.seed like the reference's sampling
+    res = ver.verify(torch.from_numpy(pool_d).cuda(), torch.from_numpy(pool_l).cuda(), off, cnt, pairs,
+                     inliers_percent=LOOP_INLIERS_PERCENT, seed=seed, want_masks=True)
+    return res, links
+
+
+def _candidate_result(res, k, links_ref, ver):
+    """(inlier DMatch list, percentage, camera_to_world pose or None) of candidate k, as
+    check_candidate_match returns them (loop_closure.py:425-436 + ransac.py:185-204)."""
+    import cv2
+    from . import ransac
+    from .triangulation import triangulate_link_array
+    keys, mask = res["keys"][k], res["mask"][k]
+    idx = np.nonzero(mask)[0]
+    if len(idx) < 4:  # ransac.py:187-188: (None, [], []) -> percentage_inliers = 0 via the except branch
+        return [], 0, None
+    ti = (keys & _cabi.KEY_IDX_MASK).astype(np.int64)
+    td = (keys >> _cabi.KEY_IDX_BITS).astype(np.float64)
+    pts = triangulate_link_array(links_ref[idx], ver.P, ver.Q)
+    cur = res["_links"][k + 1][ti[idx]]
+    ok, rvec, tvec = cv2.solvePnP(pts, np.ascontiguousarray(cur[:, [0, 2]]), ver.K, distCoeffs=np.zeros((5, 1)),
+                                  flags=cv2.SOLVEPNP_EPNP)
+    if not ok:  # ransac.py:204 -> (None, None, None): the reference then fails on `for i in None`
+        raise TypeError("'NoneType' object is not iterable")
+    pose = ransac._pose3(ransac.rodriguez_to_mat(rvec, tvec)).inverse()
+    matches = list(map(cv2.DMatch, idx.tolist(), ti[idx].tolist(), [0] * len(idx), td[idx].tolist()))
+    return matches, len(idx) / len(keys), pose
+
+
+def check_candidate_match(reference_key_frame, candiate_keyframe, db):
+    """loop_closure.py:405-436 -> ([inlier DMatch], percentage_inliers, camera_to_world Pose3 or None)."""
+    res, links = _verify_from_db(reference_key_frame, [candiate_keyframe], db)
+    res["_links"] = links
+    return _candidate_result(res, 0, links[0], _verifier())
+
+
+def consensus_matches(reference_key_frame, candidates_index_lst, data_base):
+    """loop_closure.py:572-599: the first candidate (in list order) with more than INLIERS_THRESHOLD inlier
+    matches wins.  All candidates are verified in ONE batch (match + 888-hypothesis RANSAC each); the
+    return value — (best_candidate or None, best_matches, rel_T of the winner, else of the last candidate
+    evaluated) — is what the reference's sequential loop produces."""
+    candidates = list(candidates_index_lst)
+    if not candidates:
+        return None, [], None
+    res, links = _verify_from_db(reference_key_frame, candidates, data_base)
+    res["_links"] = links
+    ver = _verifier()
+    rel_T = None
+    for k, cand in enumerate(candidates):
+        if res["inliers"][k] > INLIERS_THRESHOLD:
+            matches, _, rel_T = _candidate_result(res, k, links[0], ver)
+            return cand, matches, rel_T
+    _, _, rel_T = _candidate_result(res, len(candidates) - 1, links[0], ver)
+    return None, [], rel_T

@@ -47,7 +47,7 @@ def replacements():
     }
 
 
-def patch(modules=None, batched_db=False, **pipeline_kw):
+def patch(modules=None, batched_db=False, batched_loop=False, **pipeline_kw):
     """Rebind every already-imported reference module (or the given {name: module} mapping).
     Also copies the reference's cameras into slamfe.ransac so both sides score with the same
     K, M1, M2.  Returns {module_name: [rebound attribute names]}; `unpatch(token)` restores.
@@ -55,7 +55,11 @@ def patch(modules=None, batched_db=False, **pipeline_kw):
     batched_db=True additionally replaces `database.create_db` (database.py:30, called by
     `database.run`, :92-98) with the batched whole-sequence builder of slamfe.database: frames are
     still read and described on the CPU exactly as the reference does, everything else of the loop
-    runs as one GPU pipeline (hypotheses from the GPU generator)."""
+    runs as one GPU pipeline (hypotheses from the GPU generator).
+
+    batched_loop=True replaces `loop_closure.check_candidate_match` / `consensus_matches`
+    (loop_closure.py:405-436, :572-599) with slamfe.loop's: all candidates of a keyframe are verified
+    in one device-resident batch (match + 888-hypothesis RANSAC-PnP each)."""
     from . import ransac
     rep = replacements()
     mods = modules if modules is not None else sys.modules
@@ -72,6 +76,14 @@ def patch(modules=None, batched_db=False, **pipeline_kw):
                 saved.append((mod, a, getattr(mod, a)))
                 setattr(mod, a, rep[a])
                 done.setdefault(mod_name, []).append(a)
+    lcm = mods.get("final_project.backend.loop.loop_closure")
+    if batched_loop and lcm is not None:
+        from . import loop as sloop
+        for a, fn in (("check_candidate_match", sloop.check_candidate_match), ("consensus_matches", sloop.consensus_matches)):
+            if hasattr(lcm, a):
+                saved.append((lcm, a, getattr(lcm, a)))
+                setattr(lcm, a, fn)
+                done.setdefault("final_project.backend.loop.loop_closure", []).append(a)
     if batched_db:
         dbm = mods.get("final_project.backend.database.database")
         if dbm is not None and hasattr(dbm, "create_db"):

@@ -135,3 +135,52 @@ def test_candidates_against_the_reference_golden(slamfe, golden):
     unrelated = [k for k, (a, b) in enumerate(pairs) if abs(int(a) - int(b)) > 1]
     assert all(res["inliers"][k] < 15 and len(g[f"inlier_q{k}"]) < 15 for k in unrelated)
     assert not res["accepted"].any()       # tiny keyframes: nobody reaches the 120-inlier threshold
+
+
+class _L:
+    def __init__(self, a, b, c):
+        self.x_left, self.x_right, self.y = a, b, c
+
+
+class _GoldenDB:
+    """TrackingDB-shaped view of tests/golden/create_db.npz: features(f) / all_frame_links(f)."""
+
+    def __init__(self, g):
+        self.g = g
+
+    def features(self, f):
+        return self.g[f"features{f}"]
+
+    def all_frame_links(self, f):
+        return [_L(*r) for r in self.g[f"links{f}"]]
+
+
+def test_loop_closure_dropins_against_the_reference_golden(slamfe, golden, monkeypatch):
+    """slamfe.loop.check_candidate_match / consensus_matches (same signatures and returns as
+    loop_closure.py:405-436, :572-599) on the reference's own TrackingDB content, against the reference's
+    recorded check_candidate_match results."""
+    from slamfe import loop
+    db, g = _GoldenDB(golden("create_db")), golden("loop_candidates")
+    np.random.seed(8)
+    for k, (a, b) in enumerate(g["pairs"]):
+        ref_q = set(g[f"inlier_q{k}"].tolist())
+        matches, pct, pose = loop.check_candidate_match(int(a), int(b), db)
+        got_q = {m.queryIdx for m in matches}
+        assert all(m.imgIdx == 0 and g[f"match_t{k}"][m.queryIdx] == m.trainIdx and
+                   g[f"match_d{k}"][m.queryIdx] == m.distance for m in matches)
+        assert len(got_q) >= 0.8 * len(ref_q)
+        if len(ref_q) >= 20:
+            assert len(got_q & ref_q) / len(ref_q) >= 0.75 and abs(pct - float(g[f"percentage{k}"])) < 0.1
+            P_ref, P_got = g[f"pose{k}"], pose.matrix()
+            assert np.abs(P_got[:3, 3] - P_ref[:3, 3]).max() < 0.15 and np.abs(P_got[:3, :3] - P_ref[:3, :3]).max() < 0.02
+        if abs(int(a) - int(b)) > 1:
+            assert len(matches) < 15
+    # consensus_matches: first candidate in list order above the threshold wins; none -> (None, [], last rel_T)
+    cand, ms, rel = loop.consensus_matches(4, [1, 3], db)
+    assert cand is None and ms == []
+    monkeypatch.setattr(loop, "INLIERS_THRESHOLD", 30)
+    cand, ms, rel = loop.consensus_matches(4, [1, 3], db)
+    assert cand == 3 and len(ms) > 30 and rel is not None
+    cand2, ms2, _ = loop.consensus_matches(4, [3, 1], db)
+    assert cand2 == 3 and abs(len(ms2) - len(ms)) <= 0.2 * len(ms)
+    assert loop.consensus_matches(4, [], db) == (None, [], None)

@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_int, c_int32, c_int64, c_uint64, c_void_p, POINTER
+from ctypes import c_char_p, c_int, c_int64, c_uint64, c_void_p, POINTER
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 # SLAMFE_LIBRARY overrides the in-tree build (development: A/B timing of two builds on one box)

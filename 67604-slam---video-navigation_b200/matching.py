@@ -66,6 +66,29 @@ class _Staging:
         return pin[:nbytes].numpy().view(npdtype).reshape(tuple(t.shape)).copy()
 
 
+class _ThreadLocalStaging:
+    """One _Staging per Python thread: the module-level entry points (extract_inliers_outliers,
+    triangulate_links, transformation_agreement, ...) may be called from several threads, each on its
+    own CUDA stream, and must not share pinned buffers."""
+
+    def __init__(self):
+        import threading
+        self._tls = threading.local()
+
+    def _get(self):
+        st = getattr(self._tls, "st", None)
+        if st is None:
+            st = self._tls.st = _Staging()
+        return st
+
+    def to_device(self, key, arr):
+        return self._get().to_device(key, arr)
+
+    def to_host(self, key, t):
+        return self._get().to_host(key, t)
+
+
+
 def _cv2_error(msg):
     if cv2 is not None:
         return cv2.error(msg)
@@ -106,7 +129,7 @@ class Matcher:
             raise ValueError("slamfe.Matcher implements NORM_HAMMING only (SIFT/L2 is out of scope)")
         self.normType = normType
         self.crossCheck = bool(crossCheck)
-        self._st = _Staging()
+        self._st = _ThreadLocalStaging()  # the module-global MATCHER objects may be shared by threads
 
     # -- array-level API (no per-match Python objects) ------------------------------------
     def match_arrays(self, queryDescriptors, trainDescriptors):
@@ -182,28 +205,6 @@ def get_akaze_matcher_lr_matcher():
     matcher = Matcher(normType=NORM_HAMMING, crossCheck=False)
     matcher_left_right = Matcher(normType=NORM_HAMMING, crossCheck=True)
     return feature, matcher_left_right, matcher
-
-
-class _ThreadLocalStaging:
-    """One _Staging per Python thread: the module-level entry points (extract_inliers_outliers,
-    triangulate_links, transformation_agreement, ...) may be called from several threads, each on its
-    own CUDA stream, and must not share pinned buffers."""
-
-    def __init__(self):
-        import threading
-        self._tls = threading.local()
-
-    def _get(self):
-        st = getattr(self._tls, "st", None)
-        if st is None:
-            st = self._tls.st = _Staging()
-        return st
-
-    def to_device(self, key, arr):
-        return self._get().to_device(key, arr)
-
-    def to_host(self, key, t):
-        return self._get().to_host(key, t)
 
 
 _filter_staging = _ThreadLocalStaging()

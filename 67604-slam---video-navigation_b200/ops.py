@@ -312,9 +312,10 @@ def measure_peak(mode: int, iters: int = 4096, ctas_per_sm: int = 8, block: int 
     """Run a pipe-peak micro-benchmark; returns ops/s (popc/s for modes 0-1, fp64 FMA/s for mode 2)."""
     import ctypes
     torch = _torch()
-    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    dev = torch.cuda.current_device()
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
     grid = sms * ctas_per_sm
-    sink = torch.empty((grid * block,), dtype=torch.int32, device="cuda")
+    sink = torch.empty((grid * block,), dtype=torch.int32, device=torch.device("cuda", dev))
     ops = ctypes.c_int(0)
     lib = load_library()
     best = 0.0

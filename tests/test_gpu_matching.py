@@ -272,3 +272,36 @@ def test_knn_inner_tuple_lengths(slamfe):
     k2 = m.knnMatch(q, t3, k=2)
     assert all(len(p) == 1 for p in k1) and all(len(p) == 2 for p in k2)
     assert [p[0].trainIdx for p in k1] == [p[0].trainIdx for p in k2] == [x.trainIdx for x in m.match(q, t3)]
+
+
+def test_shared_matcher_from_several_threads(slamfe, oracle):
+    """The module-global MATCHER objects of the reference are shared; here each Python thread gets its
+    own pinned staging buffers and runs on its own CUDA stream (the C-ABI keeps no global state)."""
+    import threading
+    import torch
+    from slamfe import matching, synth
+    rng = np.random.default_rng(45)
+    m = matching.Matcher(crossCheck=True)
+    jobs = []
+    for _ in range(6):
+        dl, dr, _, _ = synth.stereo_frame(rng, int(rng.integers(300, 900)))
+        jobs.append((dl, dr, oracle.match_crosscheck(dl, dr)))
+    errors = []
+
+    def work(k):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for _ in range(5):
+                    dl, dr, (cq, ct, cd) = jobs[k]
+                    qi, ti, d = m.match_arrays(dl, dr)
+                    assert np.array_equal(qi, cq) and np.array_equal(ti, ct) and np.array_equal(d, cd)
+        except Exception as exc:  # pragma: no cover - reported below
+            errors.append((k, repr(exc)))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors

@@ -134,3 +134,40 @@ def test_chunk_schedule_of_the_host_pipeline(slamfe):
             assert (sizes > 0).all() and sizes.max(initial=0) <= max(c, 1)
     sizes = np.diff(frontend.chunk_bounds(4541, 576))
     assert sizes[0] == 72 and sizes[-1] == 72 and (sizes == 576).sum() >= 4   # ramp up, full speed, ramp down
+
+
+def test_sharding_properties(slamfe):
+    """Property tests of the host-side sharding arithmetic (slamfe.dist)."""
+    from hypothesis import given, settings, strategies as st
+    from slamfe import dist
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.integers(0, 10_000), min_size=0, max_size=60), st.integers(1, 9))
+    def ranges(work, world):
+        b = dist.balanced_ranges(work, world)
+        assert len(b) == world + 1 and b[0] == 0 and b[-1] == len(work)
+        assert all(x <= y for x, y in zip(b, b[1:]))
+        if sum(work) > 0 and len(work) >= world:
+            shares = [sum(work[b[r]:b[r + 1]]) for r in range(world)]
+            assert max(shares) <= sum(work) / world + max(work)      # never worse than one unit off
+
+    @settings(max_examples=100, deadline=None)
+    @given(st.integers(0, 100_000), st.integers(1, 9))
+    def slices(n, world):
+        b = dist.train_slices(n, world)
+        assert b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:]))
+        assert all(int(x) % 16 == 0 for x in b[:-1] if x < n)      # every non-empty slice starts 16-row aligned
+
+    @settings(max_examples=100, deadline=None)
+    @given(st.integers(1, 6), st.integers(1, 40), st.integers(0, 2 ** 32 - 1))
+    def merge(shards, nq, seed):
+        rng = np.random.default_rng(seed)
+        keys = rng.integers(0, 2 ** 32, (shards, nq, 2), dtype=np.uint64).astype(np.uint32)
+        keys.sort(axis=2)
+        got = dist.merge_top2_host(keys)
+        want = np.sort(keys.transpose(1, 0, 2).reshape(nq, -1), axis=1)[:, :2]
+        assert np.array_equal(got, want)
+
+    ranges(); slices(); merge()
+    pairs = dist.candidate_pairs(7)
+    assert len(pairs) == 21 and (pairs[:, 0] > pairs[:, 1]).all() and pairs[0].tolist() == [1, 0]

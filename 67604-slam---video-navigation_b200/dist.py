@@ -41,6 +41,27 @@ def init_from_env(backend=None):
     return rank, world, local_rank
 
 
+def bind_to_gpu_numa(gpu_index):
+    """Restrict this process to the CPUs NVML reports as local to its GPU (best effort, Linux only), so
+    that pinned staging buffers are first-touched on the GPU's NUMA node.  Returns the previous affinity
+    set (pass it to os.sched_setaffinity(0, ...) to undo) or None when nothing was changed.  Opt-in:
+    bench.py calls it when SLAMFE_BIND_NUMA=1 (to be measured at 8 GPUs)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1}
+        old = os.sched_getaffinity(0)
+        new = cpus & old
+        if not new or new == old:
+            return None
+        os.sched_setaffinity(0, new)
+        return old
+    except Exception:
+        return None
+
+
 def balanced_ranges(work, world):
     """Cut len(work) consecutive units into `world` contiguous ranges of near-equal total work.
     Returns an int64 array of world+1 boundaries."""

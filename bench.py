@@ -243,6 +243,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
     dev = torch.device("cuda", local_rank)
     slamfe.load_library()
+    old_affinity = sdist.bind_to_gpu_numa(local_rank) if os.environ.get("SLAMFE_BIND_NUMA") == "1" else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -415,6 +416,8 @@ def main():
         }
 
         # ---- CPU baseline on a bounded sample + parity of the GPU tables on those frames ----
+        if old_affinity is not None:  # the CPU baseline uses every host thread
+            os.sched_setaffinity(0, old_affinity)
         if not args.no_cpu_baseline:
             n = max(2, min(args.cpu_sample_frames, F))
             frames = host_frames(seq_t, 0, n)

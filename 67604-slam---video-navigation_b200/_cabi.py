@@ -18,6 +18,7 @@ KEY_NONE = 0xFFFFFFFF
 MAX_DESC_BYTES = 64
 MATCH_BEST_ONLY = 1
 MATCH_COMPACT_KEYS = 2
+MATCH_MMA = 4
 
 # name -> (restype, argtypes); mirrors include/slamfe.h one to one
 _SIGNATURES = {
@@ -48,7 +49,7 @@ _SIGNATURES = {
     "slamfe_ransac_score": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "slamfe_track_gather": (c_int, [c_void_p] * 10 + [c_int, c_void_p, c_void_p, c_int] + [c_void_p] * 8),
+    "slamfe_track_gather": (c_int, [c_void_p] * 10 + [c_int, c_void_p, c_void_p, c_int] + [c_void_p] * 9),
     "slamfe_pairs_gather": (c_int, [c_void_p] * 5 + [c_int, c_int] + [c_void_p] * 6),
     "slamfe_scatter_inliers": (c_int, [c_void_p] * 5 + [c_int, c_void_p, c_int64, c_void_p]),
     "slamfe_ransac_hypotheses": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,

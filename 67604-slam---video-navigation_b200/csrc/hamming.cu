@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "hamming_core.cuh"
+#include "hamming_params.cuh"
 
 namespace slamfe {
 
@@ -31,71 +32,6 @@ namespace {
 
 constexpr int TS = 128;  // train rows per shared-memory stage
 constexpr int RAW_BYTES = TS * SLAMFE_MAX_DESC_BYTES + 16;
-
-struct HammingParams {
-    const uint8_t *q;
-    const uint8_t *t;
-    int q_stride, t_stride, desc_bytes;
-    const int32_t *q_off, *q_cnt, *t_off, *t_cnt;  // null q_off / t_off => single problem
-    const int32_t *row_out_off;                    // null => row results are indexed like q rows
-    int nq, nt;                                    // single-problem sizes
-    int t_index_base;
-    int t_slice;      // train rows per blockIdx.y slice (multiple of TS)
-    int tma_quantum;  // rows per 16-byte-multiple chunk of the train layout
-    uint2 *row_keys;
-    uint32_t *col_keys;
-    int compact;      // best-only results as one u32 per query row instead of (best, second)
-};
-
-// Load one descriptor (desc_bytes useful bytes) from global memory into 16 zero-padded words.
-__device__ __forceinline__ void load_desc_global(const uint8_t *src, int desc_bytes, uint32_t (&w)[W])
-{
-    if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
-        const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src);
-#pragma unroll
-        for (int k = 0; k < W; ++k) {
-            const int rem = desc_bytes - 4 * k;
-            uint32_t v = 0;
-            if (rem >= 4) {
-                v = __ldg(s32 + k);
-            } else if (rem > 0) {
-                for (int b = 0; b < rem; ++b) v |= static_cast<uint32_t>(__ldg(src + 4 * k + b)) << (8 * b);
-            }
-            w[k] = v;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < W; ++k) {
-            uint32_t v = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-                if (4 * k + b < desc_bytes) v |= static_cast<uint32_t>(__ldg(src + 4 * k + b)) << (8 * b);
-            w[k] = v;
-        }
-    }
-}
-
-__device__ __forceinline__ uint32_t word_mask(int desc_bytes, int k)
-{
-    const int rem = desc_bytes - 4 * k;
-    return rem >= 4 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << (8 * rem)) - 1u));
-}
-
-// Merge a CTA-local sorted pair (k1 <= k2) into the global (key1, key2) of one query row.
-__device__ __forceinline__ void merge_row_keys(uint2 *g, uint32_t k1, uint32_t k2)
-{
-    unsigned long long *a = reinterpret_cast<unsigned long long *>(g);
-    unsigned long long old = *a, assumed;
-    do {
-        assumed = old;
-        const uint32_t o1 = static_cast<uint32_t>(assumed), o2 = static_cast<uint32_t>(assumed >> 32);
-        const uint32_t n1 = min(o1, k1);
-        const uint32_t n2 = min(max(o1, k1), min(o2, k2));
-        const unsigned long long nv = (static_cast<unsigned long long>(n2) << 32) | n1;
-        if (nv == assumed) break;
-        old = atomicCAS(a, assumed, nv);
-    } while (old != assumed);
-}
 
 // One shared-memory stage (rows train rows) against the NR query rows each lane holds.
 template <int NR, int RMAX, bool COL, bool TOP2, int CS>
@@ -432,6 +368,18 @@ int launch_big(const HammingParams &p, dim3 grid, bool top2, cudaStream_t stream
 }
 #endif
 
+// Kernel choice: SLAMFE_MATCH_MMA in `flags` selects the tcgen05 kernel (hamming_mma.cu) for this call;
+// the environment variable SLAMFE_MATCH_MMA=1 / 0 (read once) forces it on / off for every call.
+bool use_mma(int flags)
+{
+    static const int env = [] {
+        const char *v = getenv("SLAMFE_MATCH_MMA");
+        return v && *v ? (atoi(v) != 0 ? 1 : 0) : -1;
+    }();
+    if (env >= 0) return env == 1;
+    return (flags & SLAMFE_MATCH_MMA) != 0;
+}
+
 // Pick the CTA shape and the train slicing so that the grid fills the SMs.
 int run_hamming(HammingParams p, int n_problems, int max_nq, int max_nt, int64_t q_rows_total, int64_t t_rows_total,
                 int flags, cudaStream_t stream)
@@ -446,6 +394,7 @@ int run_hamming(HammingParams p, int n_problems, int max_nq, int max_nt, int64_t
         SLAMFE_CUDA_OK(cudaMemsetAsync(p.col_keys, 0xFF, sizeof(uint32_t) * t_rows_total, stream));
     if (max_nq <= 0 || max_nt <= 0) return 0;
     p.tma_quantum = 16 / gcd(p.t_stride, 16);
+    if (use_mma(flags)) return run_hamming_mma(p, n_problems, max_nq, max_nt, top2, stream);
 
     const int sms = sm_count();
     const int stages_total = (max_nt + TS - 1) / TS;

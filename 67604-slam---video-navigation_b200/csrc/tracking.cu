@@ -31,7 +31,7 @@ struct GatherParams {
     const int32_t *match_t;     // (L,): mutual right keypoint index per left keypoint
     Cams cam;
     int h_max;
-    int32_t *good_j, *good_t, *n_good, *n_hyp;
+    int32_t *good_j, *good_t, *n_good, *n_hyp, *n_hyp_full;
     double *pts, *lpix, *rpix;
 };
 
@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(TG_THREADS) track_gather_kernel(const GatherPa
         int it = 0;
         if (nm > 0) it = ransac_iterations(100.0 * (static_cast<double>(n_cur) / static_cast<double>(nm)));
         p.n_hyp[pair] = min(it, p.h_max);
+        if (p.n_hyp_full) p.n_hyp_full[pair] = it;  // it > h_max: this pair's RANSAC is truncated
     }
 }
 
@@ -186,8 +187,9 @@ extern "C" int slamfe_track_gather(const uint32_t *fwd_keys, const uint32_t *bwd
                                    const int32_t *r_off, const int32_t *n_links, const int32_t *n_matches,
                                    const float *pts_left, const float *pts_right, const int32_t *link_src,
                                    const int32_t *match_t, int n_pairs, const double *P, const double *Q, int h_max,
-                                   int32_t *good_j, int32_t *good_t, int32_t *n_good, int32_t *n_hyp, double *pts,
-                                   double *lpix, double *rpix, slamfe_stream_t stream)
+                                   int32_t *good_j, int32_t *good_t, int32_t *n_good, int32_t *n_hyp,
+                                   int32_t *n_hyp_full, double *pts, double *lpix, double *rpix,
+                                   slamfe_stream_t stream)
 {
     if (n_pairs < 0 || h_max < 0) return SLAMFE_EINVAL;
     if (n_pairs == 0) return 0;
@@ -205,7 +207,7 @@ extern "C" int slamfe_track_gather(const uint32_t *fwd_keys, const uint32_t *bwd
     p.pl = reinterpret_cast<const float2 *>(pts_left);
     p.pr = reinterpret_cast<const float2 *>(pts_right);
     p.link_src = link_src; p.match_t = match_t; p.h_max = h_max;
-    p.good_j = good_j; p.good_t = good_t; p.n_good = n_good; p.n_hyp = n_hyp;
+    p.good_j = good_j; p.good_t = good_t; p.n_good = n_good; p.n_hyp = n_hyp; p.n_hyp_full = n_hyp_full;
     p.pts = pts; p.lpix = lpix; p.rpix = rpix;
     track_gather_kernel<<<n_pairs, TG_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
     return launch_status();

@@ -167,11 +167,16 @@ class FrontEnd:
                      the D2H copy of chunk c-1 run concurrently (copy-in, 2 compute, copy-out streams).
     """
 
-    def __init__(self, P=None, Q=None):
-        from . import utils
-        self.P = utils.P if P is None else np.asarray(P, dtype=np.float64)
-        self.Q = utils.Q if Q is None else np.asarray(Q, dtype=np.float64)
-        self.K, self.M1, self.M2 = utils.K, utils.M1, utils.M2
+    def __init__(self, K=None, M1=None, M2=None):
+        """Cameras default to the ones the drop-in entry points score with at construction time
+        (slamfe.ransac.K / M1 / M2, which patch() copies from the reference, ransac.py:11); the projection
+        matrices of the triangulation stages are always derived from the same three (P = K @ M1,
+        Q = K @ M2, ransac.py:12), so matching, triangulation, hypotheses and scoring cannot disagree."""
+        from . import ransac as _ransac
+        self.K = np.asarray(_ransac.K if K is None else K, dtype=np.float64).reshape(3, 3)
+        self.M1 = np.asarray(_ransac.M1 if M1 is None else M1, dtype=np.float64).reshape(3, 4)
+        self.M2 = np.asarray(_ransac.M2 if M2 is None else M2, dtype=np.float64).reshape(3, 4)
+        self.P, self.Q = self.K @ self.M1, self.K @ self.M2
         self._out = None
         self._key = None
         self._trk = None

@@ -138,11 +138,15 @@ _default_verifier = None
 
 
 def _verifier():
+    """The verifier behind the drop-in entry points; rebuilt when slamfe.ransac.set_cameras (patch())
+    has changed the cameras since it was made."""
     global _default_verifier
-    if _default_verifier is None:
-        from . import ransac
-        _default_verifier = CandidateVerifier(K=ransac.K, M1=ransac.M1, M2=ransac.M2, block_pairs=64)
-    return _default_verifier
+    from . import ransac
+    v = _default_verifier
+    if v is None or not (np.array_equal(v.K, ransac.K) and np.array_equal(v.M1, ransac.M1)
+                         and np.array_equal(v.M2, ransac.M2)):
+        v = _default_verifier = CandidateVerifier(K=ransac.K, M1=ransac.M1, M2=ransac.M2, block_pairs=64)
+    return v
 
 
 def _keyframe_pool(db, frames):

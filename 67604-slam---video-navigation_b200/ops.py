@@ -16,8 +16,28 @@ def _torch():
     return _cabi.require_cuda()
 
 
+_MATCHER_KERNEL = "int"
+
+
+def set_matcher_kernel(kind):
+    """Which kernel the matcher entry points run: "int" = the INT-pipe carry-save kernel
+    (csrc/hamming.cu), "mma" = the tcgen05 tensor-core kernel (csrc/hamming_mma.cu, SLAMFE_MATCH_MMA).
+    Both produce identical keys.  Returns the previous setting.  (The environment variable
+    SLAMFE_MATCH_MMA=0/1, read by the library, overrides this per process.)"""
+    global _MATCHER_KERNEL
+    if kind not in ("int", "mma"):
+        raise ValueError("matcher kernel must be 'int' or 'mma'")
+    old, _MATCHER_KERNEL = _MATCHER_KERNEL, kind
+    return old
+
+
+def matcher_kernel():
+    return _MATCHER_KERNEL
+
+
 def _flags(best_only, compact=False):
-    return (_cabi.MATCH_BEST_ONLY if best_only else 0) | (_cabi.MATCH_COMPACT_KEYS if compact else 0)
+    return ((_cabi.MATCH_BEST_ONLY if best_only else 0) | (_cabi.MATCH_COMPACT_KEYS if compact else 0)
+            | (_cabi.MATCH_MMA if _MATCHER_KERNEL == "mma" else 0))
 
 
 def _desc_tensor(d):
@@ -47,7 +67,7 @@ def hamming_top2(q, t, desc_bytes=None, want_cols=False, t_index_base=0, best_on
     with torch.cuda.device(q.device):
         check(load_library().slamfe_hamming_top2(
             ptr(q), nq, q.stride(0), ptr(t), nt, t.stride(0) if nt else max(desc_bytes, 1), desc_bytes, t_index_base,
-            ptr(row_keys), ptr(col_keys), _cabi.MATCH_BEST_ONLY if best_only else 0, stream_handle()),
+            ptr(row_keys), ptr(col_keys), _flags(best_only), stream_handle()),
             "slamfe_hamming_top2")
     return row_keys, col_keys
 
@@ -286,7 +306,8 @@ def track_gather(o, ds_l_off, ds_r_off, pts_left, pts_right, n_pairs, P, Q, h_ma
             ptr(o["fwd_keys"]), ptr(o["bwd_keys"]), ptr(ds_l_off), ptr(ds_r_off), ptr(o["n_links"]),
             ptr(o["n_matches"]), ptr(pts_left), ptr(pts_right), ptr(o["link_src"]), ptr(o["match_t"]), n_pairs,
             Pb, Qb, int(h_max), ptr(out["good_j"]), ptr(out["good_t"]), ptr(out["n_good"]), ptr(out["n_hyp"]),
-            ptr(out["pts"]), ptr(out["lpix"]), ptr(out["rpix"]), stream_handle()), "slamfe_track_gather")
+            ptr(out.get("n_hyp_full")), ptr(out["pts"]), ptr(out["lpix"]), ptr(out["rpix"]), stream_handle()),
+            "slamfe_track_gather")
     return out
 
 

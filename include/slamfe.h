@@ -44,6 +44,7 @@ typedef void *slamfe_stream_t;
 /* matcher flags */
 #define SLAMFE_MATCH_BEST_ONLY 1 /* keep only the best neighbour (.match / crossCheck); row_keys[:,1] = KEY_NONE */
 #define SLAMFE_MATCH_COMPACT_KEYS 2 /* with BEST_ONLY: row_keys is (rows,) uint32, one key per query row */
+#define SLAMFE_MATCH_MMA 4 /* run the sweep on the tcgen05 tensor cores (int8 contraction, identical keys) */
 
 #define SLAMFE_EINVAL (-1)   /* bad argument (null pointer, negative size, stride < desc_bytes ...) */
 #define SLAMFE_ERANGE (-2)   /* size exceeds what the key encoding / grid can address */
@@ -231,7 +232,9 @@ int slamfe_ransac_score(const double *T, const uint8_t *hyp_valid, int H,
  *   - link gather + pixel arrays (ransac.py:76-81, :85-88) and fp64 triangulation of the previous
  *     frame's links (ransac.py:83) from the exact Link values (x float32, y = (yl+yr)/2 in double);
  *   - n_hyp[f] = min(h_max, calc_ransac_iteration(100 * n_links[f+1] / n_matches[f+1]))
- *     (ransac.py:59-67, database.py:26,80).
+ *     (ransac.py:59-67, database.py:26,80); n_hyp_full[f] (optional, may be NULL) receives the
+ *     UNCAPPED iteration count, so the caller can see which pairs h_max truncated (n_hyp_full[f] >
+ *     h_max) and re-run those at their full count — the reference always runs the full count.
  * Row-indexed outputs use frame f's row offset l_off[f] as base and hold n_good[f] entries:
  *   good_j, good_t (L,) int32 link indices in frame f / f+1;  pts (L,3), lpix (L,2), rpix (L,2) fp64.
  * They are the pts / l_pix / r_pix (pt_off = l_off, pt_cnt = n_good) of slamfe_ransac_hypotheses and
@@ -241,8 +244,8 @@ int slamfe_track_gather(const uint32_t *fwd_keys, const uint32_t *bwd_keys, cons
                         const int32_t *n_links, const int32_t *n_matches, const float *pts_left,
                         const float *pts_right, const int32_t *link_src, const int32_t *match_t, int n_pairs,
                         const double *P, const double *Q, int h_max, int32_t *good_j, int32_t *good_t,
-                        int32_t *n_good, int32_t *n_hyp, double *pts, double *lpix, double *rpix,
-                        slamfe_stream_t stream);
+                        int32_t *n_good, int32_t *n_hyp, int32_t *n_hyp_full, double *pts, double *lpix,
+                        double *rpix, slamfe_stream_t stream);
 
 /*
  * Loop-closure candidate gather (check_candidate_match, backend/loop/loop_closure.py:405-436, feeding

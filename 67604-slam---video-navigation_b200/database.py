@@ -80,12 +80,15 @@ def frames_from_tables(seq, tables):
 def create_db(frames, db, link_factory=None, chunk_frames=576, h_max=256, seed=1, front_end=None):
     """database.py:30-89 for a whole sequence.  `frames` as for pack_frames (or a PackedSequence),
     `db` a TrackingDB-like object, `link_factory` the reference's Link class (default: the stand-in
-    above).  Returns db.  Raises IndexError where the reference does (a frame pair without any
-    forward match: `matches_l_l[0]`, database.py:56)."""
+    above).  Returns db.  Raises where the reference does: IndexError for a frame pair without any
+    forward match (`matches_l_l[0]`, database.py:56), ValueError for a pair with fewer than 4 mutual
+    matches (`np.random.choice(n < 4, 4, replace=False)`, ransac.py:95).  h_max only sizes the batched
+    RANSAC launch: pairs whose calc_ransac_iteration exceeds it are re-run at their full count
+    (FrontEnd.rescore_truncated), so every pair gets the reference's number of hypotheses."""
     mk_link = link_factory or Link
     seq = frames if isinstance(frames, frontend.PackedSequence) else pack_frames(frames)
     fe = front_end or frontend.FrontEnd()
-    tables, _, _ = fe.run_host(seq, chunk_frames=chunk_frames, track=True, h_max=h_max, seed=seed)
+    tables, _, _ = fe.run_host(seq, chunk_frames=chunk_frames, track=True, h_max=h_max, seed=seed, full_ransac=True)
     for fr in frames_from_tables(seq, tables):
         links = [mk_link(float(a), float(b), float(c)) for a, b, c in fr["links"]]
         if fr["inliers_percent"] is None:
@@ -97,6 +100,8 @@ def create_db(frames, db, link_factory=None, chunk_frames=576, h_max=256, seed=1
             continue
         if len(fr["fwd_idx"]) == 0 or not fr["fwd_valid"].all():
             raise IndexError("tuple index out of range")  # database.py:56 on an empty match list
+        if int(tables["n_good"][fr["frame"] - 1]) < 4:   # ransac.py:95: np.random.choice(n < 4, 4, replace=False)
+            raise ValueError("Cannot take a larger sample than population when 'replace=False'")
         n = len(fr["fwd_idx"])
         matches = np.empty(n, dtype=object)  # database.py:60: np.array(matches_l_l)
         matches[:] = list(map(cv2.DMatch, range(n), fr["fwd_idx"].tolist(), [0] * n, fr["fwd_dist"].tolist()))

@@ -126,7 +126,7 @@ def to_device(seq: PackedSequence, device="cuda", non_blocking=True) -> DeviceSe
 
 
 RESULT_KEYS = ("match_t", "n_matches", "n_links", "link_src", "links", "xyz", "fwd_keys", "bwd_keys")
-TRACK_KEYS = ("inlier_fwd", "best", "n_good", "n_hyp")
+TRACK_KEYS = ("inlier_fwd", "best", "n_good", "n_hyp", "n_hyp_full")
 
 
 def chunk_bounds(n_frames, chunk_frames):
@@ -189,6 +189,7 @@ class FrontEnd:
         # (cudaMemsetAsync initialisation of the key tables is not counted)
         self.launches_per_run = 4
         self.last_launches = 0
+        self.last_truncated = 0   # pairs whose RANSAC iteration count exceeded h_max in the last run
 
     def _buffers(self, L, R, F, dev):
         torch = _cabi.require_cuda()
@@ -258,6 +259,7 @@ class FrontEnd:
             self._trk = {
                 "good_j": torch.empty((L,), **i32), "good_t": torch.empty((L,), **i32),
                 "n_good": torch.empty((n,), **i32), "n_hyp": torch.empty((n,), **i32),
+                "n_hyp_full": torch.empty((n,), **i32),
                 "pts": torch.empty((L, 3), **f64), "lpix": torch.empty((L, 2), **f64),
                 "rpix": torch.empty((L, 2), **f64),
                 "T": torch.empty((n * h_max, 3, 4), **f64), "hyp_valid": torch.empty((n * h_max,), dtype=torch.uint8,
@@ -280,7 +282,7 @@ class FrontEnd:
                          pt_off=l_off, pt_cnt=t["n_good"], n_frames=n_pairs, max_points=max_links, out=t)
         ops.scatter_inliers(t["best_mask"], t["good_j"], l_off, t["n_good"], t["best"], n_pairs, t["inlier_fwd"])
 
-    def track(self, ds: DeviceSequence, h_max=256, seed=1):
+    def track(self, ds: DeviceSequence, h_max=256, seed=1, full_ransac=False):
         """run(ds) followed by the frame-to-frame tracking of database.py:54-85 for every consecutive
         pair, without leaving the device: mutual forward/backward check + link gather + fp64
         triangulation of the previous links (slamfe_track_gather), RANSAC-PnP hypothesis generation
@@ -288,7 +290,12 @@ class FrontEnd:
         h_max), scoring of all hypotheses of all pairs in one launch (slamfe_ransac_score) and the
         inlier flags per forward match (in_prev_cur, database.py:84-85).  Returns the output dict of
         run() extended with good_j, good_t, n_good, n_hyp, pts, lpix, rpix, T, hyp_valid, counts, best,
-        best_mask, inlier_fwd."""
+        best_mask, inlier_fwd, n_hyp_full.
+
+        h_max caps the hypotheses per pair of the batched launch; n_hyp_full holds the reference's
+        uncapped count (calc_ransac_iteration, ransac.py:59-67).  full_ransac=True synchronises and re-runs
+        every pair with n_hyp_full > h_max at its full count (rescore_truncated), so the result never
+        depends on h_max; with False the caller can inspect n_hyp_full itself."""
         o = self.run(ds)
         F = ds.n_frames
         L = ds.desc_l.shape[0]
@@ -296,12 +303,59 @@ class FrontEnd:
         out = dict(o)
         out.update(t)
         if F < 2 or L == 0:  # nothing to track: report "no mutual matches, no hypothesis" for every pair
-            t["n_good"].zero_(); t["n_hyp"].zero_(); t["best"].fill_(-1); t["best"][:, 1].zero_()
+            t["n_good"].zero_(); t["n_hyp"].zero_(); t["n_hyp_full"].zero_(); t["best"].fill_(-1)
+            t["best"][:, 1].zero_()
             t["inlier_fwd"].zero_()
+            self.last_truncated = 0
             return out
         self._track_stages(o, t, ds.l_off, ds.r_off, ds.pts_l, ds.pts_r, F - 1, min(ds.max_nl, ds.max_nr), h_max, seed)
         self.last_launches += 4
+        if full_ransac:
+            self.rescore_truncated(ds.l_off.cpu().numpy(), F - 1, h_max, seed)
         return out
+
+    def rescore_truncated(self, l_off, n_pairs, h_max, seed=1, host_tables=None, h_cap=1 << 16):
+        """Re-run RANSAC-PnP at the reference's FULL iteration count for every pair the batched launch
+        truncated (n_hyp_full > h_max), on the device tables of the last track() / run_host():
+        hypotheses 0..n_hyp_full-1 of pair f are the same pure function of (seed, f, h) the batched
+        launch used, so the outcome equals a run with h_max >= n_hyp_full.  Synchronises.  Patches
+        best / best_mask / inlier_fwd on the device and, when given, in the host tables.  Returns the
+        list of re-run pairs.  A count above h_cap raises instead (calc_ransac_iteration grows without
+        bound as the stereo inlier rate falls: 14 389 at 20 %, 230 257 at 10 %)."""
+        torch = _cabi.require_cuda()
+        t = self._trk
+        full = t["n_hyp_full"][:n_pairs].cpu().numpy()
+        n_good = t["n_good"][:n_pairs].cpu().numpy()
+        todo = [int(f) for f in np.nonzero(full > h_max)[0]]
+        self.last_truncated = len(todo)
+        if not todo:
+            return todo
+        worst = int(full[todo].max())
+        if worst > h_cap:
+            raise _cabi.SlamfeError(f"calc_ransac_iteration asks for {worst} hypotheses (> {h_cap}) on pair "
+                                    f"{todo[int(np.argmax(full[todo]))]}: stereo inlier rate too low")
+        l_off = np.asarray(l_off, dtype=np.int64)
+        zero = torch.zeros((1,), dtype=torch.int32, device=t["pts"].device)
+        for f in todo:
+            l0, n, cap = int(l_off[f]), int(n_good[f]), int(l_off[f + 1] - l_off[f])
+            if n < 4:
+                continue
+            H = int(full[f])
+            pts, lp, rp = t["pts"][l0:l0 + n], t["lpix"][l0:l0 + n], t["rpix"][l0:l0 + n]
+            T, valid = ops.ransac_hypotheses(pts, lp, self.K, H, seed=seed, n_frames=1, frame_index_base=f)
+            _, best, mask = ops.ransac_score(T, pts, lp, rp, self.K, self.M1, self.M2, hyp_valid=valid)
+            t["best"][f:f + 1].copy_(best)
+            t["best_mask"][l0:l0 + n].copy_(mask)
+            ops.scatter_inliers(mask, t["good_j"][l0:l0 + n], zero, t["n_good"][f:f + 1], best, 1,
+                                t["inlier_fwd"][l0:l0 + cap])
+            self.last_launches += 3
+            if host_tables is not None:
+                if "best" in host_tables:
+                    host_tables["best"][f] = best[0].cpu().numpy()
+                if "inlier_fwd" in host_tables:
+                    host_tables["inlier_fwd"][l0:l0 + cap] = t["inlier_fwd"][l0:l0 + cap].cpu().numpy()
+        torch.cuda.synchronize()
+        return todo
 
     # -- host in, host out ---------------------------------------------------------------------
     def _input_buffers(self, seq: PackedSequence, dev):
@@ -320,13 +374,15 @@ class FrontEnd:
         return self._in
 
     def run_host(self, seq: PackedSequence, chunk_frames=576, device="cuda", keys=RESULT_KEYS, track=False,
-                 h_max=256, seed=1):
+                 h_max=256, seed=1, full_ransac=True):
         """Pinned host inputs -> pinned host result tables, copies overlapped with the kernels.
 
         Returns (dict of numpy views of the pinned result tables, h2d_bytes, d2h_bytes).  The call
         returns after the last table has landed in host memory.  track=True adds the tracking stages
         of track() per chunk and the tables TRACK_KEYS (inlier flags per forward match, best
-        hypothesis / inlier count and mutual-match count per pair)."""
+        hypothesis / inlier count, mutual-match count and capped / uncapped RANSAC iteration count per
+        pair).  full_ransac=True (default) re-runs the pairs h_max truncated at their full count before
+        returning (rescore_truncated; self.last_truncated = how many)."""
         torch = _cabi.require_cuda()
         if seq.tensors is None:
             raise ValueError("run_host needs a pinned PackedSequence (pack_sequence(..., pin=True))")
@@ -452,7 +508,7 @@ class FrontEnd:
                 for k in keys:
                     if k in ("n_matches", "n_links"):
                         lo, hi = f0, f1
-                    elif k in ("best", "n_good", "n_hyp"):        # per pair: pairs p0 .. f1-2
+                    elif k in ("best", "n_good", "n_hyp", "n_hyp_full"):   # per pair: pairs p0 .. f1-2
                         lo, hi = max(f0 - 1, 0), f1 - 1
                     elif k in ("fwd_keys", "inlier_fwd"):
                         lo, hi = fa, fb
@@ -467,7 +523,14 @@ class FrontEnd:
         ev_done[-1].synchronize()
         for s in self._streams:
             cur.wait_stream(s)
-        return {k: hout[k].numpy() for k in keys}, int(h2d), int(d2h)
+        tables = {k: hout[k].numpy() for k in keys}
+        self.last_truncated = 0
+        if track and F > 1:
+            if full_ransac and bool((tables["n_hyp_full"][:F - 1] > h_max).any()):
+                self.rescore_truncated(l_off, F - 1, h_max, seed, host_tables=tables)
+            else:
+                self.last_truncated = int((tables["n_hyp_full"][:F - 1] > h_max).sum())
+        return tables, int(h2d), int(d2h)
 
 
 def descriptor_pairs(n_l, n_r, n_links=None) -> int:

@@ -118,16 +118,37 @@ def test_patch_rebinds_reference_style_modules(slamfe):
     assert mods["final_project.algorithms.ransac"].transformation_agreement == "reference"
 
 
-def test_tracking_stages_vs_oracle(slamfe, oracle):
+OTHER_CALIB = (np.array([[707.0912, 0.0, 601.8873], [0.0, 707.0912, 183.1104], [0.0, 0.0, 1.0]]),
+               np.hstack([np.eye(3), np.zeros((3, 1))]),
+               np.hstack([np.eye(3), np.array([[-0.4731], [0.0], [0.0]])]))  # not KITTI-00: other fx, cx, cy, baseline
+
+
+@pytest.fixture(params=["kitti00", "other_calib"])
+def cameras(request):
+    """The cameras of the drop-in entry points: the default (KITTI 00) or another calibration installed the
+    way patch() does it (ransac.set_cameras); FrontEnd() / create_db must follow."""
+    from slamfe import ransac
+    old = (ransac.K, ransac.M1, ransac.M2)
+    if request.param == "other_calib":
+        ransac.set_cameras(*OTHER_CALIB)
+    yield request.param
+    ransac.set_cameras(*old)
+
+
+def test_tracking_stages_vs_oracle(slamfe, oracle, cameras):
     """FrontEnd.track: mutual check, link gather, fp64 triangulation, per-pair iteration counts and the
     scoring of the device-generated hypotheses, against the oracle's restatement of
-    database.py:54-85 / ransac.py:59-113 on the same frames."""
-    from slamfe import frontend, ransac, utils
+    database.py:54-85 / ransac.py:59-113 on the same frames — for the default cameras and for a
+    calibration installed through ransac.set_cameras (what patch() does with the reference's)."""
+    from slamfe import frontend, ransac
     rng = np.random.default_rng(73)
     frames = make_sequence(rng, [800, 1000, 30, 1200, 700])
     seq = frontend.pack_sequence(frames)
     ds = frontend.to_device(seq)
     fe = frontend.FrontEnd()
+    assert np.array_equal(fe.K, ransac.K) and np.array_equal(fe.P, ransac.K @ ransac.M1)
+    if cameras == "other_calib":
+        assert not np.array_equal(fe.K, frontend.FrontEnd(*__import__("slamfe").utils.read_cameras()).K)
     H = 48
     out = fe.track(ds, h_max=H, seed=5)
     out = fe.track(ds, h_max=H, seed=5)      # buffers reused
@@ -140,7 +161,13 @@ def test_tracking_stages_vs_oracle(slamfe, oracle):
         inl, _ = oracle.extract_inliers_outliers(pl, pr, cq, ct)
         valid, ln = oracle.create_links(pl, pr, cq[inl], ct[inl])
         feats.append(dl[valid]); links.append(np.asarray(ln, dtype=np.float64).reshape(-1, 3))
-    K, M1, M2 = utils.K, utils.M1, utils.M2
+    K, M1, M2 = ransac.K, ransac.M1, ransac.M2
+    xyz_tab = out["xyz"].cpu().numpy().astype(np.float64)
+    for f in range(len(frames)):   # the fp32 triangulation stage uses the same cameras
+        if len(links[f]):
+            ref = oracle.triangulate_links(links[f], K @ M1, K @ M2)
+            got = xyz_tab[seq.l_off[f]:seq.l_off[f] + len(links[f])]
+            assert (np.linalg.norm(got - ref, axis=1) / np.linalg.norm(ref, axis=1)).max() < 1e-5
     for f in range(len(frames) - 1):
         lo = seq.l_off[f]
         fi, fd, good = oracle.mutual_forward_backward(feats[f], feats[f + 1])
@@ -176,6 +203,62 @@ def test_tracking_stages_vs_oracle(slamfe, oracle):
         else:
             flags[good] = 1                     # good_idx[None] quirk, database.py:82
         assert np.array_equal(g["inlier_fwd"][lo:lo + len(feats[f])], flags)
+
+
+def test_full_ransac_does_not_depend_on_h_max(slamfe):
+    """h_max only sizes the batched RANSAC launch (csrc/tracking.cu caps n_hyp at it); the reference
+    always runs calc_ransac_iteration in full (ransac.py:59-67,94).  With full_ransac the truncated pairs
+    are re-run at their full count from the same (seed, pair, hypothesis) samples, so a tiny h_max gives
+    exactly the tables of an h_max that truncates nothing."""
+    from slamfe import frontend, ransac
+    rng = np.random.default_rng(76)
+    frames = make_sequence(rng, [700, 900, 650, 800, 750])
+    seq = frontend.pack_sequence(frames)
+    n_pairs = seq.n_frames - 1
+    big = frontend.FrontEnd()
+    ref = big.track(frontend.to_device(seq), h_max=256, seed=4)
+    ref = {k: ref[k].cpu().numpy() for k in ("best", "inlier_fwd", "n_hyp", "n_hyp_full", "n_links", "n_matches", "n_good")}
+    assert (ref["n_hyp_full"][:n_pairs] == ref["n_hyp"][:n_pairs]).all() and big.last_truncated == 0
+    for f in range(n_pairs):
+        pct = 100 * (ref["n_links"][f + 1] / ref["n_matches"][f + 1])
+        assert ref["n_hyp_full"][f] == ransac.calc_ransac_iteration(pct) > 8
+    small = frontend.FrontEnd()
+    cut = small.track(frontend.to_device(seq), h_max=8, seed=4)
+    assert (cut["n_hyp"][:n_pairs].cpu().numpy() == 8).all()
+    assert np.array_equal(cut["n_hyp_full"][:n_pairs].cpu().numpy(), ref["n_hyp_full"][:n_pairs])
+    got = small.track(frontend.to_device(seq), h_max=8, seed=4, full_ransac=True)
+    assert small.last_truncated == n_pairs
+    assert np.array_equal(got["best"][:n_pairs].cpu().numpy(), ref["best"][:n_pairs])
+    assert np.array_equal(got["inlier_fwd"].cpu().numpy(), ref["inlier_fwd"])
+    # the host pipeline: default full_ransac=True patches the host tables too; False only reports
+    host, _, _ = frontend.FrontEnd().run_host(seq, chunk_frames=2, track=True, h_max=8, seed=4)
+    assert np.array_equal(host["best"][:n_pairs], ref["best"][:n_pairs])
+    assert np.array_equal(host["inlier_fwd"], ref["inlier_fwd"])
+    fe3 = frontend.FrontEnd()
+    fe3.run_host(seq, chunk_frames=2, track=True, h_max=8, seed=4, full_ransac=False)
+    assert fe3.last_truncated == n_pairs
+
+
+def test_create_db_raises_like_the_reference_on_tiny_pairs(slamfe, oracle):
+    """A frame pair with fewer than 4 mutual matches: the reference dies in np.random.choice(n, 4,
+    replace=False) with ValueError (ransac.py:95); the batched builder must not silently flag every
+    match as an inlier instead."""
+    from slamfe import database as sdb, synth
+    rng = np.random.default_rng(77)
+    dl, dr, pl, pr = synth.stereo_frame(rng, 500)
+    cq, ct, _ = oracle.match_crosscheck(dl, dr)
+    inl, _ = oracle.extract_inliers_outliers(pl, pr, cq, ct)
+    keep_l, keep_r = cq[inl][:3], ct[inl][:3]          # second frame: exactly 3 stereo links
+    small = (pl[keep_l], pr[keep_r], dl[keep_l], dr[keep_r])
+
+    class FakeDB:
+        frameID_to_inliers_percent = {}
+
+        def add_frame(self, *a, **k):
+            pass
+
+    with pytest.raises(ValueError, match="larger sample than population"):
+        sdb.create_db([(pl, pr, dl, dr), small], FakeDB(), h_max=16)
 
 
 def test_tracking_edge_cases(slamfe):

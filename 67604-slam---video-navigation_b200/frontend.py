@@ -486,7 +486,7 @@ class FrontEnd:
                               "link_src": o["link_src"][qa:b], "match_t": o["match_t"][qa:b]}
                         tv = {k: trk[k][qa:qb] for k in ("good_j", "good_t", "pts", "lpix", "rpix", "best_mask",
                                                          "inlier_fwd")}
-                        tv.update({k: trk[k][p0:f1 - 1] for k in ("n_good", "n_hyp", "counts", "best", "work")})
+                        tv.update({k: trk[k][p0:f1 - 1] for k in ("n_good", "n_hyp", "n_hyp_full", "counts", "best", "work")})
                         tv["T"] = trk["T"][p0 * h_max:(f1 - 1) * h_max]
                         tv["hyp_valid"] = trk["hyp_valid"][p0 * h_max:(f1 - 1) * h_max]
                         self._track_stages(ov, tv, small_dev[lp0:lp1], small_dev[rp0:rp1], din["pts_l"][qa:b],

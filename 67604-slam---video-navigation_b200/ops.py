@@ -16,7 +16,7 @@ def _torch():
     return _cabi.require_cuda()
 
 
-_MATCHER_KERNEL = "int"
+_MATCHER_KERNEL = "mma"
 
 
 def set_matcher_kernel(kind):
@@ -272,6 +272,32 @@ def ransac_score(T, pts, l_pix, r_pix, K, M1, M2, hyp_valid=None, pt_off=None, n
             max_points,
             Kb, M1b, M2b, ptr(counts), ptr(best), ptr(mask), ptr(work), stream_handle()), "slamfe_ransac_score")
     return counts, best, mask
+
+
+def pnp_refit(T, best, pts, l_pix, mask, K, pt_off=None, pt_cnt=None, n_frames=1, max_iter=20, tol=1e-12, out=None):
+    """Refit of the pose on the consensus set (ransac.py:185-193) for n_frames problems in one launch
+    (slamfe_pnp_refit): T / best / mask as returned by ransac_hypotheses / ransac_score.
+    Returns (T_refit (n_frames, 3, 4) float64, status (n_frames,) int32, rms (n_frames,) float64)."""
+    torch = _torch()
+    dev = pts.device
+    T = T.contiguous()
+    H = T.numel() // (12 * n_frames) if n_frames else 0
+    out = out or {}
+    T_out = out.get("T_refit")
+    if T_out is None:
+        T_out = torch.empty((n_frames, 3, 4), dtype=torch.float64, device=dev)
+    status = out.get("refit_status")
+    if status is None:
+        status = torch.empty((n_frames,), dtype=torch.int32, device=dev)
+    rms = out.get("refit_rms")
+    if rms is None:
+        rms = torch.empty((n_frames,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(load_library().slamfe_pnp_refit(
+            ptr(T), H, ptr(best), ptr(pts.contiguous()), ptr(l_pix.contiguous()), ptr(mask), ptr(pt_off), ptr(pt_cnt),
+            pts.shape[0], n_frames, _cabi.host_doubles(K, 9), int(max_iter), float(tol), ptr(T_out), ptr(status),
+            ptr(rms), stream_handle()), "slamfe_pnp_refit")
+    return T_out, status, rms
 
 
 def ransac_hypotheses(pts, l_pix, K, H, seed=0, pt_off=None, pt_cnt=None, n_frames=1, n_hyp=None, sample_idx=None,

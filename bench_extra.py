@@ -43,6 +43,51 @@ class Workload:
         raise NotImplementedError
 
 
+def matcher_roofline(kernel_role, pairs_per_launch, launch_ms, peak_popc_g, sm_mhz=None, sms=148, desc_bytes=61):
+    """Roofline record of one matcher launch for whichever kernel is selected (ops.matcher_kernel()).
+
+    tcgen05 kernel (default): tensor bound.  Algorithmic work = one int8 MAC per descriptor bit and pair
+    (8*desc_bytes MAC = 2 ops each); peak = int8 dense rate = 2 x the bf16 rate in MEASURED_PEAKS.json (the
+    file has no int8 figure; tcgen05 kind::i8 runs at twice the kind::f16 rate).  The kernel's own ceiling is
+    the MMA issue floor: M128 x N192 x K32 per 96 clocks, 16 K-steps per tile -> 16 pairs/clk/SM.
+    INT kernel: popc bound as in round 1 (16 popc32 per pair against the measured POPC-pipe peak).
+    Both records carry the popc-equivalent figures BASELINE.json's metric names."""
+    from slamfe import ops
+    secs = launch_ms * 1e-3
+    pairs_s = pairs_per_launch / secs
+    popc = 16.0 * pairs_s / 1e9
+    common = {"launch_ms": launch_ms, "descriptor_pairs_per_launch": pairs_per_launch,
+              "gdesc_pairs_per_s": pairs_s / 1e9, "gpopc32_equiv_per_s": popc,
+              "popc_peak_measured_gpopc32": peak_popc_g, "frac_of_popc_peak": popc / peak_popc_g if peak_popc_g else None,
+              "traffic": None, "traffic_source": None}
+    if ops.matcher_kernel() == "mma":
+        peaks = _peaks()
+        bf16 = peaks.get("bf16_tflops", 1647.8)
+        peak = 2.0 * bf16
+        ach = 2.0 * 8 * desc_bytes * pairs_s / 1e12
+        mhz = sm_mhz or peaks.get("sm_max_mhz", 1965.0)
+        floor = sms * 16.0 * mhz * 1e6
+        common.update({
+            "kernel": f"hamming_mma_kernel ({kernel_role}): tcgen05.mma kind::i8, M128 N192 K32, A in TMEM",
+            "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TOP/s", "frac": ach / peak,
+            "peak_source": ("2 x bf16_tflops of MEASURED_PEAKS.json (int8 dense = twice the bf16 rate; the file "
+                            "has no int8 figure)" if peaks else "fallback 2 x 1647.8 TF"),
+            "mma_issue_floor_gdesc_pairs_per_s": floor / 1e9, "frac_of_mma_issue_floor": pairs_s / floor,
+            "note": "achieved = 2 ops x 8*desc_bytes MACs per descriptor pair (one MAC per descriptor bit; the "
+                    "kernel pads K to 512).  d = popc(q) + (1-2q).t accumulates exactly in int32, keys are "
+                    "bit-identical to the XOR/POPC kernel.  The binding resource is not the tensor pipe but the "
+                    "INT work around it: bit->byte expansion of the train tile (ALU) and the key fold of the "
+                    "128 x 192 accumulators (DESIGN.md 2.1)"})
+    else:
+        common.update({
+            "kernel": f"hamming_top2_kernel<256,2,9 adders> ({kernel_role})", "bound": "popc", "achieved": popc,
+            "peak": peak_popc_g, "unit": "Gpopc32/s", "frac": popc / peak_popc_g if peak_popc_g else None,
+            "peak_source": "measured on this GPU: slamfe_peak_kernel mode 0 (pure POPC chains)",
+            "note": "achieved counts the ALGORITHMIC 16 popc32 per descriptor pair (SURVEY 8d); the carry-save "
+                    "adders execute 7, so frac > 1 against the plain POPC-pipe peak is expected"})
+    return common
+
+
 # ------------------------------------------------------------------------------------------------
 class RansacWorkload(Workload):
     metric = "frames/s of RANSAC-PnP inlier scoring (4096 hypotheses x 5000 correspondences per frame)"
@@ -178,6 +223,7 @@ class LoopWorkload(Workload):
         self.pairs = pairs
         b = sdist.candidate_blocks(pairs, np.full(self.K, n), world)
         self.lo, self.hi = int(b[rank]), int(b[rank + 1])
+        self.bounds = b
         self.lengths = (b[1:] - b[:-1]) * n
         self.pair_lengths = b[1:] - b[:-1]
         self.kf_off = np.arange(self.K, dtype=np.int64) * n
@@ -241,15 +287,15 @@ class LoopWorkload(Workload):
         return fn
 
     def roofline(self, launch_ms, peak_popc):
-        ach = 16.0 * self._kernel_pairs / launch_ms / 1e6
-        return {"kernel": "hamming_top2_kernel<256,2,rows only,best-only,9 adders> via slamfe_hamming_top2_pairs",
-                "bound": "popc", "achieved": ach, "peak": peak_popc, "unit": "Gpopc32/s", "frac": ach / peak_popc,
-                "traffic": None, "launch_ms": launch_ms,
-                "note": "algorithmic 16 popc32 per descriptor pair; carry-save adders execute 7 (DESIGN.md 2.1); the "
-                        "RANSAC stages (hypotheses + scoring, fp64-bound) are the other ~40 % of a step",
-                "gdesc_pairs_per_s": self._kernel_pairs / launch_ms / 1e6}
+        r = matcher_roofline("rows only, best-only, compact keys, via slamfe_hamming_top2_pairs", self._kernel_pairs,
+                             launch_ms, peak_popc)
+        r["note"] += "; the RANSAC stages (hypotheses + scoring, fp64-bound) are the rest of a step"
+        return r
 
     def cpu_baseline(self):
+        """Rank 0: the reference's check_candidate_match on a few candidates of EVERY rank's block (cv2 match +
+        the oracle's 888-iteration RANSAC loop), compared with the all-gathered tables (world > 1) or the
+        local ones: match tables bit-exact, consensus sizes side by side."""
         import cv2
         from oracle import ref_oracle as ora
         from slamfe import utils
@@ -259,36 +305,52 @@ class LoopWorkload(Workload):
         n = self.n
         kf = lambda i: pool[i * n:(i + 1) * n]
         lk = lambda i: self.links_host[i * n:(i + 1) * n]
-        sample = [tuple(p) for p in self.pairs[self.lo:self.lo + 6].tolist()]
-        if self.rank == 0 and self.world == 1:
-            sample += [r for r in self.revisits][:2]
+        per_rank = max(1, 6 // self.world)
+        sample_idx = [int(self.bounds[r]) + k for r in range(self.world) for k in range(per_rank)
+                      if int(self.bounds[r]) + k < int(self.bounds[r + 1])]
+        index_of = {tuple(p): k for k, p in enumerate(self.pairs.tolist())}
+        sample_idx += [index_of[tuple(r)] for r in self.revisits[:2] if tuple(r) in index_of]
         mm.match(kf(1), kf(0))
         t0 = time.perf_counter()
         out = []
-        for i, j in sample:  # check_candidate_match, loop_closure.py:405-436
+        for g in sample_idx:  # check_candidate_match, loop_closure.py:405-436
+            i, j = (int(v) for v in self.pairs[g])
             ms = mm.match(kf(i), kf(j))
             ti = np.fromiter((m.trainIdx for m in ms), np.int64, n)
             idx = ora.ransac_pnp_for_tracking_db(np.arange(n), ti, lk(i), lk(j), 40, utils.K, utils.M1, utils.M2)
             out.append((ti, np.fromiter((int(m.distance) for m in ms), np.int64, n), 0 if idx is None else len(idx)))
         dt = time.perf_counter() - t0
-        table = self.table.cpu().numpy().view(np.uint32)
-        best = self.best.cpu().numpy()
-        index = {tuple(p): k for k, p in enumerate(self.pairs[self.lo:self.hi].tolist())}
+        if self.world > 1:   # what the all-gather delivered to this rank
+            tables = self.gathered.cpu().numpy().view(np.uint32)          # (world, max rows)
+            bests = self.gathered_best.cpu().numpy()                       # (world, max pairs, 2)
+        else:
+            tables = self.table.cpu().numpy().view(np.uint32)[None]
+            bests = self.best.cpu().numpy()[None]
         ok, ratios = True, []
-        for (i, j), (ti, td, cnt) in zip(sample, out):
-            k = index[(i, j)]
-            row = table[k * n:(k + 1) * n]
+        for g, (ti, td, cnt) in zip(sample_idx, out):
+            r = int(np.searchsorted(self.bounds, g, side="right") - 1)
+            k = g - int(self.bounds[r])
+            row = tables[r, k * n:(k + 1) * n]
             ok &= bool(np.array_equal(row & 0x3FFFFF, ti.astype(np.uint32)) and np.array_equal(row >> 22, td.astype(np.uint32)))
-            ratios.append((int(best[k, 1]), cnt))
-        accepted = {tuple(r): int(best[index[tuple(r)], 1]) for r in self.revisits if tuple(r) in index}
-        n_acc = int((best[:, 1] > 120).sum())
-        return ({"value": len(sample) / dt, "unit": self.unit, "cores": cv2.getNumThreads(), "kind": "port",
-                 "sample": f"{len(sample)} candidate pairs ({dt:.1f} s): cv2 {cv2.__version__} BFMatcher.match "
+            ratios.append((int(bests[r, k, 1]), cnt))
+        accepted, n_acc = {}, 0
+        for r in range(self.world):
+            cnt_r = int(self.bounds[r + 1] - self.bounds[r])
+            n_acc += int((bests[r, :cnt_r, 1] > 120).sum())
+        for rv in self.revisits:
+            g = index_of.get(tuple(rv))
+            if g is not None:
+                r = int(np.searchsorted(self.bounds, g, side="right") - 1)
+                accepted[str(tuple(rv))] = int(bests[r, g - int(self.bounds[r]), 1])
+        return ({"value": len(sample_idx) / dt, "unit": self.unit, "cores": cv2.getNumThreads(), "kind": "port",
+                 "sample": f"{len(sample_idx)} candidate pairs ({dt:.1f} s): cv2 {cv2.__version__} BFMatcher.match "
                            f"(all host threads) + the oracle's restatement of ransac_pnp's 888-iteration loop with "
                            f"cv2 EPnP (single thread, as the reference), loop_closure.py:405-436"},
-                {"pairs_checked": len(sample), "match_tables_bit_exact": ok,
-                 "inliers_gpu_vs_cpu": ratios, "planted_revisit_inliers": {str(k): v for k, v in accepted.items()},
-                 "candidates_accepted_over_120_inliers": n_acc, "planted": len(self.revisits)})
+                {"pairs_checked": len(sample_idx), "ranks_covered": self.world, "match_tables_bit_exact": ok,
+                 "inliers_gpu_vs_cpu": ratios, "planted_revisit_inliers": accepted,
+                 "candidates_accepted_over_120_inliers": n_acc, "planted": len(self.revisits),
+                 "bytes_all_gathered_per_step": int((self.gathered.numel() + self.gathered_best.numel()) * 4)
+                 if self.world > 1 else 0})
 
 
 # ------------------------------------------------------------------------------------------------
@@ -342,15 +404,20 @@ class DenseWorkload(Workload):
         return self._run(self.q, self.t)
 
     def e2e_step(self):
+        """Host buffers in, host table out.  Every rank needs all queries (replicated by design of the
+        train-slice sharding) but only ITS slice of every frame's train rows: one strided copy per frame."""
         torch = self.torch
         self.q.copy_(self.pinned["q"], non_blocking=True)
-        self.t.copy_(self.pinned["t"], non_blocking=True)
+        t3, p3 = self.t.view(self.F, self.n, 61), self.pinned["t"].view(self.F, self.n, 61)
+        lo, hi = self.base, self.base + self.cnt_slice
+        for f in range(self.F):
+            t3[f, lo:hi].copy_(p3[f, lo:hi], non_blocking=True)
         m = self._run(self.q, self.t)
         if not hasattr(self, "host_keys"):
             self.host_keys = torch.empty(m.shape, dtype=m.dtype, pin_memory=True)
         self.host_keys.copy_(m, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return self.pinned["q"].numel() * 2, m.numel() * 4
+        return self.pinned["q"].numel() + self.F * self.cnt_slice * 61, m.numel() * 4
 
     def time_kernel(self):
         from slamfe import ops
@@ -360,15 +427,11 @@ class DenseWorkload(Workload):
                                                 t_index_base=self.base)
 
     def roofline(self, launch_ms, peak_popc):
-        ach = 16.0 * self._kernel_pairs / launch_ms / 1e6
-        return {"kernel": "hamming_top2_kernel<256,2,rows only,top-2,9 adders> (batched over frames)",
-                "bound": "popc", "achieved": ach, "peak": peak_popc, "unit": "Gpopc32/s", "frac": ach / peak_popc,
-                "traffic": None, "launch_ms": launch_ms,
-                "note": "algorithmic 16 popc32 per descriptor pair; carry-save adders execute 7 (DESIGN.md 2.1)",
-                "gdesc_pairs_per_s": self._kernel_pairs / launch_ms / 1e6}
+        return matcher_roofline("rows only, top-2, batched over frames", self._kernel_pairs, launch_ms, peak_popc)
 
     def cpu_baseline(self):
         import cv2
+        from oracle import ref_oracle as ora
         cv2.setNumThreads(os.cpu_count() or 1)
         mm = cv2.BFMatcher(normType=cv2.NORM_HAMMING, crossCheck=False)
         q = self.pinned["q"].numpy()[: self.n]
@@ -381,11 +444,23 @@ class DenseWorkload(Workload):
         ti = np.array([[m.trainIdx for m in r] for r in res], np.uint32)
         td = np.array([[int(m.distance) for m in r] for r in res], np.uint32)
         ok = bool(np.array_equal(k & 0x3FFFFF, ti) and np.array_equal(k >> 22, td))
+        # the table every rank holds after all-gather + slamfe_merge_top2 (world > 1) against the C oracle
+        # (oracle/hamming_oracle.c) on sampled query rows of the last frame, which cv2 above did not see
+        f, rows = self.F - 1, np.arange(0, self.n, max(1, self.n // 1024))
+        qf = self.pinned["q"].numpy()[f * self.n:(f + 1) * self.n][rows]
+        tf = self.pinned["t"].numpy()[f * self.n:(f + 1) * self.n]
+        oi, od = ora.knn2(qf, tf)
+        kf = self.merged[f * self.n:(f + 1) * self.n].cpu().numpy().view(np.uint32)[rows]
+        ok_oracle = bool(np.array_equal(kf & 0x3FFFFF, oi.astype(np.uint32)) and
+                         np.array_equal(kf >> 22, od.astype(np.uint32)))
         return ({"value": float(self.n) * self.n / dt, "unit": self.unit, "cores": cv2.getNumThreads(),
                  "kind": "reference",
                  "sample": f"frame 0 (20000 x 20000, {dt:.2f} s): cv2 {cv2.__version__} BFMatcher.knnMatch(k=2), all "
                            f"host threads"},
-                {"frames_checked": 1, "top2_tables_bit_exact": ok})
+                {"frames_checked": 2, "top2_tables_bit_exact": ok and ok_oracle,
+                 "merged_over_ranks": self.world, "frame0_vs_cv2_knnMatch": ok,
+                 f"frame{f}_{len(rows)}_rows_vs_c_oracle": ok_oracle,
+                 "bytes_all_gathered_per_step": int(self.keys.numel() * 4 * self.world) if self.world > 1 else 0})
 
 
 # ------------------------------------------------------------------------------------------------
@@ -469,23 +544,15 @@ WORKLOADS = {"ransac": RansacWorkload, "loop": LoopWorkload, "dense": DenseWorkl
 
 
 # ------------------------------------------------------------------------------------------------
-def run(args, ClockSampler):
-    """Harness shared by the extra workloads: W warm-up steps, K timed steps between barriers with CUDA
-    events, max over ranks, e2e with host buffers, roofline of the dominant kernel, CPU baseline."""
+def run_workload(w, args, ClockSampler, rank, world, local_rank, dev, steps=None, warm=None):
+    """W warm-up steps, K timed steps between barriers with CUDA events (max over ranks), the e2e leg with
+    host buffers, the roofline of the dominant kernel and (rank 0) the CPU baseline + in-run parity.
+    Collective: every rank must call it.  Returns the record on rank 0, None elsewhere."""
     import torch
     import torch.distributed as tdist
-    import slamfe
-    from slamfe import dist as sdist, ops
-    if args.workload == "dropin":
-        if int(os.environ.get("RANK", "0")) == 0:
-            run_dropin(args)
-        return
-    rank, world, local_rank = sdist.init_from_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    dev = torch.device("cuda", local_rank)
-    slamfe.load_library()
-    w = WORKLOADS[args.workload](args, rank, world, dev)
+    from slamfe import ops
+    steps = args.steps if steps is None else steps
+    warm = max(args.warmup, 3) if warm is None else warm
 
     def barrier():
         torch.cuda.synchronize()
@@ -499,7 +566,6 @@ def run(args, ClockSampler):
             tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
         return float(t.item())
 
-    warm = max(args.warmup, 3)
     for _ in range(warm):
         w.step()
     barrier()
@@ -507,11 +573,11 @@ def run(args, ClockSampler):
     with ClockSampler(local_rank) as clocks:
         barrier()
         ev0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             w.step()
         ev1.record()
         barrier()
-    ms_per_step = allmax(ev0.elapsed_time(ev1)) / args.steps
+    ms_per_step = allmax(ev0.elapsed_time(ev1)) / steps
     units = getattr(w, "units_total", None)
     if units is None:
         units = w.units_local * world
@@ -523,38 +589,59 @@ def run(args, ClockSampler):
             h2d, d2h = w.e2e_step()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             h2d, d2h = w.e2e_step()
         barrier()
-        e_ms = allmax((time.perf_counter() - t0) * 1e3) / args.steps
+        e_ms = allmax((time.perf_counter() - t0) * 1e3) / steps
         e2e = {"value": units / (e_ms * 1e-3), "unit": w.unit, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": e_ms}
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": e_ms, "bytes_are": "per rank"}
 
-    roofline = cpu_baseline = parity = None
-    if rank == 0:
-        fn = w.time_kernel()
+    if rank != 0:
+        return None
+    fn = w.time_kernel()
+    fn()
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(2, steps)
+    k0.record()
+    for _ in range(reps):
         fn()
-        torch.cuda.synchronize()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = max(2, args.steps)
-        k0.record()
-        for _ in range(reps):
-            fn()
-        k1.record()
-        torch.cuda.synchronize()
-        launch_ms = k0.elapsed_time(k1) / reps
-        peak = ops.measure_peak(2 if args.workload == "ransac" else 0) / 1e9
-        roofline = w.roofline(launch_ms, peak)
-        roofline["peak_source"] = "measured on this GPU by slamfe_peak_kernel"
-        if not args.no_cpu_baseline:  # results of the last (collective) step are still in place
-            cpu_baseline, parity = w.cpu_baseline()
-        line = {"metric": w.metric, "value": value, "unit": w.unit, "n_gpus": world, "steps": args.steps,
-                "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": w.scaling,
-                "vs_baseline": None, "dtype": w.dtype, "data": "synthetic", "config": w.config,
-                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": w.launches_per_step * args.steps,
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity}
-        if hasattr(w, "desc_pairs_total"):
-            line["descriptor_pairs_per_s"] = w.desc_pairs_total / (ms_per_step * 1e-3)
+    k1.record()
+    torch.cuda.synchronize()
+    launch_ms = k0.elapsed_time(k1) / reps
+    roofline = w.roofline(launch_ms, ops.measure_peak(2 if w.dtype == "f64" else 0) / 1e9)
+    roofline.setdefault("peak_source", "measured on this GPU by slamfe_peak_kernel")
+    cpu_baseline = parity = None
+    if not args.no_cpu_baseline:  # results of the last (collective) step are still in place
+        cpu_baseline, parity = w.cpu_baseline()
+    line = {"metric": w.metric, "value": value, "unit": w.unit, "n_gpus": world, "steps": steps,
+            "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": w.scaling,
+            "vs_baseline": None, "dtype": w.dtype, "data": "synthetic", "config": w.config,
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": w.launches_per_step * steps,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity}
+    if hasattr(w, "desc_pairs_total"):
+        line["descriptor_pairs_per_s"] = w.desc_pairs_total / (ms_per_step * 1e-3)
+    return line
+
+
+def run(args, ClockSampler):
+    """bench.py --workload ransac|loop|dense|dropin: one workload, one JSON line on rank 0."""
+    import torch
+    import torch.distributed as tdist
+    import slamfe
+    from slamfe import dist as sdist
+    if args.workload == "dropin":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_dropin(args)
+        return
+    rank, world, local_rank = sdist.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    dev = torch.device("cuda", local_rank)
+    slamfe.load_library()
+    w = WORKLOADS[args.workload](args, rank, world, dev)
+    line = run_workload(w, args, ClockSampler, rank, world, local_rank, dev)
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         tdist.barrier()

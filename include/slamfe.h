@@ -293,6 +293,28 @@ int slamfe_ransac_hypotheses(const double *pts, const double *l_pix, const int32
                              uint64_t seed, int frame_index_base, const double *K, double *T, uint8_t *hyp_valid,
                              slamfe_stream_t stream);
 
+/*
+ * PnP refit on the consensus set: the final solve of ransac_pnp (final_project/algorithms/ransac.py:185-193,
+ * cv2.solvePnP(points_3d[best_idx], l_pix[best_idx], K, EPNP)) for every frame pair / loop-closure candidate
+ * of a batch in one launch, so the pose needs no host solve.  Levenberg-Marquardt on the left-image
+ * reprojection error of the inliers (mask = best_mask of slamfe_ransac_score), seeded by the winning
+ * hypothesis T[(f*H + best[f][0])]; one CTA per problem, fp64.  Not bit-comparable with OpenCV's EPnP
+ * (a different algorithm for the same objective): tolerance contract in DESIGN.md (rotation < 1e-3 rad,
+ * translation < 1 cm against cv2 on the reference's golden runs; equals an independent Gauss-Newton to 1e-9).
+ *   T (n_frames*H,12), best (n_frames,2) [index or -1, inlier count], pts/l_pix/mask as for slamfe_ransac_score
+ *   T_out  (n_frames,12) fp64: refit [R|t] (world -> camera, as rodriguez_to_mat, utils.py:16-18); zeros when
+ *          the problem has no pose
+ *   status (n_frames,) int32: k > 0 converged after k evaluations; 0 = no pose (no hypothesis or fewer than 4
+ *          inliers: ransac.py:187-188 returns None); -1 = singular normal equations (T_out = the seed);
+ *          -(max_iter+1) = iteration cap reached (T_out = best pose so far)
+ *   rms    (n_frames,) fp64 or NULL: RMS left reprojection error of the inliers at T_out, pixels
+ * K: 9 HOST doubles.  tol: relative decrease of the squared error that counts as converged (e.g. 1e-12).
+ */
+int slamfe_pnp_refit(const double *T, int H, const int32_t *best, const double *pts, const double *l_pix,
+                     const uint8_t *mask, const int32_t *pt_off, const int32_t *pt_cnt, int n_points, int n_frames,
+                     const double *K, int max_iter, double tol, double *T_out, int32_t *status, double *rms,
+                     slamfe_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Roofline micro-benchmarks (measure the pipe peaks the matcher / scorer are bound by)
  * ---------------------------------------------------------------------------------------- */

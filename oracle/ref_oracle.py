@@ -133,6 +133,74 @@ class ScorerHost:
         return out[:12].reshape(3, 4), out[12:].reshape(3, 4)
 
 
+_REFIT_LIB_PATH = os.path.join(_HERE, "librefit_host.so")
+_refit_lib = None
+
+
+def build_refit_shim(force: bool = False) -> str:
+    """Compile oracle/refit_host_shim.cpp (the product's csrc/refit_core.cuh, built for the HOST) ->
+    oracle/librefit_host.so."""
+    src = os.path.join(_HERE, "refit_host_shim.cpp")
+    hdr = os.path.join(os.path.dirname(_HERE), "67604-slam---video-navigation_b200", "csrc", "refit_core.cuh")
+    newest = max(os.path.getmtime(src), os.path.getmtime(hdr))
+    if force or not os.path.exists(_REFIT_LIB_PATH) or os.path.getmtime(_REFIT_LIB_PATH) < newest:
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++", src, "-o",
+                               _REFIT_LIB_PATH])
+    return _REFIT_LIB_PATH
+
+
+def refit_host_build(T_seed, K, pts, pix, mask=None, max_iter=20, tol=1e-12):
+    """Host build of the product's refit (same control flow as pnp_refit_kernel).
+    Returns (T (3,4), status, rms)."""
+    global _refit_lib
+    if _refit_lib is None:
+        build_refit_shim()
+        _refit_lib = ctypes.CDLL(_REFIT_LIB_PATH)
+    dp = ctypes.POINTER(ctypes.c_double)
+    c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    T0, Kc, P, uv = c(T_seed), c(K), c(pts), c(pix)
+    m = np.ones(len(P), np.uint8) if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+    out, rms = np.zeros(12), ctypes.c_double(0.0)
+    st = _refit_lib.refit_host(T0.ctypes.data_as(dp), Kc.ctypes.data_as(dp), P.ctypes.data_as(dp),
+                               uv.ctypes.data_as(dp), m.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)),
+                               ctypes.c_long(len(P)), int(max_iter), ctypes.c_double(tol), out.ctypes.data_as(dp),
+                               ctypes.byref(rms))
+    return out.reshape(3, 4), int(st), float(rms.value)
+
+
+def pnp_refit(T_seed, K, pts, pix, iters=30):
+    """Independent numpy restatement of the refit's objective (ransac.py:185-193: the pose that fits
+    the left-image pixels of the consensus set): Gauss-Newton on the left reprojection error with a
+    numerical-free analytic Jacobian in the axis-angle + translation chart at the current pose.
+    Returns (T (3,4), rms)."""
+    T = np.array(T_seed, dtype=np.float64).reshape(3, 4)
+    K = np.asarray(K, dtype=np.float64)
+    X = np.asarray(pts, dtype=np.float64)
+    uv = np.asarray(pix, dtype=np.float64)
+
+    def residual(T):
+        Y = X @ T[:, :3].T + T[:, 3]
+        q = Y @ K.T
+        return (q[:, :2] / q[:, 2:3] - uv), Y, q
+
+    for _ in range(iters):
+        r, Y, q = residual(T)
+        W = Y - T[:, 3]
+        J = np.zeros((len(X), 2, 6))
+        for row in range(2):
+            a = (K[row][None, :] - (q[:, row] / q[:, 2])[:, None] * K[2][None, :]) / q[:, 2:3]
+            J[:, row, :3] = np.cross(W, a)          # a . (w x W) = w . (W x a)
+            J[:, row, 3:] = a
+        Jf, rf = J.reshape(-1, 6), r.reshape(-1)
+        d = np.linalg.lstsq(Jf, -rf, rcond=None)[0]
+        T = np.hstack([rodriguez_to_mat(d[:3].reshape(3, 1), np.zeros((3, 1)))[:, :3] @ T[:, :3],
+                       (T[:, 3] + d[3:])[:, None]])
+        if np.linalg.norm(d) < 1e-13:
+            break
+    r, _, _ = residual(T)
+    return T, float(np.sqrt((r ** 2).sum() / len(X)))
+
+
 _TRI_LIB_PATH = os.path.join(_HERE, "libtriangulate_host.so")
 _tri_lib = None
 

@@ -50,3 +50,13 @@ def oracle():
 def slamfe():
     import slamfe as pkg
     return pkg
+
+
+@pytest.fixture(params=["mma", "int"])
+def matcher_kernel(request):
+    """Runs a test once per matcher kernel: "mma" = tcgen05 tensor-core kernel (csrc/hamming_mma.cu, the
+    default), "int" = INT-pipe carry-save kernel (csrc/hamming.cu).  Both must give identical keys."""
+    from slamfe import ops
+    old = ops.set_matcher_kernel(request.param)
+    yield request.param
+    ops.set_matcher_kernel(old)

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("matcher_kernel")]
 
 
 def make_sequence(rng, sizes):

@@ -4,7 +4,7 @@ bit-exact on the device-generated hypotheses, planted revisits accepted."""
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("matcher_kernel")]
 
 
 def _keyframes(rng, sizes, revisits):

@@ -3,7 +3,7 @@ oracle: bit-exact indices, distances, ordering and tie-breaks."""
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("matcher_kernel")]
 
 CASES = ("akaze", "ragged", "orb", "ties", "one_train")
 

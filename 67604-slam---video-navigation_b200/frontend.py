@@ -126,7 +126,7 @@ def to_device(seq: PackedSequence, device="cuda", non_blocking=True) -> DeviceSe
 
 
 RESULT_KEYS = ("match_t", "n_matches", "n_links", "link_src", "links", "xyz", "fwd_keys", "bwd_keys")
-TRACK_KEYS = ("inlier_fwd", "best", "n_good", "n_hyp", "n_hyp_full")
+TRACK_KEYS = ("inlier_fwd", "best", "n_good", "n_hyp", "n_hyp_full", "pose", "pose_status")
 
 
 def chunk_bounds(n_frames, chunk_frames):
@@ -267,6 +267,8 @@ class FrontEnd:
                 "counts": torch.empty((n, h_max), **i32), "best": torch.empty((n, 2), **i32),
                 "best_mask": torch.empty((L,), dtype=torch.uint8, device=dev), "work": torch.empty((n,), **i32),
                 "inlier_fwd": torch.empty((L,), dtype=torch.uint8, device=dev),
+                "pose": torch.empty((n, 3, 4), **f64), "pose_status": torch.empty((n,), **i32),
+                "pose_rms": torch.empty((n,), **f64),
             }
             self._trk_key = key
         return self._trk
@@ -281,6 +283,10 @@ class FrontEnd:
         ops.ransac_score(t["T"], t["pts"], t["lpix"], t["rpix"], self.K, self.M1, self.M2, hyp_valid=t["hyp_valid"],
                          pt_off=l_off, pt_cnt=t["n_good"], n_frames=n_pairs, max_points=max_links, out=t)
         ops.scatter_inliers(t["best_mask"], t["good_j"], l_off, t["n_good"], t["best"], n_pairs, t["inlier_fwd"])
+        # relative pose of every pair: refit on the consensus set (ransac.py:185-193), no host solve
+        ops.pnp_refit(t["T"], t["best"], t["pts"], t["lpix"], t["best_mask"], self.K, pt_off=l_off, pt_cnt=t["n_good"],
+                      n_frames=n_pairs, out={"T_refit": t["pose"], "refit_status": t["pose_status"],
+                                             "refit_rms": t["pose_rms"]})
 
     def track(self, ds: DeviceSequence, h_max=256, seed=1, full_ransac=False):
         """run(ds) followed by the frame-to-frame tracking of database.py:54-85 for every consecutive
@@ -290,7 +296,8 @@ class FrontEnd:
         h_max), scoring of all hypotheses of all pairs in one launch (slamfe_ransac_score) and the
         inlier flags per forward match (in_prev_cur, database.py:84-85).  Returns the output dict of
         run() extended with good_j, good_t, n_good, n_hyp, pts, lpix, rpix, T, hyp_valid, counts, best,
-        best_mask, inlier_fwd, n_hyp_full.
+        best_mask, inlier_fwd, n_hyp_full, pose (world-to-camera [R|t] of frame f+1 relative to frame f, refit
+        on the consensus set by slamfe_pnp_refit), pose_status, pose_rms.
 
         h_max caps the hypotheses per pair of the batched launch; n_hyp_full holds the reference's
         uncapped count (calc_ransac_iteration, ransac.py:59-67).  full_ransac=True synchronises and re-runs
@@ -305,11 +312,11 @@ class FrontEnd:
         if F < 2 or L == 0:  # nothing to track: report "no mutual matches, no hypothesis" for every pair
             t["n_good"].zero_(); t["n_hyp"].zero_(); t["n_hyp_full"].zero_(); t["best"].fill_(-1)
             t["best"][:, 1].zero_()
-            t["inlier_fwd"].zero_()
+            t["inlier_fwd"].zero_(); t["pose"].zero_(); t["pose_status"].zero_()
             self.last_truncated = 0
             return out
         self._track_stages(o, t, ds.l_off, ds.r_off, ds.pts_l, ds.pts_r, F - 1, min(ds.max_nl, ds.max_nr), h_max, seed)
-        self.last_launches += 4
+        self.last_launches += 5
         if full_ransac:
             self.rescore_truncated(ds.l_off.cpu().numpy(), F - 1, h_max, seed)
         return out
@@ -348,8 +355,14 @@ class FrontEnd:
             t["best_mask"][l0:l0 + n].copy_(mask)
             ops.scatter_inliers(mask, t["good_j"][l0:l0 + n], zero, t["n_good"][f:f + 1], best, 1,
                                 t["inlier_fwd"][l0:l0 + cap])
-            self.last_launches += 3
+            ops.pnp_refit(T, best, pts, lp, mask, self.K, out={"T_refit": t["pose"][f:f + 1],
+                                                               "refit_status": t["pose_status"][f:f + 1],
+                                                               "refit_rms": t["pose_rms"][f:f + 1]})
+            self.last_launches += 4
             if host_tables is not None:
+                for k in ("pose", "pose_status"):
+                    if k in host_tables:
+                        host_tables[k][f] = t[k][f].cpu().numpy()
                 if "best" in host_tables:
                     host_tables["best"][f] = best[0].cpu().numpy()
                 if "inlier_fwd" in host_tables:
@@ -486,12 +499,13 @@ class FrontEnd:
                               "link_src": o["link_src"][qa:b], "match_t": o["match_t"][qa:b]}
                         tv = {k: trk[k][qa:qb] for k in ("good_j", "good_t", "pts", "lpix", "rpix", "best_mask",
                                                          "inlier_fwd")}
-                        tv.update({k: trk[k][p0:f1 - 1] for k in ("n_good", "n_hyp", "n_hyp_full", "counts", "best", "work")})
+                        tv.update({k: trk[k][p0:f1 - 1] for k in ("n_good", "n_hyp", "n_hyp_full", "counts", "best", "work",
+                                                                  "pose", "pose_status", "pose_rms")})
                         tv["T"] = trk["T"][p0 * h_max:(f1 - 1) * h_max]
                         tv["hyp_valid"] = trk["hyp_valid"][p0 * h_max:(f1 - 1) * h_max]
                         self._track_stages(ov, tv, small_dev[lp0:lp1], small_dev[rp0:rp1], din["pts_l"][qa:b],
                                            din["pts_r"][ra0:rb], n_pairs, max_links, h_max, seed, pair_base=p0)
-                        self.last_launches += 4
+                        self.last_launches += 5
                 if f1 == F:  # the last frame has no successor, frame 0 no predecessor
                     o["fwd_keys"][int(l_off[F - 1]):].fill_(-1)
                     if track:
@@ -508,7 +522,7 @@ class FrontEnd:
                 for k in keys:
                     if k in ("n_matches", "n_links"):
                         lo, hi = f0, f1
-                    elif k in ("best", "n_good", "n_hyp", "n_hyp_full"):   # per pair: pairs p0 .. f1-2
+                    elif k in ("best", "n_good", "n_hyp", "n_hyp_full", "pose", "pose_status"):   # per pair: p0 .. f1-2
                         lo, hi = max(f0 - 1, 0), f1 - 1
                     elif k in ("fwd_keys", "inlier_fwd"):
                         lo, hi = fa, fb

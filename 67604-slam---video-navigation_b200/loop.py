@@ -8,9 +8,10 @@ than INLIERS_THRESHOLD = 120 inliers (`consensus_matches`, :572-599).  Here a wh
 (keyframe, candidate) pairs goes through each stage in one launch, device resident:
 
     slamfe_hamming_top2_pairs -> slamfe_pairs_gather -> slamfe_ransac_hypotheses -> slamfe_ransac_score
+    -> slamfe_pnp_refit (the final solve on the consensus set, ransac.py:185-193)
 
-Candidate gating (Mahalanobis distance on the pose graph), the final refit and the GTSAM bundle stay
-with the reference (out of scope).  Hypotheses come from the GPU generator
+Candidate gating (Mahalanobis distance on the pose graph) and the GTSAM bundle stay with the
+reference (out of scope).  Hypotheses come from the GPU generator
 (DESIGN.md section 2.6), so inlier counts are statistically — not bit-wise — equal to a run of the
 reference, which is itself unseeded.
 """
@@ -52,6 +53,7 @@ class CandidateVerifier:
                 "hyp_valid": torch.empty((n_pairs * H,), dtype=torch.uint8, device=dev),
                 "counts": torch.empty((n_pairs, H), **i32), "best": torch.empty((n_pairs, 2), **i32),
                 "best_mask": torch.empty((rows,), dtype=torch.uint8, device=dev), "work": torch.empty((n_pairs,), **i32),
+                "refit_status": torch.empty((n_pairs,), **i32), "refit_rms": torch.empty((n_pairs,), **f64),
             }
             self._key = key
         return self._buf
@@ -67,7 +69,9 @@ class CandidateVerifier:
         key_table: optional (sum of n_matches,) int32 CUDA tensor that receives the best-match keys of
         all pairs (pair-major), e.g. for the multi-GPU all-gather of match tables.  sync=False leaves
         the per-pair [best_hyp, inliers] table on the device (res["best_dev"], (P, 2) int32) and skips
-        the host copies."""
+        the host copies.  res["pose"] (P, 3, 4) / res["pose_status"] (P,): the world-to-camera [R|t] refit
+        on each candidate's consensus set (slamfe_pnp_refit; status > 0 = converged, 0 = fewer than 4
+        inliers) — `pose_dev` / `pose_status_dev` with sync=False."""
         torch = _cabi.require_cuda()
         dev = pool_desc.device
         pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
@@ -78,6 +82,8 @@ class CandidateVerifier:
         res = {"n_matches": kf_cnt[pairs[:, 0]].copy(), "inliers": np.zeros(len(pairs), np.int64),
                "best_hyp": np.full(len(pairs), -1, np.int64)}
         best_dev = torch.empty((len(pairs), 2), dtype=torch.int32, device=dev)
+        pose_dev = torch.empty((len(pairs), 3, 4), dtype=torch.float64, device=dev)
+        pose_ok_dev = torch.empty((len(pairs),), dtype=torch.int32, device=dev)
         row0 = 0
         keys_out, mask_out = [], []
         self.last_launches = 1
@@ -110,17 +116,21 @@ class CandidateVerifier:
                    "work": buf["work"][:n]}
             ops.ransac_score(T, v["pts"], v["lpix"], v["rpix"], self.K, self.M1, self.M2, hyp_valid=valid,
                              pt_off=out_off, pt_cnt=q_cnt, n_frames=n, max_points=max_n, out=out)
-            self.last_launches += 4
+            ops.pnp_refit(T, out["best"], v["pts"], v["lpix"], v["best_mask"], self.K, pt_off=out_off, pt_cnt=q_cnt,
+                          n_frames=n, out={"T_refit": pose_dev[b0:b0 + n], "refit_status": pose_ok_dev[b0:b0 + n],
+                                           "refit_rms": buf["refit_rms"][:n]})
+            self.last_launches += 5
             if want_masks:
                 kh = v["keys"].cpu().numpy().view(np.uint32)
                 mh = v["best_mask"].cpu().numpy().astype(bool)
                 for p in range(n):
                     keys_out.append(kh[out_off_h[p]:out_off_h[p + 1]].copy())
                     mask_out.append(mh[out_off_h[p]:out_off_h[p + 1]].copy())
-        res["best_dev"] = best_dev
+        res["best_dev"], res["pose_dev"], res["pose_status_dev"] = best_dev, pose_dev, pose_ok_dev
         if not sync:
             return res
         best = best_dev.cpu().numpy()
+        res["pose"], res["pose_status"] = pose_dev.cpu().numpy(), pose_ok_dev.cpu().numpy()
         res["best_hyp"][:] = best[:, 0]
         res["inliers"][:] = best[:, 1]
         with np.errstate(divide="ignore", invalid="ignore"):
@@ -179,25 +189,32 @@ def _verify_from_db(reference_key_frame, candidates, db, seed=None):
     return res, links
 
 
+REFIT = "gpu"   # "gpu": slamfe_pnp_refit inside the batch (default); "cv2": host cv2.solvePnP(EPNP) per candidate
+
+
 def _candidate_result(res, k, links_ref, ver):
     """(inlier DMatch list, percentage, camera_to_world pose or None) of candidate k, as
     check_candidate_match returns them (loop_closure.py:425-436 + ransac.py:185-204)."""
     import cv2
     from . import ransac
-    from .triangulation import triangulate_link_array
     keys, mask = res["keys"][k], res["mask"][k]
     idx = np.nonzero(mask)[0]
     if len(idx) < 4:  # ransac.py:187-188: (None, [], []) -> percentage_inliers = 0 via the except branch
         return [], 0, None
     ti = (keys & _cabi.KEY_IDX_MASK).astype(np.int64)
     td = (keys >> _cabi.KEY_IDX_BITS).astype(np.float64)
-    pts = triangulate_link_array(links_ref[idx], ver.P, ver.Q)
-    cur = res["_links"][k + 1][ti[idx]]
-    ok, rvec, tvec = cv2.solvePnP(pts, np.ascontiguousarray(cur[:, [0, 2]]), ver.K, distCoeffs=np.zeros((5, 1)),
-                                  flags=cv2.SOLVEPNP_EPNP)
-    if not ok:  # ransac.py:204 -> (None, None, None): the reference then fails on `for i in None`
-        raise TypeError("'NoneType' object is not iterable")
-    pose = ransac._pose3(ransac.rodriguez_to_mat(rvec, tvec)).inverse()
+    if REFIT == "gpu" and res["pose_status"][k] != 0:
+        T = res["pose"][k]
+    else:
+        from .triangulation import triangulate_link_array
+        pts = triangulate_link_array(links_ref[idx], ver.P, ver.Q)
+        cur = res["_links"][k + 1][ti[idx]]
+        ok, rvec, tvec = cv2.solvePnP(pts, np.ascontiguousarray(cur[:, [0, 2]]), ver.K, distCoeffs=np.zeros((5, 1)),
+                                      flags=cv2.SOLVEPNP_EPNP)
+        if not ok:  # ransac.py:204 -> (None, None, None): the reference then fails on `for i in None`
+            raise TypeError("'NoneType' object is not iterable")
+        T = ransac.rodriguez_to_mat(rvec, tvec)
+    pose = ransac._pose3(T).inverse()
     matches = list(map(cv2.DMatch, idx.tolist(), ti[idx].tolist(), [0] * len(idx), td[idx].tolist()))
     return matches, len(idx) / len(keys), pose
 

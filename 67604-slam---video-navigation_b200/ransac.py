@@ -128,9 +128,11 @@ def set_hypothesis_generator(name, seed=None):
         _gpu_seed[0] = int(seed)
 
 
-def ransac_device(points_3d, l_pix, r_pix, n_iter, seed=None, sample_idx=None):
+def ransac_device(points_3d, l_pix, r_pix, n_iter, seed=None, sample_idx=None, refit=False):
     """Generate n_iter hypotheses on the GPU and score them, one H2D and one D2H.
-    Returns (best_index or -1, best_count, best_mask (N,) bool, T_best (3,4) or None)."""
+    Returns (best_index or -1, best_count, best_mask (N,) bool, T_best (3,4) or None); with refit=True
+    T_best is the pose refit on the consensus set (slamfe_pnp_refit, ransac.py:185-193) when it has at
+    least 4 inliers, else the winning hypothesis."""
     import torch
     pts = _st.to_device("pts", np.ascontiguousarray(points_3d, dtype=np.float64).reshape(-1, 3))
     lp = _st.to_device("lp", np.ascontiguousarray(l_pix, dtype=np.float64).reshape(-1, 2))
@@ -144,6 +146,12 @@ def ransac_device(points_3d, l_pix, r_pix, n_iter, seed=None, sample_idx=None):
     b = _st.to_host("cb", best.view(-1))
     mask_h = _st.to_host("mask", mask).astype(bool)
     bi = int(b[0])
+    if refit and bi >= 0 and int(b[1]) >= 4:
+        Tr, status, _ = ops.pnp_refit(T, best, pts, lp, mask, K)
+        Tb = _st.to_host("Tb", Tr[0]).copy()
+        if int(_st.to_host("rs", status)[0]) == 0:
+            Tb = None
+        return bi, int(b[1]), mask_h, Tb
     Tb = _st.to_host("Tb", T[bi]).copy() if bi >= 0 else None
     return bi, int(b[1]), mask_h, Tb
 
@@ -209,9 +217,16 @@ def ransac_pnp(matches_l_l, prev_links, cur_links, inliers_percent=50):
     ransac_iterations = calc_ransac_iteration(inliers_percent)
     points_3d, l_pix, r_pix = _gather(matches_l_l, prev_links, cur_links)
     if HYPOTHESIS_GENERATOR == "p3p_gpu":
+        # the whole call on the device: sampling + P3P, scoring, refit on the consensus set; no host solve
         if len(points_3d) < 4:
             raise ValueError("Cannot take a larger sample than population when 'replace=False'")
-        best, best_inliers, mask, _ = ransac_device(points_3d, l_pix, r_pix, ransac_iterations)
+        best, best_inliers, mask, T = ransac_device(points_3d, l_pix, r_pix, ransac_iterations, refit=True)
+        best_matches_idx = np.where(mask)[0] if best >= 0 else []
+        if len(best_matches_idx) < 4:
+            return None, [], []
+        if T is None:
+            return None, None, None
+        return _pose3(T).inverse(), best_matches_idx, np.int64(best_inliers)
     else:
         Ts, ok = generate_hypotheses(points_3d, l_pix, ransac_iterations)
         _, best, best_inliers, mask = score_hypotheses(Ts, points_3d, l_pix, r_pix, hyp_valid=ok)

@@ -375,8 +375,8 @@ def main():
             g = e2e_tables[k]
             if k in ("n_matches", "n_links"):
                 same[k] = bool(np.array_equal(v[:FFh], g[:FFh]))
-            elif k in ("best", "n_good", "n_hyp", "n_hyp_full"):
-                if k == "best" and trunc.any():
+            elif k in ("best", "n_good", "n_hyp", "n_hyp_full", "pose", "pose_status"):
+                if k in ("best", "pose", "pose_status") and trunc.any():
                     continue   # run_host re-ran the truncated pairs at their full count; the resident run did not
                 same[k] = bool(np.array_equal(v[:n_pairs_loc], g[:n_pairs_loc]))
             elif k == "match_t":

@@ -184,3 +184,32 @@ def test_loop_closure_dropins_against_the_reference_golden(slamfe, golden, monke
     cand2, ms2, _ = loop.consensus_matches(4, [3, 1], db)
     assert cand2 == 3 and abs(len(ms2) - len(ms)) <= 0.2 * len(ms)
     assert loop.consensus_matches(4, [], db) == (None, [], None)
+
+
+def test_loop_closure_pose_needs_no_host_solve(slamfe, golden, monkeypatch):
+    """check_candidate_match's pose comes from slamfe_pnp_refit inside the batch (loop.REFIT = "gpu"); with
+    the same seed (same consensus set) it agrees with the reference's recipe, cv2.solvePnP(EPNP) on the
+    consensus set (loop.REFIT = "cv2", ransac.py:185-204)."""
+    import cv2
+    from slamfe import loop
+    db, g = _GoldenDB(golden("create_db")), golden("loop_candidates")
+    checked = 0
+    for k, (a, b) in enumerate(g["pairs"]):
+        poses = {}
+        for mode in ("gpu", "cv2"):
+            monkeypatch.setattr(loop, "REFIT", mode)
+            np.random.seed(8 + k)
+            calls = []
+            if mode == "gpu":
+                monkeypatch.setattr(cv2, "solvePnP", lambda *a, **kw: calls.append(1) or (_ for _ in ()).throw(
+                    AssertionError("host solve on the device-refit path")))
+            matches, pct, pose = loop.check_candidate_match(int(a), int(b), db)
+            monkeypatch.undo()
+            poses[mode] = (None if pose is None else pose.matrix(), len(matches))
+        assert poses["gpu"][1] == poses["cv2"][1]
+        if poses["gpu"][1] >= 60:
+            Pg, Pc = poses["gpu"][0], poses["cv2"][0]
+            dR = Pg[:3, :3] @ Pc[:3, :3].T
+            assert np.linalg.norm(dR - dR.T) / (2 * np.sqrt(2)) < 2e-3 and np.linalg.norm(Pg[:3, 3] - Pc[:3, 3]) < 0.02
+            checked += 1
+    assert checked >= 2

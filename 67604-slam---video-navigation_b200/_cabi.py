@@ -54,6 +54,7 @@ _SIGNATURES = {
     "slamfe_scatter_inliers": (c_int, [c_void_p] * 5 + [c_int, c_void_p, c_int64, c_void_p]),
     "slamfe_ransac_hypotheses": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                          c_void_p, c_uint64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "slamfe_track_ids": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64] + [c_void_p] * 7),
     "slamfe_pnp_refit": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                  c_int, c_void_p, c_int, ctypes.c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "slamfe_peak_kernel": (c_int, [c_int, c_int, c_int, c_int, c_void_p, POINTER(c_int), c_void_p]),

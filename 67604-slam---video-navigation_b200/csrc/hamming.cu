@@ -394,7 +394,7 @@ int run_hamming(HammingParams p, int n_problems, int max_nq, int max_nt, int64_t
         SLAMFE_CUDA_OK(cudaMemsetAsync(p.col_keys, 0xFF, sizeof(uint32_t) * t_rows_total, stream));
     if (max_nq <= 0 || max_nt <= 0) return 0;
     p.tma_quantum = 16 / gcd(p.t_stride, 16);
-    if (use_mma(flags)) return run_hamming_mma(p, n_problems, max_nq, max_nt, top2, stream);
+    if (use_mma(flags) && hamming_mma_supports(p.desc_bytes)) return run_hamming_mma(p, n_problems, max_nq, max_nt, top2, stream);
 
     const int sms = sm_count();
     const int stages_total = (max_nt + TS - 1) / TS;

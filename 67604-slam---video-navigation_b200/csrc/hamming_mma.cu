@@ -5,29 +5,48 @@
 //
 // Hamming distance as an exact integer contraction.  With query bits q_k and train bits t_k,
 //     d(q, t) = sum_k q_k + sum_k t_k * (1 - 2 q_k) = popc(q) + A_q . B_t,
-// A_q = (1 - 2 q_k) in {+1, -1} (int8), B_t = t_k in {0, 1} (uint8).  tcgen05.mma kind::i8 accumulates
-// A . B^T exactly in int32, so distance, key = (d << 22) | index and therefore every tie-break are
-// bit-identical to the XOR/POPC kernel.  The order of the 512 K positions is irrelevant as long as A
-// and B agree, which makes the bit -> byte expansion cheap: output word s of input word w holds bits
-// s, s+8, s+16, s+24 of w, i.e. (w >> s) & 0x01010101.
+// A_q = (1 - 2 q_k) in {+1, -1} (int8), B_t = t_k.  tcgen05.mma kind::i8 accumulates A . B^T exactly
+// in int32, so distance, key = (d << 22) | index and every tie-break are bit-identical to the
+// XOR/POPC kernel.  Three refinements make the accumulator directly usable as a 16-bit key field:
+//   * B_t = 128 * t_k (uint8 0x80): the bit -> byte expansion is one IMAD (w << (7 - s), FMA pipe) and
+//     one LOP3 (& 0x80808080, ALU pipe) per four K positions, and the accumulator is 128 * (...), i.e.
+//     already shifted past a 7-bit index field;
+//   * popc(q) rides in spare K positions: descriptor byte 4*ws + 3 (ws = desc_bytes / 4) lies beyond
+//     the descriptor, its 8 K positions are free.  Four of them carry A = c_i (sum c_i = popc(q),
+//     c_i <= 127) against B = 0x80 on every valid train row, so acc = 128 * d >= 0 and d needs no
+//     per-pair fix-up;
+//   * the other four carry A = 127 against B = 0x80 on INVALID train rows only (rows past the end of
+//     the last stage, whose data bits are zero): acc = 128 * 508, larger than any real distance
+//     (d <= 8 * 63), so ragged stages need no masking in the epilogue.
+// The order of the K positions is irrelevant as long as A and B agree: output word s of input word w
+// holds bits s, s+8, s+16, s+24 of w.  Needs desc_bytes <= 63 (AKAZE: 61); 64-byte descriptors take
+// the INT kernel.
 //
-// One CTA = 128 query rows (UMMA M) against a train sweep in stages of 192 rows (UMMA N):
-//   warps 0-3   epilogue: write the +-1 query tile into TMEM once (A operand, 128 columns), then per
-//               stage tcgen05.ld the 128 x 192 int32 accumulators (lane = query row) and fold them into
-//               the running row keys (1 IMAD + 1 add-min per pair); column minima (crossCheck /
-//               backward match) by one redux.sync.min per column and warp, merged through shared
-//               memory into one global atomicMin per train row and CTA;
-//   warps 4-9   expanders: raw 61-byte train rows (1-D TMA bulk copy, double buffered) -> 0/1 bytes in
+// One CTA = 256 query rows (two UMMA M = 128 tiles, both +-1 tiles resident in TMEM as the A operands)
+// against a train sweep in stages of 128 rows (UMMA N = 128):
+//   warps 0-7   epilogue, warp w owns TMEM lane quarter w & 3 of query tile w >> 2.  Once: write the
+//               query tile into TMEM (A operand, 128 columns per tile).  Per stage and 64 columns: one
+//               tcgen05.ld (.pack::16b, 64 columns in 32 registers), key16 = acc + column (one IMAD per two
+//               pairs), running minimum with VIMNMX3.U16x2 (one per four pairs), folded into the 32-bit row
+//               keys once per stage.  Column minima (crossCheck / backward match): the warp transposes its
+//               32 x 64 block of distances through a swizzled shared-memory scratch, every lane reduces
+//               two train columns over the warp's 32 query rows (key16 = acc/4 + row), the 4 warps of a
+//               tile merge through shared-memory atomics, one global atomicMin per train row, tile and stage;
+//   warps 8-11  expanders: raw 61-byte train rows (1-D TMA bulk copy, double buffered) -> 0x80/0 bytes in
 //               the K-major SWIZZLE_NONE core-matrix layout of the B operand (8 rows x 16 B contiguous,
-//               K chunks LBO = 192*16 B apart), one row per lane, conflict-free STS.128;
-//   warp 10     one thread issues the TMA copies and 16 tcgen05.mma (M128 N192 K32, A from TMEM) per
-//               stage; tcgen05.commit hands the B stage back to the expanders and the accumulator
-//               stage to the epilogue.  Two B stages (2 x 96 KB) and two accumulator stages
-//               (2 x 192 TMEM columns) keep expansion, MMA and epilogue of consecutive stages overlapped.
+//               K chunks LBO = 128*16 B apart), one row per thread, conflict-free STS.128;
+//   warp 12     issues the TMA copies and 2 x 16 tcgen05.mma (M128 N128 K32, A from TMEM) per stage from one
+//               elected lane; tcgen05.commit hands the B stage back to the expanders and the accumulator
+//               to the epilogue.  The two query tiles' accumulators (2 x 128 TMEM columns) double-buffer
+//               each other: while the epilogue drains tile 0 the tensor core works on tile 1 of the same
+//               B stage (a CTA with a single tile alternates between the two accumulators instead).
+// Expanding a train row once per 256 query rows (v1: per 128) and the packed epilogue take the INT work
+// around the tensor pipe from ~6000 to ~1000 warp instructions per 16 K pairs (profiles/r02_*).  The MMA
+// issue loop is fully unrolled with precomputed descriptors: a tcgen05.mma that takes 64 cycles leaves the
+// issuing thread no room for per-instruction descriptor arithmetic (scripts/probe_tcgen05.cu rate2).
 // Facts pinned on a B200 by scripts/probe_tcgen05.cu (profiles/r02_probe_tcgen05.log): descriptor
 // field meaning (LBO = K-chunk stride, SBO = 8-row stride), TMEM A layout (4 K-bytes per column),
-// exactness, 135 cycles per M128 N256 K32 TS-mode MMA (94 % of the 128-cycle floor), TMEM reads
-// >= 577 B/clk/SM, redux.sync ~1 per clk per SM.
+// exactness, MMA cycles at the issue floor, TMEM read bandwidth.
 #include "common.cuh"
 #include "hamming_params.cuh"
 
@@ -35,23 +54,28 @@ namespace slamfe {
 
 namespace {
 
-constexpr int MQ = 128;                 // query rows per CTA = UMMA M
-constexpr int NT = 192;                 // train rows per stage = UMMA N
+constexpr int MQ = 128;                 // query rows per UMMA tile (M)
+constexpr int QT = 2;                   // query tiles per CTA
+constexpr int CQ = MQ * QT;             // query rows per CTA
+constexpr int NT = 128;                 // train rows per stage = UMMA N
 constexpr int KCH = 32;                 // 16-byte K chunks per row (512 K positions)
 constexpr int LBO = NT * 16;            // bytes between consecutive K chunks of the B tile
-constexpr int B_STAGE = KCH * LBO;      // 98304
+constexpr int B_STAGE = KCH * LBO;      // 65536
+constexpr int NB = 2;                   // B (and raw) stages
+constexpr int ND = 2;                   // accumulators (one per query tile; see above)
 constexpr int RAW_STAGE = NT * SLAMFE_MAX_DESC_BYTES + 16;
-constexpr int N_EPI_WARPS = 4, N_EXP_WARPS = 6;
+constexpr int N_EPI_WARPS = 8, N_EXP_WARPS = 4;
 constexpr int MMA_WARP = N_EPI_WARPS + N_EXP_WARPS;
 constexpr int THREADS = (MMA_WARP + 1) * 32;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t TMEM_A = 2 * NT;     // columns 384..511 hold the query tile
+constexpr uint32_t TMEM_A = ND * NT;    // columns 256..511 hold the two query tiles
 
 struct __align__(16) Smem {
-    uint8_t b[2][B_STAGE];
-    uint8_t raw[2][RAW_STAGE];
-    uint32_t colmin[2][N_EPI_WARPS][NT];
-    uint64_t raw_full[2], b_full[2], b_empty[2], d_full[2], d_empty[2], a_ready;
+    uint8_t b[NB][B_STAGE];
+    uint8_t raw[NB][RAW_STAGE];
+    uint32_t scratch[N_EPI_WARPS][32 * 32];  // per-warp 32 rows x 64 packed distances, chunk-swizzled
+    uint32_t colmin[QT][2][NT];              // per query tile, double buffered over stages
+    uint64_t raw_full[NB], b_full[NB], b_empty[NB], d_full[ND], d_empty[ND], a_ready;
     uint32_t tmem_base;
 };
 
@@ -89,18 +113,39 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                  "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+// 64 accumulator columns of this warp's 32 lanes as 32 registers: register j = column 2j (low half) and
+// column 2j + 1 (high half); the accumulators are < 2^16 by construction.
+#ifndef SLAMFE_MMA_PACK16
+#define SLAMFE_MMA_PACK16 1
+#endif
+#define SLAMFE_LD32_OPERANDS                                                                                          \
+    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"      \
+    "%29,%30,%31}, [%32];"                                                                                            \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), \
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),      \
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),     \
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                   \
+        : "r"(taddr)                                                                                                  \
+        : "memory"
+__device__ __forceinline__ void tmem_ld64_packed(uint32_t taddr, uint32_t (&v)[32])
 {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
-        "%29,%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
+#if SLAMFE_MMA_PACK16
+    // .pack::16b: two adjacent 32-bit columns -> one register (low 16 bits of each), done by the load path
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 " SLAMFE_LD32_OPERANDS);
+#else
+    // plain loads, packed with one IMAD per column pair
+    uint32_t out[32];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 " SLAMFE_LD32_OPERANDS);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; ++j) out[16 * half + j] = v[2 * j + 1] * 65536u + v[2 * j];
+        taddr += 32;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = out[j];
+#endif
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -113,31 +158,40 @@ constexpr uint32_t kIdesc = (2u << 4)                               // D format 
 
 // bits s, s+8, s+16, s+24 of w as four 0/1 bytes
 __device__ __forceinline__ uint32_t spread(uint32_t w, int s) { return (w >> s) & 0x01010101u; }
-
-// Fold 32 accumulator columns [c0, c0+32) of one stage into the running keys.
-template <bool COL, bool TOP2, bool MASKED>
-__device__ __forceinline__ void fold_chunk(const uint32_t (&v)[32], int c0, int rows, uint32_t rowbase_j,
-                                           uint32_t colbias, uint32_t &b1, uint32_t &b2, uint32_t colmin_addr, int lane)
+// the same four bits as 0x80 / 0 bytes; `mul` = 1 << (7 - s) lives in a register so that the shift is an
+// IMAD on the FMA pipe (ptxas would turn a constant power of two into an ALU shift)
+__device__ __forceinline__ uint32_t spread80(uint32_t w, uint32_t mul)
 {
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-        if (MASKED && c0 + c >= rows) break;
-        // v = popc-free part of the distance: d = popc(q) + v; all arithmetic is exact mod 2^32
-        const uint32_t key = v[c] * (1u << KEY_IDX_BITS) + rowbase_j + static_cast<uint32_t>(c);
-        if (TOP2) {
-            const uint32_t hi = max(b1, key);
-            b2 = min(b2, hi);
-        }
-        b1 = min(b1, key);
-        if (COL) {
-            const uint32_t ck = v[c] * (1u << KEY_IDX_BITS) + colbias;
-            const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, ck);
-            if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(colmin_addr + 4u * (c0 + c)), "r"(m) : "memory");
-        }
-    }
+    uint32_t x;
+    asm("mad.lo.u32 %0, %1, %2, 0;" : "=r"(x) : "r"(w), "r"(mul));
+    return x & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t add_imad(uint32_t x, uint32_t one, uint32_t c)
+{
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(one), "r"(c));
+    return r;
 }
 
-// grid = (query tiles of 128 rows, train slices, problems)
+// merge a candidate key into a sorted (b1 <= b2) pair
+__device__ __forceinline__ void top2_insert(uint32_t key, uint32_t &b1, uint32_t &b2)
+{
+    b2 = min(b2, max(b1, key));
+    b1 = min(b1, key);
+}
+
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// accumulator used by (stage s, query tile t) and how many times it was used before
+__device__ __forceinline__ int acc_of(int s, int t, int n_tiles) { return n_tiles == 2 ? t : (s & 1); }
+__device__ __forceinline__ int acc_use(int s, int n_tiles) { return n_tiles == 2 ? s : (s >> 1); }
+
+// grid = (query tiles of 256 rows, train slices, problems)
 template <bool COL, bool TOP2>
 __global__ void __launch_bounds__(THREADS, 1) hamming_mma_kernel(const HammingParams p)
 {
@@ -158,24 +212,30 @@ __global__ void __launch_bounds__(THREADS, 1) hamming_mma_kernel(const HammingPa
         t_row0 = p.t_off[prob];
         nt = p.t_cnt ? p.t_cnt[prob] : p.t_off[prob + 1] - t_row0;
     }
-    const int qt0 = blockIdx.x * MQ;
+    const int qt0 = blockIdx.x * CQ;
     const int tb = blockIdx.y * p.t_slice;
     if (qt0 >= nq || tb >= nt) return;  // CTA-uniform; outputs were pre-set to KEY_NONE
     const int te = min(nt, tb + p.t_slice);
     const int n_stage = (te - tb + NT - 1) / NT;
-    const int n_k = (p.desc_bytes + 3) >> 2;  // MMA K steps: 32 K positions = 4 descriptor bytes each
+    const int ws = p.desc_bytes >> 2;   // input word whose byte 3 holds the 8 spare K positions
+    const int n_k = ws + 1;             // MMA K steps: 32 K positions = 4 descriptor bytes each
+    const int n_tiles = (nq - qt0 > MQ) ? 2 : 1;
 
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NB; ++i) {
             mbar_init(&sm.raw_full[i], 1);
             mbar_init(&sm.b_full[i], N_EXP_WARPS * 32);
             mbar_init(&sm.b_empty[i], 1);
-            mbar_init(&sm.d_full[i], 1);
-            mbar_init(&sm.d_empty[i], N_EPI_WARPS * 32);
         }
-        mbar_init(&sm.a_ready, N_EPI_WARPS * 32);
+        for (int i = 0; i < ND; ++i) {
+            mbar_init(&sm.d_full[i], 1);
+            mbar_init(&sm.d_empty[i], 128);
+        }
+        mbar_init(&sm.a_ready, n_tiles * 128);
         fence_mbar_init();
     }
+    if (COL)
+        for (int i = tid; i < QT * 2 * NT; i += THREADS) (&sm.colmin[0][0][0])[i] = KEY_NONE;
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)),
                      "r"(TMEM_COLS)
@@ -198,161 +258,252 @@ __global__ void __launch_bounds__(THREADS, 1) hamming_mma_kernel(const HammingPa
 
     if (warp < N_EPI_WARPS) {
         // ============================== epilogue warps ==============================
-        const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;  // this warp's TMEM lane quarter
-        const int row = qt0 + tid;
-        const int src_row = min(row, nq - 1);  // rows past the end mirror the last row (results not written)
-        uint32_t pq = 0;
-        {
-            uint32_t w[W];
-            load_desc_global(p.q + static_cast<size_t>(q_row0 + src_row) * p.q_stride, p.desc_bytes, w);
+        const int tile = warp >> 2;
+        if (tile < n_tiles) {  // warp-uniform: a CTA over the last <= 128 query rows has a single tile
+            const int quarter = warp & 3;
+            const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;  // this warp's TMEM lanes
+            const int row_in_tile = quarter * 32 + lane;
+            const int row = qt0 + tile * MQ + row_in_tile;
+            const int src_row = min(row, nq - 1);  // rows past the end mirror the last row (results not written;
+                                                   // for column minima they lose every tie to the real row)
+            const uint32_t one = static_cast<uint32_t>(p.desc_bytes > 0);  // opaque 1: keeps key adds on the FMA pipe
+            {
+                uint32_t w[W];
+                load_desc_global(p.q + static_cast<size_t>(q_row0 + src_row) * p.q_stride, p.desc_bytes, w);
+                uint32_t pq = 0;
 #pragma unroll
-            for (int k = 0; k < W; ++k) {
-                pq += __popc(w[k]);
-                uint32_t a[8];
+                for (int k = 0; k < W; ++k) pq += __popc(w[k]);
+                // popc(q) split over the four spare positions s = 0..3; 127 on the invalid-row markers s = 4..7
+                uint32_t spare[8];
 #pragma unroll
-                for (int s = 0; s < 8; ++s) a[s] = spread(w[k], s) * 0xFEu | 0x01010101u;  // bit 0 -> +1, bit 1 -> -1
-                tmem_st8(tmem + lane_base + TMEM_A + 8 * k, a);
-            }
-            tmem_wait_st();
-            tc_fence_before();
-            mbar_arrive(&sm.a_ready);
-        }
-        const uint32_t rowbase = pq << KEY_IDX_BITS;
-        const uint32_t colbias = rowbase + static_cast<uint32_t>(src_row);
-        uint32_t b1 = KEY_NONE, b2 = KEY_NONE;
-        for (int s = 0; s < n_stage; ++s) {
-            const int b = s & 1;
-            const int rows = stage_rows(s);
-            mbar_wait(&sm.d_full[b], (s >> 1) & 1);
-            tc_fence_after();
-            const uint32_t jstage = rowbase + static_cast<uint32_t>(p.t_index_base + tb + s * NT);
-            const uint32_t colmin_addr = COL ? smem_u32(&sm.colmin[b][warp][0]) : 0u;
-#pragma unroll 1
-            for (int c0 = 0; c0 < rows; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem + lane_base + b * NT + c0, v);
-                tmem_wait_ld();
-                if (c0 + 32 <= rows)
-                    fold_chunk<COL, TOP2, false>(v, c0, rows, jstage + c0, colbias, b1, b2, colmin_addr, lane);
-                else
-                    fold_chunk<COL, TOP2, true>(v, c0, rows, jstage + c0, colbias, b1, b2, colmin_addr, lane);
-            }
-            tc_fence_before();
-            mbar_arrive(&sm.d_empty[b]);  // accumulator stage b may be overwritten
-            if (COL) {
-                // the 4 epilogue warps merge their column minima: one global atomicMin per train row
-                asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32) : "memory");
-                for (int c = tid; c < rows; c += N_EPI_WARPS * 32) {
-                    const uint32_t m = min(min(sm.colmin[b][0][c], sm.colmin[b][1][c]),
-                                           min(sm.colmin[b][2][c], sm.colmin[b][3][c]));
-                    atomicMin(p.col_keys + t_row0 + tb + s * NT + c, m);
+                for (int s = 0; s < 4; ++s) {
+                    const uint32_t c = min(pq, 127u);
+                    spare[s] = c << 24;
+                    pq -= c;
                 }
-                // colmin[b] is rewritten in stage s+2, after the bar.sync of stage s+1
+#pragma unroll
+                for (int s = 4; s < 8; ++s) spare[s] = 127u << 24;
+#pragma unroll
+                for (int k = 0; k < W; ++k) {
+                    if (k < n_k) {
+                        uint32_t a[8];
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) {
+                            a[s] = spread(w[k], s) * 0xFEu | 0x01010101u;  // bit 0 -> +1, bit 1 -> -1
+                            if (k == ws) a[s] = (a[s] & 0x00FFFFFFu) | spare[s];
+                        }
+                        tmem_st8(tmem + lane_base + TMEM_A + tile * 128 + 8 * k, a);
+                    }
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&sm.a_ready);
             }
-        }
-        if (row < nq) {
-            const size_t orow = static_cast<size_t>(p.row_out_off ? p.row_out_off[prob] : q_row0) + row;
-            if (!TOP2 && p.compact) {
-                uint32_t *c = reinterpret_cast<uint32_t *>(p.row_keys) + orow;
-                if (gridDim.y == 1)
-                    *c = b1;
-                else
-                    atomicMin(c, b1);
-            } else {
-                uint2 *g = p.row_keys + orow;
-                if (gridDim.y == 1)
-                    *g = make_uint2(b1, b2);
-                else if (TOP2)
-                    merge_row_keys(g, b1, b2);
-                else
-                    atomicMin(&g->x, b1);  // second key stays KEY_NONE (pre-set)
+            uint32_t b1 = KEY_NONE, b2 = KEY_NONE;
+            const uint32_t scr_addr = smem_u32(sm.scratch[warp]);
+            const uint32_t rbase = static_cast<uint32_t>(qt0 + tile * MQ + quarter * 32);
+            for (int s = 0; s < n_stage; ++s) {
+                const int acc = acc_of(s, tile, n_tiles), use = acc_use(s, n_tiles);
+                const int rows = stage_rows(s);
+                mbar_wait(&sm.d_full[acc], use & 1);
+                tc_fence_after();
+                uint32_t v[2][32];
+                tmem_ld64_packed(tmem + lane_base + acc * NT, v[0]);
+                tmem_ld64_packed(tmem + lane_base + acc * NT + 64, v[1]);
+                tmem_wait_ld();
+                tc_fence_before();
+                mbar_arrive(&sm.d_empty[acc]);  // the accumulator may be overwritten
+                const uint32_t jstage = static_cast<uint32_t>(p.t_index_base + tb + s * NT);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (h == 1 && rows <= 64) break;  // warp-uniform: the second half holds no valid train row
+                    if (COL) {
+                        // scratch[row = lane][32 words], 16-byte chunk i stored at chunk i ^ (lane & 7):
+                        // conflict-free both for these row-wise STS.128 and for the column-wise LDS.32 below
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const uint32_t a = scr_addr + lane * 128 + ((i ^ (lane & 7)) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v[h][4 * i]),
+                                         "r"(v[h][4 * i + 1]), "r"(v[h][4 * i + 2]), "r"(v[h][4 * i + 3])
+                                         : "memory");
+                        }
+                    }
+                    // ---- row minima: key16 = acc + column = (d << 7) | column-in-half ----
+                    const uint32_t jh = jstage + 64u * h;
+                    if (!TOP2) {
+                        uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const uint32_t k0 = add_imad(v[h][j], one, ((2u * j + 1u) << 16) | (2u * j));
+                            const uint32_t k1 = add_imad(v[h][j + 1], one, ((2u * j + 3u) << 16) | (2u * j + 2u));
+                            m = __vimin3_u16x2(m, k0, k1);
+                        }
+                        const uint32_t k16 = min(m & 0xFFFFu, m >> 16);
+                        b1 = min(b1, ((k16 >> 7) << KEY_IDX_BITS) + jh + (k16 & 127u));
+                    } else {
+                        uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;  // per 16-bit half: best and second best
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const uint32_t k = add_imad(v[h][j], one, ((2u * j + 1u) << 16) | (2u * j));
+                            m2 = __vminu2(m2, __vmaxu2(m1, k));
+                            m1 = __vminu2(m1, k);
+                        }
+                        const uint32_t c[4] = {m1 & 0xFFFFu, m1 >> 16, m2 & 0xFFFFu, m2 >> 16};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)  // empty slots and invalid train rows (d = 508) are no candidates
+                            top2_insert(c[i] >= (505u << 7) ? KEY_NONE : ((c[i] >> 7) << KEY_IDX_BITS) + jh + (c[i] & 127u),
+                                        b1, b2);
+                    }
+                    if (COL) {
+                        // ---- column minima over this warp's 32 query rows: lane = train column pair ----
+                        __syncwarp();
+                        uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int r = 0; r < 32; r += 2) {
+                            uint32_t x0, x1;
+                            const uint32_t a0 = scr_addr + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2));
+                            const uint32_t a1 =
+                                scr_addr + (r + 1) * 128 + ((((lane >> 2) ^ ((r + 1) & 7)) << 4) | ((lane & 3) << 2));
+                            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x0) : "r"(a0) : "memory");
+                            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x1) : "r"(a1) : "memory");
+                            // key16 = (d << 5) | row: acc = d << 7, so acc >> 2 per half; both halves shift
+                            // together because bits 0-1 of every half are zero
+                            const uint32_t k0 = add_imad(x0 >> 2, one, (static_cast<uint32_t>(r) << 16) | r);
+                            const uint32_t k1 = add_imad(x1 >> 2, one, (static_cast<uint32_t>(r + 1) << 16) | (r + 1));
+                            m = __vimin3_u16x2(m, k0, k1);
+                        }
+                        __syncwarp();  // the scratch is rewritten by the next half / stage
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const uint32_t k16 = hh ? (m >> 16) : (m & 0xFFFFu);
+                            const int c = 64 * h + 2 * lane + hh;
+                            if (c < rows)
+                                atomicMin(&sm.colmin[tile][s & 1][c], ((k16 >> 5) << KEY_IDX_BITS) + rbase + (k16 & 31u));
+                        }
+                    }
+                }
+                if (COL) {
+                    // the 4 warps of this query tile merge: one global atomicMin per train row, tile and stage
+                    if (tile == 0)
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                    else
+                        asm volatile("bar.sync 2, 128;" ::: "memory");
+                    if (row_in_tile < rows) {
+                        atomicMin(p.col_keys + t_row0 + tb + s * NT + row_in_tile, sm.colmin[tile][s & 1][row_in_tile]);
+                        sm.colmin[tile][s & 1][row_in_tile] = KEY_NONE;  // reused in stage s + 2, after the barrier of s + 1
+                    }
+                }
+            }
+            if (row < nq) {
+                const size_t orow = static_cast<size_t>(p.row_out_off ? p.row_out_off[prob] : q_row0) + row;
+                if (!TOP2 && p.compact) {
+                    uint32_t *c = reinterpret_cast<uint32_t *>(p.row_keys) + orow;
+                    if (gridDim.y == 1)
+                        *c = b1;
+                    else
+                        atomicMin(c, b1);
+                } else {
+                    uint2 *g = p.row_keys + orow;
+                    if (gridDim.y == 1)
+                        *g = make_uint2(b1, b2);
+                    else if (TOP2)
+                        merge_row_keys(g, b1, b2);
+                    else
+                        atomicMin(&g->x, b1);  // second key stays KEY_NONE (pre-set)
+                }
             }
         }
     } else if (warp < MMA_WARP) {
         // ============================== expander warps ==============================
-        const int e = warp - N_EPI_WARPS;
-        const int r = 32 * e + lane;  // this lane's train row within every stage
-        const bool aligned = (p.t_stride & 3) == 0;
+        const int r = tid - N_EPI_WARPS * 32;   // this thread's train row within every stage
+        uint32_t mul[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) mul[s] = (1u << (7 - s)) * static_cast<uint32_t>(p.desc_bytes > 0);
         for (int s = 0; s < n_stage; ++s) {
-            const int b = s & 1;
+            const int b = s % NB;
+            const uint32_t ph = (s / NB) & 1;
             const int rows = stage_rows(s), trows = stage_tma_rows(s);
-            if (trows > 0) mbar_wait(&sm.raw_full[b], (s >> 1) & 1);
-            mbar_wait(&sm.b_empty[b], ((s >> 1) & 1) ^ 1);
-            if (r < rows) {
-                uint8_t *dst = sm.b[b] + r * 16;
-                if (r < trows && aligned) {
-                    // 4-byte aligned rows: lane l starts at word l (mod 16) so that both the LDS.32 of the 32
-                    // rows (stride a multiple of 4 words) and the STS.128 spread over all banks
-                    const uint32_t *row32 = reinterpret_cast<const uint32_t *>(sm.raw[b] + r * p.t_stride);
-#pragma unroll 4
-                    for (int i = 0; i < W; ++i) {
-                        const int k = (i + lane) & (W - 1);
-                        if (k < n_k) {
-                            const uint32_t w = row32[k] & word_mask(p.desc_bytes, k);
-                            uint8_t *d = dst + 2 * k * LBO;
-                            *reinterpret_cast<uint4 *>(d) = make_uint4(spread(w, 0), spread(w, 1), spread(w, 2), spread(w, 3));
-                            *reinterpret_cast<uint4 *>(d + LBO) =
-                                make_uint4(spread(w, 4), spread(w, 5), spread(w, 6), spread(w, 7));
-                        }
-                    }
-                } else {
-                    uint32_t w[W];
-                    if (r < trows) {  // unaligned rows (61-byte stride): 17 LDS.32 + funnel shifts
-                        const int o = r * p.t_stride;
-                        const uint32_t *raw32 = reinterpret_cast<const uint32_t *>(sm.raw[b]) + (o >> 2);
-                        const int sh = (o & 3) * 8;
-                        uint32_t lo = raw32[0];
+            if (trows > 0) mbar_wait(&sm.raw_full[b], ph);
+            mbar_wait(&sm.b_empty[b], ph ^ 1);
+            uint32_t w[W];
+            if (r >= rows) {
 #pragma unroll
-                        for (int k = 0; k < W; ++k) {
-                            const uint32_t hi = raw32[k + 1];
-                            w[k] = __funnelshift_r(lo, hi, sh) & word_mask(p.desc_bytes, k);
-                            lo = hi;
-                        }
-                    } else {  // rows the bulk copy could not take (misaligned source / tail): read global memory
-                        load_desc_global(stage_src(s) + static_cast<size_t>(r) * p.t_stride, p.desc_bytes, w);
-                    }
+                for (int k = 0; k < W; ++k) w[k] = 0;
+            } else if (r < trows) {
+                const int o = r * p.t_stride;  // any alignment: LDS.32 + funnel shift
+                const uint32_t *raw32 = reinterpret_cast<const uint32_t *>(sm.raw[b]) + (o >> 2);
+                const int sh = (o & 3) * 8;
+                uint32_t lo = raw32[0];
 #pragma unroll
-                    for (int k = 0; k < W; ++k) {
-                        if (k < n_k) {
-                            uint8_t *d = dst + 2 * k * LBO;
-                            *reinterpret_cast<uint4 *>(d) =
-                                make_uint4(spread(w[k], 0), spread(w[k], 1), spread(w[k], 2), spread(w[k], 3));
-                            *reinterpret_cast<uint4 *>(d + LBO) =
-                                make_uint4(spread(w[k], 4), spread(w[k], 5), spread(w[k], 6), spread(w[k], 7));
-                        }
-                    }
+                for (int k = 0; k < W; ++k) {
+                    // words past the descriptor hold stale bytes of the staging buffer (never past its end:
+                    // RAW_STAGE has 16 bytes of slack); word_mask clears them
+                    const uint32_t hi = raw32[k + 1];
+                    w[k] = __funnelshift_r(lo, hi, sh) & word_mask(p.desc_bytes, k);
+                    lo = hi;
+                }
+            } else {  // rows the bulk copy could not take (misaligned source / tail): read global memory
+                load_desc_global(stage_src(s) + static_cast<size_t>(r) * p.t_stride, p.desc_bytes, w);
+            }
+            uint8_t *dst = sm.b[b] + r * 16;
+            // valid rows carry 0x80 on the four popc positions, invalid rows on the four marker positions
+            const uint32_t spare_lo = (r < rows) ? 0x80000000u : 0u, spare_hi = (r < rows) ? 0u : 0x80000000u;
+#pragma unroll
+            for (int k = 0; k < W; ++k) {
+                if (k < n_k) {
+                    const uint32_t slo = (k == ws) ? spare_lo : 0u, shi = (k == ws) ? spare_hi : 0u;
+                    uint8_t *d = dst + 2 * k * LBO;
+                    *reinterpret_cast<uint4 *>(d) = make_uint4(spread80(w[k], mul[0]) | slo, spread80(w[k], mul[1]) | slo,
+                                                               spread80(w[k], mul[2]) | slo, spread80(w[k], mul[3]) | slo);
+                    *reinterpret_cast<uint4 *>(d + LBO) =
+                        make_uint4(spread80(w[k], mul[4]) | shi, spread80(w[k], mul[5]) | shi,
+                                   spread80(w[k], mul[6]) | shi, spread80(w[k], mul[7]) | shi);
                 }
             }
             fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(&sm.b_full[b]);
         }
-    } else if (lane == 0) {
-        // ============================== TMA + MMA issue (one thread) ==============================
+    } else {
+        // ============================== TMA + MMA issue (whole warp, one elected lane issues) ===========
+        const bool leader = elect_one();
         auto issue_tma = [&](int s) {
             const int trows = stage_tma_rows(s);
             if (trows > 0) {
                 const uint32_t bytes = static_cast<uint32_t>(trows) * p.t_stride;
-                mbar_arrive_expect_tx(&sm.raw_full[s & 1], bytes);
-                tma_load_1d(sm.raw[s & 1], stage_src(s), bytes, &sm.raw_full[s & 1]);
+                mbar_arrive_expect_tx(&sm.raw_full[s % NB], bytes);
+                tma_load_1d(sm.raw[s % NB], stage_src(s), bytes, &sm.raw_full[s % NB]);
             }
         };
-        issue_tma(0);
-        if (n_stage > 1) issue_tma(1);
+        if (leader)
+            for (int s = 0; s < min(NB, n_stage); ++s) issue_tma(s);
         mbar_wait(&sm.a_ready, 0);
         tc_fence_after();
+        // K-step k of a B stage: descriptor start address advances by 2 chunks = 2 * LBO bytes
+        const uint64_t desc0 = umma_desc(smem_u32(sm.b[0]), LBO, 128);
         for (int s = 0; s < n_stage; ++s) {
-            const int b = s & 1;
-            const uint32_t ph = (s >> 1) & 1;
-            mbar_wait(&sm.b_full[b], ph);
-            if (s + 2 < n_stage) issue_tma(s + 2);  // every expander has finished reading raw[b]
-            mbar_wait(&sm.d_empty[b], ph ^ 1);
-            tc_fence_after();
-            const uint32_t b_addr = smem_u32(sm.b[b]);
-            for (int k = 0; k < n_k; ++k)
-                umma_i8_ts(tmem + b * NT, tmem + TMEM_A + 8 * k, umma_desc(b_addr + 2 * k * LBO, LBO, 128), kIdesc,
-                           k > 0);
-            umma_commit(&sm.b_empty[b]);
-            umma_commit(&sm.d_full[b]);
+            const int b = s % NB;
+            mbar_wait(&sm.b_full[b], (s / NB) & 1);
+            if (leader && s + NB < n_stage) issue_tma(s + NB);  // every expander has finished reading raw[b]
+            const uint64_t desc_b = desc0 + static_cast<uint64_t>(b * (B_STAGE >> 4));
+            for (int t = 0; t < n_tiles; ++t) {
+                const int acc = acc_of(s, t, n_tiles), use = acc_use(s, n_tiles);
+                mbar_wait(&sm.d_empty[acc], (use & 1) ^ 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t d_addr = tmem + acc * NT, a_addr = tmem + TMEM_A + t * 128;
+                    if (n_k == 16) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k)
+                            umma_i8_ts(d_addr, a_addr + 8 * k, desc_b + static_cast<uint64_t>(k * (2 * LBO >> 4)), kIdesc, k > 0);
+                    } else {
+                        for (int k = 0; k < n_k; ++k)
+                            umma_i8_ts(d_addr, a_addr + 8 * k, desc_b + static_cast<uint64_t>(k * (2 * LBO >> 4)), kIdesc, k > 0);
+                    }
+                    if (t == n_tiles - 1) umma_commit(&sm.b_empty[b]);
+                    umma_commit(&sm.d_full[acc]);
+                }
+                __syncwarp();
+            }
         }
     }
 
@@ -377,23 +528,25 @@ int launch_mma(const HammingParams &p, dim3 grid, cudaStream_t stream)
 
 }  // namespace
 
+bool hamming_mma_supports(int desc_bytes) { return desc_bytes >= 1 && desc_bytes <= 63; }
+
 int run_hamming_mma(HammingParams p, int n_problems, int max_nq, int max_nt, bool top2, cudaStream_t stream)
 {
-    // One CTA per SM (192 KB of shared memory, all 512 TMEM columns).  When the query tiles alone do not
-    // fill the machine the train set is cut into slices (grid.y); their results merge exactly through
-    // atomicMin / the CAS pair merge, as in the INT kernel.
+    // One CTA per SM (all 512 TMEM columns).  When the query tiles alone do not fill the machine the train
+    // set is cut into slices (grid.y); their results merge exactly through atomicMin / the CAS pair merge,
+    // as in the INT kernel.
     const int sms = sm_count();
     const int stages_total = (max_nt + NT - 1) / NT;
-    const long long ctas = static_cast<long long>((max_nq + MQ - 1) / MQ) * n_problems;
+    const long long ctas = static_cast<long long>((max_nq + CQ - 1) / CQ) * n_problems;
     int slices = 1;
     if (ctas < 2LL * sms) {
         const int want = static_cast<int>((2LL * sms + ctas - 1) / ctas);
-        slices = max(1, min(want, stages_total / 2));
+        slices = max(1, min(want, stages_total / 4));
     }
     const int stages_per_slice = (stages_total + slices - 1) / slices;
     p.t_slice = stages_per_slice * NT;
     const int n_slices = (stages_total + stages_per_slice - 1) / stages_per_slice;
-    const dim3 grid((max_nq + MQ - 1) / MQ, n_slices, n_problems);
+    const dim3 grid((max_nq + CQ - 1) / CQ, n_slices, n_problems);
     if (grid.y > 65535u || grid.z > 65535u) return SLAMFE_ERANGE;
     if (p.col_keys) return top2 ? launch_mma<true, true>(p, grid, stream) : launch_mma<true, false>(p, grid, stream);
     return top2 ? launch_mma<false, true>(p, grid, stream) : launch_mma<false, false>(p, grid, stream);

@@ -74,5 +74,7 @@ __device__ __forceinline__ void merge_row_keys(uint2 *g, uint32_t k1, uint32_t k
 // Entry of the tensor-core kernel (hamming_mma.cu); same contract as run_hamming's launch: the key
 // tables were pre-set to KEY_NONE by the caller.
 int run_hamming_mma(HammingParams p, int n_problems, int max_nq, int max_nt, bool top2, cudaStream_t stream);
+// desc_bytes the tensor-core kernel handles (it needs a spare descriptor byte inside the 64-byte K range)
+bool hamming_mma_supports(int desc_bytes);
 
 }  // namespace slamfe

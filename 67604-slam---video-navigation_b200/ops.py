@@ -274,6 +274,32 @@ def ransac_score(T, pts, l_pix, r_pix, K, M1, M2, hyp_valid=None, pt_off=None, n
     return counts, best, mask
 
 
+def track_ids(fwd_keys, inlier_fwd, l_off, n_links, n_frames, out=None):
+    """Track id of every link row of a sequence (slamfe_track_ids; TrackingDB.add_frame's bookkeeping,
+    tracking_database.py:273-337).  fwd_keys (L, 2) / inlier_fwd (L,) as FrontEnd.track leaves them.
+    Returns (track_id (L,) int32 with -1 = NO_ID, n_tracks (1,) int32, head_base (n_frames + 1,) int32)."""
+    torch = _torch()
+    dev = fwd_keys.device
+    L = fwd_keys.shape[0]
+    out = out if out is not None else {}
+    i32 = dict(dtype=torch.int32, device=dev)
+
+    def buf(name, shape):
+        t = out.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = out[name] = torch.empty(shape, **i32)
+        return t
+
+    pred, rank, track_id = buf("trk_pred", (L,)), buf("trk_rank", (L,)), buf("track_id", (L,))
+    head_cnt, head_base, n_tracks = buf("trk_head_cnt", (max(n_frames, 1),)), buf("head_base", (n_frames + 1,)), \
+        buf("n_tracks", (1,))
+    with torch.cuda.device(dev):
+        check(load_library().slamfe_track_ids(ptr(fwd_keys), ptr(inlier_fwd), ptr(l_off), ptr(n_links), n_frames, L,
+                                              ptr(pred), ptr(rank), ptr(head_cnt), ptr(head_base), ptr(track_id),
+                                              ptr(n_tracks), stream_handle()), "slamfe_track_ids")
+    return track_id, n_tracks, head_base
+
+
 def pnp_refit(T, best, pts, l_pix, mask, K, pt_off=None, pt_cnt=None, n_frames=1, max_iter=20, tol=1e-12, out=None):
     """Refit of the pose on the consensus set (ransac.py:185-193) for n_frames problems in one launch
     (slamfe_pnp_refit): T / best / mask as returned by ransac_hypotheses / ransac_score.

@@ -469,7 +469,13 @@ def main():
             cpu_frames_pass(host_frames(seq_t, 0, min(3, FF)), utils.P, utils.Q)
             host, _, _ = frontend.results_to_host(out)
             trk = {k: out[k].cpu().numpy() for k in ("good_j", "n_good", "best", "best_mask", "pts", "lpix", "rpix",
-                                                     "n_hyp", "n_hyp_full")}
+                                                     "n_hyp", "n_hyp_full", "pose", "pose_status")}
+            pose_gpu, pose_cpu = [], []
+
+            def pose_error(T, Rg, tg):
+                dR = T[:, :3] @ Rg.T
+                return float(np.linalg.norm(dR - dR.T) / (2 * np.sqrt(2))), float(np.linalg.norm(T[:, 3] - tg))
+
             ok, worst, mutual_ok, dt, n_pairs_cpu, frames_checked = True, 0.0, True, 0.0, 0, 0
             ratios, rec_gpu, rec_cpu, gt_sizes = [], [], [], []
             for s0 in starts:
@@ -518,6 +524,15 @@ def main():
                             rec_gpu.append(float((gmask & gt).sum()) / gt.sum())
                             rec_cpu.append(float((cmask & gt).sum()) / gt.sum())
                             gt_sizes.append(int(gt.sum()))
+                            # pose: device refit on the device consensus vs the reference's recipe (cv2 EPnP
+                            # on the CPU arm's consensus, ransac.py:185-193), both against the true motion
+                            if trk["pose_status"][f] > 0:
+                                pose_gpu.append(pose_error(trk["pose"][f], Rg, tg))
+                            if cmask.sum() >= 4:
+                                okc, rv, tv = cv2.solvePnP(trk["pts"][lo:lo + ng][cmask], trk["lpix"][lo:lo + ng][cmask],
+                                                           utils.K, np.zeros((5, 1)), flags=cv2.SOLVEPNP_EPNP)
+                                if okc:
+                                    pose_cpu.append(pose_error(utils.rodriguez_to_mat(rv, tv), Rg, tg))
             cpu_baseline = {"value": n_pairs_cpu / dt, "unit": UNIT, "cores": threads, "kind": "port",
                             "sample": f"{len(starts)} windows of {wlen} consecutive frames spread over the sequence "
                                       f"(starts {starts}; {dt:.1f} s): cv2 {cv2.__version__} BFMatcher crossCheck + "
@@ -536,6 +551,12 @@ def main():
                           "gpu_p3p_median_recall": float(np.median(rg)) if len(rg) else None,
                           "cpu_epnp_median_recall": float(np.median(rc)) if len(rc) else None,
                           "gpu_at_least_cpu": bool(len(rg) == 0 or (rg >= 0.9).mean() >= (rc >= 0.9).mean()),
+                          "pose_error_median_rad_m": {
+                              "gpu_refit": [float(x) for x in np.median(np.array(pose_gpu), axis=0)] if pose_gpu else None,
+                              "cpu_epnp_refit": [float(x) for x in np.median(np.array(pose_cpu), axis=0)] if pose_cpu else None},
+                          "frac_pairs_pose_within_1cm_1mrad": {
+                              "gpu_refit": float(np.mean([a < 1e-3 and b < 0.01 for a, b in pose_gpu])) if pose_gpu else None,
+                              "cpu_epnp_refit": float(np.mean([a < 1e-3 and b < 0.01 for a, b in pose_cpu])) if pose_cpu else None},
                           "note": "ground truth = correspondences agreeing with the sequence's true motion under "
                                   "transformation_agreement; both arms run the reference's own iteration count "
                                   "(calc_ransac_iteration, ~57 here) from different random samples and solvers "

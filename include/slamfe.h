@@ -294,6 +294,22 @@ int slamfe_ransac_hypotheses(const double *pts, const double *l_pix, const int32
                              slamfe_stream_t stream);
 
 /*
+ * Track ids of a whole sequence — the bookkeeping of TrackingDB.add_frame
+ * (backend/database/tracking_database.py:273-337) over the tables of the tracking stages: link k of frame f
+ * (row l_off[f] + k) continues into link j = index(fwd_keys[row][0]) of frame f + 1 when inlier_fwd[row] is set
+ * (in_prev_cur, database.py:84-85; mutual matches, hence one-to-one).  A link with an inlier successor and no
+ * inlier predecessor starts a track; ids are issued as issue_trackId does (:196-198): frame pairs in order,
+ * ascending previous-feature index inside a pair.
+ *   track_id (rows_total,) int32 out: id of the track the link belongs to, -1 (NO_ID) for links on no track
+ *            and for padding rows;  n_tracks (1,) int32 out;  head_base (n_frames + 1,) int32 out: number of
+ *            tracks that start before frame f
+ *   pred, rank (rows_total,), head_cnt (n_frames,): int32 scratch
+ */
+int slamfe_track_ids(const uint32_t *fwd_keys, const uint8_t *inlier_fwd, const int32_t *l_off, const int32_t *n_links,
+                     int n_frames, int64_t rows_total, int32_t *pred, int32_t *rank, int32_t *head_cnt,
+                     int32_t *head_base, int32_t *track_id, int32_t *n_tracks, slamfe_stream_t stream);
+
+/*
  * PnP refit on the consensus set: the final solve of ransac_pnp (final_project/algorithms/ransac.py:185-193,
  * cv2.solvePnP(points_3d[best_idx], l_pix[best_idx], K, EPNP)) for every frame pair / loop-closure candidate
  * of a batch in one launch, so the pose needs no host solve.  Levenberg-Marquardt on the left-image

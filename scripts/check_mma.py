@@ -34,7 +34,7 @@ def compare(name, fn):
 rng = np.random.default_rng(0)
 dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 allok = True
-for nq, nt in [(128, 192), (1, 1), (100, 50), (130, 400), (513, 2049), (3000, 3000), (4999, 1), (1, 5000)]:
+for nq, nt in [(128, 192), (1, 1), (100, 50), (130, 400), (256, 64), (257, 65), (129, 63), (300, 128), (513, 2049), (3000, 3000), (4999, 1), (1, 5000)]:
     q = synth.descriptors(rng, nq)
     t, _ = synth.paired_descriptors(rng, q, n_out=nt, dup_frac=0.05)
     qd, td = dev(q), dev(t)
@@ -78,7 +78,7 @@ def timeit(fn, reps=5):
 n = 20000
 q = dev(synth.descriptors(rng, n)); t = dev(synth.descriptors(rng, n))
 for kind in ("int", "mma"):
-    for cols, bo in ((False, True), (True, True), (False, False)):
+    for cols, bo in ((False, True), (True, True), (False, False), (True, False)):
         ops.set_matcher_kernel(kind)
         ms = timeit(lambda: ops.hamming_top2(q, t, want_cols=cols, best_only=bo))
         print(f"dense 20k {kind} cols={cols} best_only={bo}: {ms:.3f} ms, {n*n/ms/1e6:.1f} G pairs/s", flush=True)

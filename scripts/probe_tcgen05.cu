@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(128) mma_check(const uint8_t *A, const uint8_t
 // rate: one CTA per SM, thread 0 issues `iters` MMAs back to back
 // ------------------------------------------------------------------------------------------------
 template <int KIND>
-__global__ void __launch_bounds__(128) mma_rate(int N, uint32_t idesc, int ts, int iters, long long *cycles)
+__global__ void __launch_bounds__(128) mma_rate(int N, uint32_t idesc, int ts, int iters, long long *cycles, int nacc = 1)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -223,10 +223,11 @@ __global__ void __launch_bounds__(128) mma_rate(int N, uint32_t idesc, int ts, i
             const int k = it & 15;
             const uint64_t da = make_desc(sA + k * 2 * lboA, lboA, sbo);
             const uint64_t db = make_desc(sB + k * 2 * lboB, lboB, sbo);
+            const uint32_t dd = tb + ((it / 1) % nacc) * N;   // nacc independent accumulators, round robin
             if (ts)
-                mma_ts<KIND>(tb, tb + 256 + k * 8, db, idesc, 1);
+                mma_ts<KIND>(dd, tb + 256 + k * 8, db, idesc, 1);
             else
-                mma_ss<KIND>(tb, da, db, idesc, 1);
+                mma_ss<KIND>(dd, da, db, idesc, 1);
         }
         umma_commit(&bar);
         mbar_wait(&bar, 0);
@@ -400,7 +401,7 @@ static int run_check(int kind, int ts, int swap, int K, int N, int f8pow2)
     return bad != 0;
 }
 
-static void run_rate(int kind, int ts, int N, int sms)
+static void run_rate(int kind, int ts, int N, int sms, int nacc = 1)
 {
     const int iters = 8192;
     long long *dc;
@@ -413,10 +414,10 @@ static void run_rate(int kind, int ts, int N, int sms)
         CK(cudaEventRecord(e0));
         if (kind == 0) {
             CK(cudaFuncSetAttribute(mma_rate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            mma_rate<0><<<sms, 128, smem>>>(N, idesc, ts, iters, dc);
+            mma_rate<0><<<sms, 128, smem>>>(N, idesc, ts, iters, dc, nacc);
         } else {
             CK(cudaFuncSetAttribute(mma_rate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            mma_rate<1><<<sms, 128, smem>>>(N, idesc, ts, iters, dc);
+            mma_rate<1><<<sms, 128, smem>>>(N, idesc, ts, iters, dc, nacc);
         }
         CK(cudaEventRecord(e1));
         CK(cudaDeviceSynchronize());
@@ -428,8 +429,8 @@ static void run_rate(int kind, int ts, int N, int sms)
     long long mx = 0;
     for (auto v : c) mx = v > mx ? v : mx;
     const double macs = (double)sms * iters * 128.0 * N * 32.0;
-    printf("rate kind=%s ts=%d N=%d : %.1f cycles/MMA (max CTA), %.3f ms, %.2f P MAC/s, %.2f T desc-pairs/s (K=512)\n",
-           kind ? "f8f6f4" : "i8", ts, N, (double)mx / iters, ms, macs / ms / 1e12, macs / 512.0 / ms / 1e9);
+    printf("rate nacc=%d kind=%s ts=%d N=%d : %.1f cycles/MMA (max CTA), %.3f ms, %.2f P MAC/s, %.2f T desc-pairs/s (K=512)\n",
+           nacc, kind ? "f8f6f4" : "i8", ts, N, (double)mx / iters, ms, macs / ms / 1e12, macs / 512.0 / ms / 1e9);
     cudaFree(dc);
 }
 
@@ -449,6 +450,13 @@ int main(int argc, char **argv)
         for (int kind = 0; kind < 2; ++kind)
             for (int ts = 0; ts < 2; ++ts)
                 for (int N = 128; N <= 256; N += 128) run_rate(kind, ts, N, sms);
+        return 0;
+    }
+    if (!strcmp(mode, "rate2")) {   // i8, TS: N x number of independent accumulators
+        for (int N = 32; N <= 256; N *= 2)
+            for (int nacc = 1; nacc <= 256 / N && nacc <= 4; nacc *= 2) run_rate(0, 1, N, sms, nacc);
+        run_rate(0, 1, 192, sms, 1);
+        run_rate(0, 0, 64, sms, 1); run_rate(0, 0, 64, sms, 4);
         return 0;
     }
     if (!strcmp(mode, "ldtm")) {

@@ -184,6 +184,7 @@ class FrontEnd:
         self._in = None
         self._in_key = None
         self._pinned_out = None
+        self._pinned_ids = None
         self._streams = None
         # kernels launched by one run(): 2 matcher launches, stereo epilogue, triangulation
         # (cudaMemsetAsync initialisation of the key tables is not counted)
@@ -288,7 +289,7 @@ class FrontEnd:
                       n_frames=n_pairs, out={"T_refit": t["pose"], "refit_status": t["pose_status"],
                                              "refit_rms": t["pose_rms"]})
 
-    def track(self, ds: DeviceSequence, h_max=256, seed=1, full_ransac=False):
+    def track(self, ds: DeviceSequence, h_max=256, seed=1, full_ransac=False, track_ids=False):
         """run(ds) followed by the frame-to-frame tracking of database.py:54-85 for every consecutive
         pair, without leaving the device: mutual forward/backward check + link gather + fp64
         triangulation of the previous links (slamfe_track_gather), RANSAC-PnP hypothesis generation
@@ -302,7 +303,9 @@ class FrontEnd:
         h_max caps the hypotheses per pair of the batched launch; n_hyp_full holds the reference's
         uncapped count (calc_ransac_iteration, ransac.py:59-67).  full_ransac=True synchronises and re-runs
         every pair with n_hyp_full > h_max at its full count (rescore_truncated), so the result never
-        depends on h_max; with False the caller can inspect n_hyp_full itself."""
+        depends on h_max; with False the caller can inspect n_hyp_full itself.  track_ids=True adds track_id
+        (L,) / n_tracks (1,) / head_base (F + 1,): the track every link belongs to, numbered as
+        TrackingDB.add_frame numbers them (slamfe_track_ids)."""
         o = self.run(ds)
         F = ds.n_frames
         L = ds.desc_l.shape[0]
@@ -314,11 +317,21 @@ class FrontEnd:
             t["best"][:, 1].zero_()
             t["inlier_fwd"].zero_(); t["pose"].zero_(); t["pose_status"].zero_()
             self.last_truncated = 0
+            if track_ids:   # nothing continues into a next frame: no tracks
+                torch = _cabi.require_cuda()
+                dev = ds.desc_l.device
+                out["track_id"] = torch.full((L,), -1, dtype=torch.int32, device=dev)
+                out["n_tracks"] = torch.zeros((1,), dtype=torch.int32, device=dev)
+                out["head_base"] = torch.zeros((F + 1,), dtype=torch.int32, device=dev)
             return out
         self._track_stages(o, t, ds.l_off, ds.r_off, ds.pts_l, ds.pts_r, F - 1, min(ds.max_nl, ds.max_nr), h_max, seed)
         self.last_launches += 5
         if full_ransac:
             self.rescore_truncated(ds.l_off.cpu().numpy(), F - 1, h_max, seed)
+        if track_ids:   # TrackingDB.add_frame's bookkeeping for the whole sequence (tracking_database.py:273-337)
+            ops.track_ids(o["fwd_keys"], t["inlier_fwd"], ds.l_off, o["n_links"], F, out=t)
+            out.update({k: t[k] for k in ("track_id", "n_tracks", "head_base")})
+            self.last_launches += 4
         return out
 
     def rescore_truncated(self, l_off, n_pairs, h_max, seed=1, host_tables=None, h_cap=1 << 16):
@@ -387,7 +400,7 @@ class FrontEnd:
         return self._in
 
     def run_host(self, seq: PackedSequence, chunk_frames=576, device="cuda", keys=RESULT_KEYS, track=False,
-                 h_max=256, seed=1, full_ransac=True):
+                 h_max=256, seed=1, full_ransac=True, track_ids=False):
         """Pinned host inputs -> pinned host result tables, copies overlapped with the kernels.
 
         Returns (dict of numpy views of the pinned result tables, h2d_bytes, d2h_bytes).  The call
@@ -395,8 +408,12 @@ class FrontEnd:
         of track() per chunk and the tables TRACK_KEYS (inlier flags per forward match, best
         hypothesis / inlier count, mutual-match count and capped / uncapped RANSAC iteration count per
         pair).  full_ransac=True (default) re-runs the pairs h_max truncated at their full count before
-        returning (rescore_truncated; self.last_truncated = how many)."""
+        returning (rescore_truncated; self.last_truncated = how many).  track_ids=True (needs track) adds the
+        tables track_id (L,) int32 and n_tracks (1,): computed once over the whole sequence after the last
+        chunk (tracks cross chunk boundaries), after any re-run of truncated pairs."""
         torch = _cabi.require_cuda()
+        if track_ids and not track:
+            raise ValueError("track_ids needs track=True")
         if seq.tensors is None:
             raise ValueError("run_host needs a pinned PackedSequence (pack_sequence(..., pin=True))")
         dev = torch.device(device)
@@ -544,6 +561,19 @@ class FrontEnd:
                 self.rescore_truncated(l_off, F - 1, h_max, seed, host_tables=tables)
             else:
                 self.last_truncated = int((tables["n_hyp_full"][:F - 1] > h_max).sum())
+        if track_ids:
+            l_off_dev = small_dev.new_tensor(seq.l_off) if F else None
+            tid, n_tr, _ = ops.track_ids(o["fwd_keys"], trk["inlier_fwd"], l_off_dev, o["n_links"], F, out=trk)
+            self.last_launches += 4
+            pin = self._pinned_ids
+            if pin is None or pin[0].shape != tid.shape:
+                pin = self._pinned_ids = (torch.empty(tid.shape, dtype=tid.dtype, pin_memory=True),
+                                          torch.empty((1,), dtype=torch.int32, pin_memory=True))
+            pin[0].copy_(tid, non_blocking=True)
+            pin[1].copy_(n_tr, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            tables["track_id"], tables["n_tracks"] = pin[0].numpy(), pin[1].numpy()
+            d2h += tid.numel() * 4 + 4
         return tables, int(h2d), int(d2h)
 
 

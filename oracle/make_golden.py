@@ -272,6 +272,117 @@ def golden_loop_candidates(db):
     np.savez_compressed(os.path.join(OUT, "loop_candidates.npz"), **out)
 
 
+def _texture(rng, h=376, w=1241):
+    """A corner-rich synthetic image (random rectangles and discs at three scales, blurred)."""
+    img = np.zeros((h, w), np.float32)
+    for s, n, a in ((3, 4000, 60), (7, 1500, 80), (15, 400, 90)):
+        for x, y in zip(rng.integers(0, w, n), rng.integers(0, h, n)):
+            c = float(rng.uniform(-a, a))
+            if rng.random() < 0.5:
+                cv2.rectangle(img, (int(x), int(y)), (int(x + rng.integers(2, s * 3)), int(y + rng.integers(2, s * 3))), c, -1)
+            else:
+                cv2.circle(img, (int(x), int(y)), int(rng.integers(1, s * 2)), c, -1)
+    img = cv2.GaussianBlur(img, (0, 0), 1.0)
+    img -= img.min()
+    return (img / img.max() * 255).astype(np.uint8)
+
+
+def golden_akaze(ref):
+    """REAL cv2.AKAZE output (correlated bits, cv2-owned (N, 61) arrays, > 2k keypoints) through the
+    reference's own extract_kps_descs_matches (matching.py:38-45: detectAndCompute x2 + MATCHER_LEFT_RIGHT
+    crossCheck match) and extract_inliers_outliers (:48-69), on a synthetic textured rectified stereo pair
+    (smooth disparity field) and a second left view (small zoom + shift) for MATCHER.match / knnMatch."""
+    rng = np.random.default_rng(7)
+    left = _texture(rng)
+    h, w = left.shape
+    xs, ys = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32))
+    disp = 6.0 + 40.0 * ys / h + 8.0 * np.sin(xs / 180.0)
+    right = cv2.remap(left, xs + disp, ys, cv2.INTER_LINEAR)
+    left2 = cv2.warpAffine(left, np.float32([[1.03, 0.004, -12.0], [-0.004, 1.03, -4.0]]), (w, h))
+    kp0, kp1, d0, d1, ms = ref.matching.extract_kps_descs_matches(left, right)
+    assert d0.shape[1] == 61 and d0.dtype == np.uint8 and len(kp0) > 2000 and len(kp1) > 2000
+    inl, outl = ref.matching.extract_inliers_outliers(kp0, kp1, ms)
+    cq, ct, cd, _ = dm_arrays(ms)
+    p0 = np.array([k.pt for k in kp0], np.float32)
+    p1 = np.array([k.pt for k in kp1], np.float32)
+    _, d2 = ref.matching.FEATURE.detectAndCompute(left2, None)
+    d2 = d2[:2500]
+    mq, mt, md, _ = dm_arrays(ref.matching.MATCHER.match(d0, d2))
+    bq, bt, bd, _ = dm_arrays(ref.matching.MATCHER.match(d2, d0))
+    knn = ref.matching.MATCHER.knnMatch(d0, d2, k=2)
+    k_idx = np.array([[m.trainIdx for m in pr] for pr in knn], np.int32)
+    k_dist = np.array([[int(m.distance) for m in pr] for pr in knn], np.int32)
+    # the oracle restatement must agree with cv2 on real descriptors too
+    oq, ot, od = ora.match_crosscheck(d0, d1)
+    assert np.array_equal(oq, cq) and np.array_equal(ot, ct) and np.array_equal(od, cd.astype(np.int64))
+    oi, odist = ora.match(d0, d2)
+    assert np.array_equal(oi, mt) and np.array_equal(odist, md.astype(np.int64))
+    ki, kd = ora.knn2(d0, d2)
+    assert np.array_equal(ki, k_idx) and np.array_equal(kd, k_dist)
+    o_in, o_out = ora.extract_inliers_outliers(p0, p1, cq, ct)
+    assert np.array_equal(o_in, inl) and np.array_equal(o_out, outl)
+    ties = int((k_dist[:, 0] == k_dist[:, 1]).sum())
+    np.savez_compressed(os.path.join(OUT, "akaze_real.npz"), desc_l=d0, desc_r=d1, desc_l2=d2, pts_l=p0, pts_r=p1,
+                        cross_q=cq, cross_t=ct, cross_d=cd, inliers=inl, outliers=outl, match_t=mt, match_d=md,
+                        back_t=bt, back_d=bd, knn_idx=k_idx, knn_dist=k_dist, n_exact_ties=np.array(ties))
+    print("  akaze_real:", d0.shape, d1.shape, d2.shape, "crossCheck matches", len(cq), "stereo inliers", len(inl),
+          "top-2 ties", ties)
+
+
+def golden_create_db_48(ref):
+    """The UNMODIFIED reference's create_db + TrackingDB on 48 frames at the BENCH's keypoint counts
+    (2000-5000 per image, synth.torch_sequence(seed=1), the bench workload's first frames).  The inputs are
+    regenerated from the seed on the test side (CPU generator: deterministic), so only the reference's
+    OUTPUTS are stored: per frame the stereo survivors, the forward matches, the RANSAC inlier flags
+    (np.random seeded) and the track id of every feature."""
+    import torch  # noqa: F401
+    n = 48
+    seq = synth.torch_sequence(n, first_frame=0, seed=1, device="cpu")
+    frames = []
+    for f in range(n):
+        lo, k = int(seq["l_off"][f]), int(seq["n_l"][f])
+        frames.append((seq["pts_l"][lo:lo + k].numpy(), seq["pts_r"][lo:lo + k].numpy(),
+                       seq["desc_l"][lo:lo + k].numpy(), seq["desc_r"][lo:lo + k].numpy()))
+
+    class Provider:
+        def detectAndCompute(self, token, mask):
+            side, f = token
+            pts = frames[f][0 if side == "L" else 1]
+            return tuple(cv2.KeyPoint(float(x), float(y), 1.0) for x, y in pts), frames[f][2 if side == "L" else 3]
+
+    old_feature, old_reader = ref.matching.FEATURE, ref.inputs.read_images
+    ref.matching.FEATURE = Provider()
+    ref.inputs.read_images = lambda idx: (("L", idx), ("R", idx))
+    calls = []
+    try:
+        db = ref.tracking_database.TrackingDB()
+        real_add = db.add_frame
+        db.add_frame = lambda links, left_features, matches_to_previous_left=None, inliers=None: (
+            calls.append((links, left_features, matches_to_previous_left, inliers)),
+            real_add(links, left_features, matches_to_previous_left, inliers))[1]
+        np.random.seed(11)
+        ref.database.create_db(start_frame=0, num_frames=n, db=db)
+    finally:
+        ref.matching.FEATURE, ref.inputs.read_images = old_feature, old_reader
+    db._check_consistency()
+    out = {"n_frames": np.array(n), "seed": np.array(1), "n_tracks": np.array(db.track_num()),
+           "n_links_total": np.array(db.link_num()),
+           "n_links": np.array([len(c[0]) for c in calls], np.int32),
+           "inliers_percent": np.array([db.frameID_to_inliers_percent[f] for f in range(n)])}
+    for f, (links, feats, ms, inl) in enumerate(calls):
+        # link f,k sits on left keypoint link_src: recover it from the descriptor rows (features[is_valid])
+        out[f"x_left{f}"] = np.array([l.x_left for l in links], np.float32)
+        out[f"y{f}"] = np.array([l.y for l in links], np.float64)
+        out[f"track_ids{f}"] = np.array(db.frameId_to_trackIds_list[f], np.int32)
+        if ms is not None:
+            out[f"match_t{f}"] = np.array([m.trainIdx for m in ms], np.uint16)
+            out[f"match_d{f}"] = np.array([int(m.distance) for m in ms], np.uint16)
+            out[f"inliers{f}"] = np.packbits(np.asarray(inl, dtype=bool))
+    np.savez_compressed(os.path.join(OUT, "create_db_48.npz"), **out)
+    print("  create_db_48:", n, "frames,", int(out["n_links"].sum()), "links,", db.track_num(), "tracks,",
+          db.link_num(), "links on tracks")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = refshim.load()
@@ -281,6 +392,8 @@ def main():
     golden_ransac(ref)
     golden_database(ref)
     golden_loop_candidates(golden_create_db(ref))
+    golden_akaze(ref)
+    golden_create_db_48(ref)
     print("golden vectors written to", OUT, "cv2", cv2.__version__, "numpy", np.__version__)
     for f in sorted(os.listdir(OUT)):
         print(" ", f, os.path.getsize(os.path.join(OUT, f)), "bytes")

@@ -415,3 +415,88 @@ def test_batched_create_db_through_patch(slamfe, golden):
         assert np.array_equal(feats, g[f"features{f}"])
         if f:
             assert np.array_equal([m.trainIdx for m in ms], g[f"match_t{f}"]) and len(inl) == len(ms)
+
+
+def _bench_frames(n, seed=1):
+    from slamfe import synth
+    seq = synth.torch_sequence(n, first_frame=0, seed=seed, device="cpu")
+    frames = []
+    for f in range(n):
+        lo, k = int(seq["l_off"][f]), int(seq["n_l"][f])
+        frames.append((seq["desc_l"][lo:lo + k].numpy(), seq["desc_r"][lo:lo + k].numpy(),
+                       seq["pts_l"][lo:lo + k].numpy(), seq["pts_r"][lo:lo + k].numpy()))
+    return frames
+
+
+def test_48_frames_at_bench_size_against_the_reference_run(slamfe, golden):
+    """tests/golden/create_db_48.npz: the unmodified reference's create_db + TrackingDB on the bench
+    workload's first 48 frames (2000-5000 keypoints per image).  The pipeline's stereo survivors and forward
+    matches are identical; slamfe_track_ids fed the REFERENCE's inlier flags reproduces its track ids
+    exactly; the pipeline's own RANSAC consensus (different sampler and solver) contains most of the
+    reference's and builds a consistent store of similar size."""
+    import torch
+    from slamfe import frontend, ops, trackdb
+    g = golden("create_db_48")
+    F = int(g["n_frames"])
+    seq = frontend.pack_sequence(_bench_frames(F, int(g["seed"])))
+    fe = frontend.FrontEnd()
+    tables, _, _ = fe.run_host(seq, chunk_frames=16, track=True, h_max=128, seed=3, track_ids=True)
+    n_links = g["n_links"]
+    assert np.array_equal(tables["n_links"][:F], n_links)
+    ref_flags = np.zeros(seq.desc_l.shape[0], np.uint8)
+    jac = []
+    for f in range(F):
+        lo, k = int(seq.l_off[f]), int(n_links[f])
+        src = tables["link_src"][lo:lo + k]
+        assert np.array_equal(seq.pts_l[lo + src, 0], g[f"x_left{f}"])             # the same links in the same order
+        assert np.allclose(tables["links"][lo:lo + k, 2], g[f"y{f}"], rtol=0, atol=1e-4)
+        assert abs(100 * k / tables["n_matches"][f] - g["inliers_percent"][f]) < 1e-9
+        if f + 1 < F:
+            idx, dist = ops.keys_to_numpy(tables["fwd_keys"][lo:lo + k])
+            assert np.array_equal(idx[:, 0], g[f"match_t{f + 1}"]) and np.array_equal(dist[:, 0], g[f"match_d{f + 1}"])
+            want = np.unpackbits(g[f"inliers{f + 1}"])[:k].astype(bool)
+            got = tables["inlier_fwd"][lo:lo + k].astype(bool)
+            ref_flags[lo:lo + k] = want
+            jac.append((want & got).sum() / max(1, (want | got).sum()))
+    assert np.median(jac) > 0.75, np.median(jac)
+    # the reference's flags through the device kernel -> the reference's track ids, exactly
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    tid, n_tr, _ = ops.track_ids(dev(tables["fwd_keys"]), dev(ref_flags), dev(seq.l_off), dev(tables["n_links"]), F)
+    tid = tid.cpu().numpy()
+    assert int(n_tr.item()) == int(g["n_tracks"])
+    for f in range(F):
+        lo = int(seq.l_off[f])
+        assert np.array_equal(tid[lo:lo + int(n_links[f])], g[f"track_ids{f}"]), f
+        assert (tid[lo + int(n_links[f]):int(seq.l_off[f + 1])] == -1).all()
+    # the pipeline's own store
+    db = trackdb.build(seq, tables)
+    assert db.check_consistency() and db.frame_num() == F
+    assert abs(db.track_num() - int(g["n_tracks"])) < 0.1 * int(g["n_tracks"])
+    host_ids = trackdb.build(seq, {k: v for k, v in tables.items() if k not in ("track_id", "n_tracks")})
+    assert host_ids == db                                     # device ids == host restatement
+    db2 = trackdb.create_db(seq, chunk_frames=100, h_max=128, seed=3)
+    assert db2 == db                                          # chunking does not matter
+
+
+def test_track_ids_edge_cases(slamfe):
+    """No frames, one frame, frames without links, a pair without inliers: ids stay NO_ID, counts are 0."""
+    import torch
+    from slamfe import frontend, trackdb
+    rng = np.random.default_rng(78)
+    frames = make_sequence(rng, [600])
+    out = frontend.FrontEnd().track(frontend.to_device(frontend.pack_sequence(frames)), track_ids=True)
+    assert int(out["n_tracks"].item()) == 0
+    frames = make_sequence(rng, [500, 30, 520, 510])
+    seq = frontend.pack_sequence(frames)
+    fe = frontend.FrontEnd()
+    out = fe.track(frontend.to_device(seq), h_max=32, seed=2, track_ids=True)
+    tid = out["track_id"].cpu().numpy()
+    fwd = out["fwd_keys"].cpu().numpy()
+    inl = out["inlier_fwd"].cpu().numpy()
+    n_links = out["n_links"].cpu().numpy()
+    ids, n_tracks = trackdb.track_ids_host(
+        [fwd[int(seq.l_off[f]):int(seq.l_off[f]) + int(n_links[f]), 0].view(np.uint32) & 0x3FFFFF for f in range(3)],
+        [inl[int(seq.l_off[f]):int(seq.l_off[f]) + int(n_links[f])] for f in range(3)], n_links)
+    assert int(out["n_tracks"].item()) == n_tracks
+    for f in range(4):
+        assert np.array_equal(tid[int(seq.l_off[f]):int(seq.l_off[f]) + int(n_links[f])], ids[f])

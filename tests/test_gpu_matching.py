@@ -305,3 +305,32 @@ def test_shared_matcher_from_several_threads(slamfe, oracle):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_real_akaze_descriptors_through_the_dropin_matchers(slamfe, golden):
+    """tests/golden/akaze_real.npz: real cv2.AKAZE descriptors (correlated bits, > 3k per image) through the
+    drop-in Matcher objects, against what the reference's extract_kps_descs_matches / MATCHER.match /
+    knnMatch returned (matching.py:38-45, database.py:54-55).  The arrays are also passed the way cv2 hands
+    them around: as non-contiguous views of a wider buffer."""
+    from slamfe import matching
+    g = golden("akaze_real")
+    d0, d1, d2 = g["desc_l"], g["desc_r"], g["desc_l2"]
+    wide = np.zeros((len(d0), 80), np.uint8)
+    wide[:, 7:68] = d0
+    view0 = wide[:, 7:68]
+    assert not view0.flags["C_CONTIGUOUS"]
+    lr, mm = matching.Matcher(crossCheck=True), matching.Matcher(crossCheck=False)
+    for q in (d0, view0):
+        ms = lr.match(q, d1)
+        assert [m.queryIdx for m in ms] == g["cross_q"].tolist() and [m.trainIdx for m in ms] == g["cross_t"].tolist()
+        assert [m.distance for m in ms] == g["cross_d"].tolist()
+        fw = mm.match(q, d2)
+        assert [m.trainIdx for m in fw] == g["match_t"].tolist() and [m.distance for m in fw] == g["match_d"].tolist()
+    inl, outl = matching.extract_inliers_outliers(g["pts_l"], g["pts_r"], ms)
+    assert np.array_equal(inl, g["inliers"]) and np.array_equal(outl, g["outliers"])
+    bw = mm.match(d2, d0)
+    assert [m.trainIdx for m in bw] == g["back_t"].tolist() and [m.distance for m in bw] == g["back_d"].tolist()
+    knn = mm.knnMatch(d0, d2, k=2)
+    assert [[m.trainIdx for m in p] for p in knn] == g["knn_idx"].tolist()
+    assert [[int(m.distance) for m in p] for p in knn] == g["knn_dist"].tolist()
+    assert int(g["n_exact_ties"]) >= 0

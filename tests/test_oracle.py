@@ -293,3 +293,40 @@ def test_p3p_degenerate_samples_never_yield_invalid_poses(oracle):
             R = T[:, :3]
             assert np.abs(R @ R.T - np.eye(3)).max() < 1e-6 and np.linalg.det(R) > 0
     assert checked == 300 * 8 and valid > 0
+
+
+def test_oracle_on_real_akaze_descriptors(oracle, golden):
+    """tests/golden/akaze_real.npz: REAL cv2.AKAZE descriptors (correlated bits, > 3k keypoints per image)
+    through the reference's own extract_kps_descs_matches / extract_inliers_outliers / MATCHER.match /
+    knnMatch (matching.py:38-69, database.py:54-55, ex1.py:189-190)."""
+    g = golden("akaze_real")
+    d0, d1, d2 = g["desc_l"], g["desc_r"], g["desc_l2"]
+    assert d0.shape[1] == 61 and min(len(d0), len(d1)) > 2000 and int(d0[:, 60].max()) <= 63
+    cq, ct, cd = oracle.match_crosscheck(d0, d1)
+    assert np.array_equal(cq, g["cross_q"]) and np.array_equal(ct, g["cross_t"]) and np.array_equal(cd, g["cross_d"])
+    inl, outl = oracle.extract_inliers_outliers(g["pts_l"], g["pts_r"], cq, ct)
+    assert np.array_equal(inl, g["inliers"]) and np.array_equal(outl, g["outliers"]) and len(inl) > 500
+    mi, md = oracle.match(d0, d2)
+    assert np.array_equal(mi, g["match_t"]) and np.array_equal(md, g["match_d"])
+    bi, bd = oracle.match(d2, d0)
+    assert np.array_equal(bi, g["back_t"]) and np.array_equal(bd, g["back_d"])
+    ki, kd = oracle.knn2(d0, d2)
+    assert np.array_equal(ki, g["knn_idx"]) and np.array_equal(kd, g["knn_dist"])
+
+
+def test_track_ids_restatement_on_the_48_frame_reference_run(golden):
+    """tests/golden/create_db_48.npz: the unmodified reference's create_db + TrackingDB on the bench
+    workload's first 48 frames.  The host restatement of slamfe_track_ids (slamfe.trackdb.track_ids_host),
+    fed the reference's own forward matches and inlier flags, reproduces frameId_to_trackIds_list of every
+    frame (tracking_database.py:273-337) and the track count."""
+    from slamfe import trackdb
+    g = golden("create_db_48")
+    F = int(g["n_frames"])
+    n_links = g["n_links"]
+    fwd = [g[f"match_t{f + 1}"].astype(np.int64) for f in range(F - 1)]
+    inl = [np.unpackbits(g[f"inliers{f + 1}"])[:n_links[f]].astype(bool) for f in range(F - 1)]
+    ids, n_tracks = trackdb.track_ids_host(fwd, inl, n_links)
+    assert n_tracks == int(g["n_tracks"]) > 10000
+    for f in range(F):
+        assert np.array_equal(ids[f], g[f"track_ids{f}"]), f
+    assert sum(int((a >= 0).sum()) for a in ids) == int(g["n_links_total"])

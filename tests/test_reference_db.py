@@ -129,6 +129,105 @@ def test_adapter_drives_the_reference_tracking_db_identically(oracle):
     db_new._check_consistency() if hasattr(db_new, "_check_consistency") else None
 
 
+def _reference_run(ref, frames, seed=3):
+    """The unmodified reference's create_db + TrackingDB on synthetic frames; returns (db, add_frame calls)."""
+    import cv2
+
+    class Provider:
+        def detectAndCompute(self, token, mask):
+            side, f = token
+            pts = frames[f][0 if side == "L" else 1]
+            desc = frames[f][2 if side == "L" else 3]
+            return tuple(cv2.KeyPoint(float(x), float(y), 1.0) for x, y in pts), desc
+
+    old_feature, old_reader = ref.matching.FEATURE, ref.inputs.read_images
+    ref.matching.FEATURE = Provider()
+    ref.inputs.read_images = lambda idx: (("L", idx), ("R", idx))
+    calls = []
+    try:
+        db = ref.tracking_database.TrackingDB()
+        real_add = db.add_frame
+        db.add_frame = lambda links, left_features, matches_to_previous_left=None, inliers=None: (
+            calls.append((links, left_features, matches_to_previous_left, inliers)),
+            real_add(links, left_features, matches_to_previous_left, inliers))[1]
+        np.random.seed(seed)
+        ref.database.create_db(start_frame=0, num_frames=len(frames), db=db)
+    finally:
+        ref.matching.FEATURE, ref.inputs.read_images = old_feature, old_reader
+    return db, calls
+
+
+def _links_eq(a, b):
+    return [(x.x_left, x.x_right, x.y) for x in a] == [(x.x_left, x.x_right, x.y) for x in b]
+
+
+def test_soa_tracking_db_equals_the_reference_tracking_db(oracle, tmp_path):
+    """slamfe.trackdb.SoATrackingDB (flat columns + track ids) built from run_host-format tables, against the
+    TrackingDB the UNMODIFIED reference builds frame by frame (tracking_database.py:273-337): the read API
+    answers the same, to_reference_db() rebuilds an equal dict-of-lists object (all seven maps), the .npz
+    round trip is lossless, _check_consistency (tracking_database.py:442-471) passes on both forms."""
+    ref = refshim.load()
+    from slamfe import database as sdb, trackdb
+    frames = _synthetic_frames(7)
+    db_ref, calls = _reference_run(ref, frames)
+    seq = sdb.pack_frames([(pl, pr, dl, dr) for pl, pr, dl, dr in frames], pin=False)
+    flags = [None] + [np.asarray(c[3], dtype=bool) for c in calls[1:]]
+    tables = _oracle_tables(seq, frames, oracle, flags)
+    tables["n_good"] = np.array([max(4, int(f.sum())) for f in flags[1:]], np.int32)
+    soa = trackdb.build(seq, tables, link_factory=ref.tracking_database.Link)
+    assert soa.check_consistency()
+    # --- read API
+    assert soa.frame_num() == db_ref.frame_num() and soa.track_num() == db_ref.track_num() > 20
+    assert soa.link_num() == db_ref.link_num() and sorted(soa.all_tracks()) == sorted(db_ref.all_tracks())
+    for f in db_ref.all_frames():
+        assert soa.tracks(f) == db_ref.tracks(f)
+        assert np.array_equal(soa.features(f), db_ref.features(f))
+        assert _links_eq(soa.all_frame_links(f), db_ref.all_frame_links(f))
+        got, want = soa.links(f), db_ref.links(f)
+        assert sorted(got) == sorted(want) and all(_links_eq([got[t]], [want[t]]) for t in want)
+    for t in db_ref.all_tracks():
+        assert soa.frames(t) == db_ref.frames(t) and soa.last_frame_of_track(t) == db_ref.last_frame_of_track(t)
+        got, want = soa.track(t), db_ref.track(t)
+        assert sorted(got) == sorted(want) and all(_links_eq([got[f]], [want[f]]) for f in want)
+        f0 = want and sorted(want)[0]
+        assert _links_eq([soa.link(f0, t)], [db_ref.link(f0, t)])
+    assert soa.link(0, 10 ** 6) is None and soa.features(99) is None and soa.tracks(99) == []
+    assert _links_eq(soa.all_last_frame_links(), db_ref.all_last_frame_links())
+    # --- the reference's own object, rebuilt
+    db2 = soa.to_reference_db(ref.tracking_database.TrackingDB, ref.tracking_database.Link)
+    assert db2.last_frameId == db_ref.last_frameId and db2.last_trackId == db_ref.last_trackId
+    assert db2.trackId_to_frames == db_ref.trackId_to_frames
+    assert db2.frameId_to_trackIds_list == db_ref.frameId_to_trackIds_list
+    assert db2.frameID_to_inliers_percent == db_ref.frameID_to_inliers_percent
+    assert sorted(db2.linkId_to_link) == sorted(db_ref.linkId_to_link)
+    assert all(_links_eq([db2.linkId_to_link[k]], [v]) for k, v in db_ref.linkId_to_link.items())
+    assert sorted(db2.leftover_links) == sorted(db_ref.leftover_links)
+    assert all(_links_eq(db2.leftover_links[f], v) for f, v in db_ref.leftover_links.items())
+    assert _links_eq(db2.prev_frame_links, db_ref.prev_frame_links)
+    assert all(np.array_equal(db2.frameId_to_lfeature[f], v) for f, v in db_ref.frameId_to_lfeature.items())
+    db2._check_consistency()
+    for f in db_ref.all_frames():
+        assert _links_eq(db2.all_frame_links(f), db_ref.all_frame_links(f))
+    # --- on-disk format
+    path = tmp_path / "db.npz"
+    soa.save(path)
+    back = trackdb.SoATrackingDB.load(path, link_factory=ref.tracking_database.Link)
+    assert back == soa and back.check_consistency() and back.tracks(3) == db_ref.tracks(3)
+    import zipfile
+    assert all(n.endswith(".npy") for n in zipfile.ZipFile(path).namelist())     # plain arrays, no pickle
+    # --- the device table path: track ids supplied as a table (slamfe_track_ids' output format)
+    ids, n_tracks = trackdb.track_ids_host(
+        [tables["fwd_keys"][int(seq.l_off[f]):int(seq.l_off[f]) + int(tables["n_links"][f]), 0].view(np.uint32) & 0x3FFFFF
+         for f in range(seq.n_frames - 1)],
+        [tables["inlier_fwd"][int(seq.l_off[f]):int(seq.l_off[f]) + int(tables["n_links"][f])] for f in range(seq.n_frames - 1)],
+        tables["n_links"])
+    table_ids = np.full(seq.desc_l.shape[0], -1, np.int32)
+    for f, a in enumerate(ids):
+        table_ids[int(seq.l_off[f]):int(seq.l_off[f]) + len(a)] = a
+    tables2 = dict(tables, track_id=table_ids, n_tracks=np.array([n_tracks], np.int32))
+    assert trackdb.build(seq, tables2, link_factory=ref.tracking_database.Link) == soa
+
+
 def test_patch_batched_db_rebinds_create_db_on_the_real_reference(monkeypatch):
     """patch(batched_db=True) on the real reference module tree: `database.create_db` becomes the batched
     builder, which reads and describes the frames through the reference's own `Inputs.read_images` /

@@ -19,6 +19,7 @@ MAX_DESC_BYTES = 64
 MATCH_BEST_ONLY = 1
 MATCH_COMPACT_KEYS = 2
 MATCH_MMA = 4
+ABI_VERSION = 203   # SLAMFE_ABI_VERSION of include/slamfe.h this binding was written against
 
 # name -> (restype, argtypes); mirrors include/slamfe.h one to one
 _SIGNATURES = {
@@ -55,6 +56,7 @@ _SIGNATURES = {
     "slamfe_ransac_hypotheses": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                          c_void_p, c_uint64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "slamfe_track_ids": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64] + [c_void_p] * 7),
+    "slamfe_pack_db": (c_int, [c_void_p] * 8 + [c_int, c_void_p, c_int] + [c_void_p] * 7),
     "slamfe_pnp_refit": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                  c_int, c_void_p, c_int, ctypes.c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "slamfe_peak_kernel": (c_int, [c_int, c_int, c_int, c_int, c_void_p, POINTER(c_int), c_void_p]),
@@ -74,12 +76,25 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise SlamfeError(f"{LIB_PATH} is missing: run `python __graft_entry__.py build`")
+    if not os.environ.get("SLAMFE_LIBRARY"):
+        # the in-tree build must match csrc/ and include/slamfe.h (a stale library would be called with the
+        # wrong argument lists): rebuild when the recorded source digest differs.  Under a multi-process
+        # launch a rebuild would race between ranks, so a stale library is an error there.
         from . import build as _build
-        _build.build()
+        if _build.needs_build():
+            if not build_if_missing and not os.path.exists(LIB_PATH):
+                raise SlamfeError(f"{LIB_PATH} is missing: run `python __graft_entry__.py build`")
+            if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.path.exists(LIB_PATH):
+                raise SlamfeError(f"{LIB_PATH} is older than its sources: run `python __graft_entry__.py build` "
+                                  f"before a multi-process launch")
+            _build.build(force=True)
+    elif not os.path.exists(LIB_PATH):
+        raise SlamfeError(f"SLAMFE_LIBRARY={LIB_PATH} does not exist")
     lib = ctypes.CDLL(LIB_PATH)
+    lib.slamfe_version.restype = c_int
+    if lib.slamfe_version() != ABI_VERSION:
+        raise SlamfeError(f"{LIB_PATH} has ABI version {lib.slamfe_version()}, this binding expects {ABI_VERSION}: "
+                          f"run `python __graft_entry__.py build`")
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export what the header declares
         fn.restype = res

@@ -30,12 +30,28 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; libslamfe.so cannot be built")
 
 
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def source_hash() -> str:
+    """Digest of everything the library is built from (csrc/, include/slamfe.h, the flags).  Stored next to
+    the library at build time: file times do not survive a snapshot copy, contents do."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS + SOURCES).encode())
+    for path in sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(REPO_ROOT, "include", "slamfe.h")]:
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(REPO_ROOT, "include", "slamfe.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    if not os.path.exists(HASH_PATH):   # a library of unknown provenance (digest not shipped): trust it
+        return False
+    with open(HASH_PATH) as fh:
+        return fh.read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -50,6 +66,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    with open(HASH_PATH, "w") as fh:
+        fh.write(source_hash() + "\n")
     return LIB_PATH
 
 

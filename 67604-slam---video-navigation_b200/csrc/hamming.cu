@@ -328,45 +328,15 @@ int launch_hamming(const HammingParams &p, dim3 grid, bool top2, cudaStream_t st
 }
 
 // Shipping configuration (scripts/tune_matcher.py sweep on B200): 2 query rows per
-// thread, 9 full adders per descriptor pair.  -DSLAMFE_TUNING builds every variant and lets
-// SLAMFE_HAMMING_R / SLAMFE_HAMMING_CS pick one at run time (development only).
+// thread, 9 full adders per descriptor pair (the other variants of the sweep are in the git history).
 constexpr int kRows = 2;
 constexpr int kAdders = 9;
 
-#ifdef SLAMFE_TUNING
-int env_int(const char *name, int dflt)
-{
-    const char *v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
-}
-
-template <int RMAX>
-int launch_big_cs(const HammingParams &p, dim3 grid, int cs, bool top2, cudaStream_t stream)
-{
-    switch (cs) {
-        case 7: return launch_hamming<256, RMAX, 7>(p, grid, top2, stream);
-        case 8: return launch_hamming<256, RMAX, 8>(p, grid, top2, stream);
-        case 10: return launch_hamming<256, RMAX, 10>(p, grid, top2, stream);
-        default: return launch_hamming<256, RMAX, 9>(p, grid, top2, stream);
-    }
-}
-int big_rows() { const int r = env_int("SLAMFE_HAMMING_R", kRows); return r < 2 ? 2 : r > 4 ? 4 : r; }
-int launch_big(const HammingParams &p, dim3 grid, bool top2, cudaStream_t stream)
-{
-    const int cs = env_int("SLAMFE_HAMMING_CS", kAdders);
-    switch (big_rows()) {
-        case 3: return launch_big_cs<3>(p, grid, cs, top2, stream);
-        case 4: return launch_big_cs<4>(p, grid, cs, top2, stream);
-        default: return launch_big_cs<2>(p, grid, cs, top2, stream);
-    }
-}
-#else
 int big_rows() { return kRows; }
 int launch_big(const HammingParams &p, dim3 grid, bool top2, cudaStream_t stream)
 {
     return launch_hamming<256, kRows, kAdders>(p, grid, top2, stream);
 }
-#endif
 
 // Kernel choice: SLAMFE_MATCH_MMA in `flags` selects the tcgen05 kernel (hamming_mma.cu) for this call;
 // the environment variable SLAMFE_MATCH_MMA=1 / 0 (read once) forces it on / off for every call.
@@ -413,11 +383,6 @@ int run_hamming(HammingParams p, int n_problems, int max_nq, int max_nt, int64_t
     const long long ctas_big = plan(tq_big, 4, 3 * sms, slices_big);
     const bool big = ctas_big >= 2LL * sms;
     if (!big) plan(128, 1, 4 * sms, slices_small);
-    // A CTA that sweeps a whole 3-5k-row train set lives for milliseconds, and the last wave of
-    // such CTAs leaves most SMs idle: cap the sweep at kMaxStagesPerCta stages so that the tail of
-    // a launch is short (the per-slice results merge through atomicMin, which is exact).
-    constexpr int kMaxStagesPerCta = 1 << 20;  // disabled: the extra row-merge atomics cost more than the tail (measured)
-    if (big) slices_big = max(slices_big, (stages_total + kMaxStagesPerCta - 1) / kMaxStagesPerCta);
     const int slices = big ? slices_big : slices_small;
     const int stages_per_slice = (stages_total + slices - 1) / slices;
     p.t_slice = stages_per_slice * TS;

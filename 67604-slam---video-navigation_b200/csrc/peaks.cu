@@ -86,7 +86,7 @@ __global__ void peak_fp64_kernel(int iters, uint32_t *sink)
 
 using namespace slamfe;
 
-extern "C" int slamfe_version(void) { return 100; }
+extern "C" int slamfe_version(void) { return SLAMFE_ABI_VERSION; }
 
 extern "C" const char *slamfe_error_string(int code)
 {

@@ -185,6 +185,7 @@ class FrontEnd:
         self._in_key = None
         self._pinned_out = None
         self._pinned_ids = None
+        self._pinned_db = None
         self._streams = None
         # kernels launched by one run(): 2 matcher launches, stereo epilogue, triangulation
         # (cudaMemsetAsync initialisation of the key tables is not counted)
@@ -400,7 +401,7 @@ class FrontEnd:
         return self._in
 
     def run_host(self, seq: PackedSequence, chunk_frames=576, device="cuda", keys=RESULT_KEYS, track=False,
-                 h_max=256, seed=1, full_ransac=True, track_ids=False):
+                 h_max=256, seed=1, full_ransac=True, track_ids=False, track_keys=TRACK_KEYS, pack_db=False):
         """Pinned host inputs -> pinned host result tables, copies overlapped with the kernels.
 
         Returns (dict of numpy views of the pinned result tables, h2d_bytes, d2h_bytes).  The call
@@ -410,10 +411,16 @@ class FrontEnd:
         pair).  full_ransac=True (default) re-runs the pairs h_max truncated at their full count before
         returning (rescore_truncated; self.last_truncated = how many).  track_ids=True (needs track) adds the
         tables track_id (L,) int32 and n_tracks (1,): computed once over the whole sequence after the last
-        chunk (tracks cross chunk boundaries), after any re-run of truncated pairs."""
+        chunk (tracks cross chunk boundaries), after any re-run of truncated pairs.  track_keys: which of the
+        TRACK_KEYS tables travel back (n_hyp_full always does).  pack_db=True (needs track_ids) adds the DENSE
+        tracking-database columns db_link_off / db_x_left / db_x_right / db_y / db_feat / db_track_id
+        (slamfe_pack_db) — with keys=("n_matches", "n_links") and a short track_keys list that is all
+        slamfe.trackdb needs, and far less D2H than the padded tables."""
         torch = _cabi.require_cuda()
         if track_ids and not track:
             raise ValueError("track_ids needs track=True")
+        if pack_db and not track_ids:
+            raise ValueError("pack_db needs track_ids=True")
         if seq.tensors is None:
             raise ValueError("run_host needs a pinned PackedSequence (pack_sequence(..., pin=True))")
         dev = torch.device(device)
@@ -425,7 +432,7 @@ class FrontEnd:
         o = self._buffers(L, R, F, dev)
         trk = self._track_buffers(L, F, h_max, dev) if track else None
         if track:
-            keys = tuple(keys) + tuple(k for k in TRACK_KEYS if k not in keys)
+            keys = tuple(keys) + tuple(k for k in tuple(track_keys) + ("n_hyp_full",) if k not in keys)
             o = dict(o)
             o.update(trk)
         if self._pinned_out is None or any(k not in self._pinned_out or self._pinned_out[k].shape != o[k].shape
@@ -574,6 +581,24 @@ class FrontEnd:
             torch.cuda.current_stream(dev).synchronize()
             tables["track_id"], tables["n_tracks"] = pin[0].numpy(), pin[1].numpy()
             d2h += tid.numel() * 4 + 4
+            if pack_db:
+                r_off_dev = small_dev.new_tensor(seq.r_off)
+                db = ops.pack_db(o, l_off_dev, r_off_dev, din["pts_l"], din["pts_r"], F, DESC_BYTES, track_id=tid, out=trk)
+                self.last_launches += 2
+                n_total = int(np.asarray(tables["n_links"][:F], dtype=np.int64).sum())
+                if self._pinned_db is None or self._pinned_db["x_left"].shape[0] < n_total:
+                    cap = max(n_total, 1)
+                    self._pinned_db = {k: torch.empty((cap,) + tuple(v.shape[1:]), dtype=v.dtype, pin_memory=True)
+                                       for k, v in db.items() if k != "link_off"}
+                    self._pinned_db["link_off"] = torch.empty((0,), dtype=torch.int32, pin_memory=True)
+                if self._pinned_db["link_off"].shape[0] != F + 1:
+                    self._pinned_db["link_off"] = torch.empty((F + 1,), dtype=torch.int32, pin_memory=True)
+                for k, v in db.items():
+                    n_rows = F + 1 if k == "link_off" else n_total
+                    self._pinned_db[k][:n_rows].copy_(v[:n_rows], non_blocking=True)
+                    tables["db_" + k] = self._pinned_db[k][:n_rows].numpy()
+                    d2h += n_rows * v[0:1].numel() * v.element_size()
+                torch.cuda.current_stream(dev).synchronize()
         return tables, int(h2d), int(d2h)
 
 

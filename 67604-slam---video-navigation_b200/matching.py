@@ -144,8 +144,7 @@ class Matcher:
         row_keys, col_keys = ops.hamming_top2(qd, td, want_cols=self.crossCheck, best_only=True)
         if self.crossCheck:
             mt, md = ops.cross_check(row_keys, col_keys)
-            import torch
-            both = self._st.to_host("o", torch.stack([mt, md]))
+            both = self._st.to_host("o", mt._base)   # (2, nq): match_t and match_dist share one buffer
             keep = both[0] >= 0
             return np.nonzero(keep)[0].astype(np.int32), both[0][keep], both[1][keep]
         keys = self._st.to_host("o", row_keys)

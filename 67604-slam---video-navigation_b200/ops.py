@@ -147,11 +147,12 @@ def merge_top2(shard_keys):
 
 
 def cross_check(row_keys, col_keys):
-    """crossCheck epilogue: (match_t, match_dist) int32 (nq,), -1 where the pair is not mutual."""
+    """crossCheck epilogue: (match_t, match_dist) int32 (nq,), -1 where the pair is not mutual.  The two
+    are rows of ONE (2, nq) buffer (`match_t._base`), so a caller can bring both to the host in one copy."""
     torch = _torch()
     nq, nt = row_keys.shape[0], col_keys.shape[0]
-    mt = torch.empty((nq,), dtype=torch.int32, device=row_keys.device)
-    md = torch.empty((nq,), dtype=torch.int32, device=row_keys.device)
+    both = torch.empty((2, nq), dtype=torch.int32, device=row_keys.device)
+    mt, md = both[0], both[1]
     with torch.cuda.device(mt.device):
         check(load_library().slamfe_cross_check(ptr(row_keys), ptr(col_keys), nq, nt, ptr(mt), ptr(md),
                                                 stream_handle()), "slamfe_cross_check")
@@ -298,6 +299,34 @@ def track_ids(fwd_keys, inlier_fwd, l_off, n_links, n_frames, out=None):
                                               ptr(pred), ptr(rank), ptr(head_cnt), ptr(head_base), ptr(track_id),
                                               ptr(n_tracks), stream_handle()), "slamfe_track_ids")
     return track_id, n_tracks, head_base
+
+
+def pack_db(o, l_off, r_off, pts_l, pts_r, n_frames, desc_bytes, track_id=None, out=None):
+    """Dense tracking-database columns on the device (slamfe_pack_db) from the pipeline tables `o`
+    (n_links, link_src, match_t, feat).  Returns a dict: link_off (F + 1,) int32, x_left / x_right (L,)
+    float32, y (L,) float64, feat (L, desc_bytes) uint8, track_id (L,) int32 — the first link_off[-1] rows
+    of each are the store."""
+    torch = _torch()
+    dev = o["feat"].device
+    L = o["feat"].shape[0]
+    out = out if out is not None else {}
+
+    def buf(name, shape, dtype):
+        t = out.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = out[name] = torch.empty(shape, dtype=dtype, device=dev)
+        return t
+
+    res = {"link_off": buf("db_link_off", (n_frames + 1,), torch.int32), "x_left": buf("db_x_left", (L,), torch.float32),
+           "x_right": buf("db_x_right", (L,), torch.float32), "y": buf("db_y", (L,), torch.float64),
+           "feat": buf("db_feat", (L, desc_bytes), torch.uint8), "track_id": buf("db_track_id", (L,), torch.int32)}
+    with torch.cuda.device(dev):
+        check(load_library().slamfe_pack_db(
+            ptr(l_off), ptr(r_off), ptr(o["n_links"]), ptr(o["link_src"]), ptr(o["match_t"]), ptr(pts_l), ptr(pts_r),
+            ptr(o["feat"]), int(desc_bytes), ptr(track_id), n_frames, ptr(res["link_off"]), ptr(res["x_left"]),
+            ptr(res["x_right"]), ptr(res["y"]), ptr(res["feat"]), ptr(res["track_id"]), stream_handle()),
+            "slamfe_pack_db")
+    return res
 
 
 def pnp_refit(T, best, pts, l_pix, mask, K, pt_off=None, pt_cnt=None, n_frames=1, max_iter=20, tol=1e-12, out=None):

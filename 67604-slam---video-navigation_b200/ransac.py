@@ -52,11 +52,13 @@ def score_hypotheses(Ts, pts, l_pix, r_pix, hyp_valid=None):
     if Ts.shape[0] == 0:
         return np.zeros(0, np.int32), -1, 0, np.zeros(pts.shape[0], bool)
     hv = None if hyp_valid is None else _st.to_device("hv", np.asarray(hyp_valid, dtype=np.uint8))
-    counts, best, mask = ops.ransac_score(_st.to_device("T", Ts), _st.to_device("pts", pts),
-                                          _st.to_device("lp", l_pix), _st.to_device("rp", r_pix),
-                                          K, M1, M2, hyp_valid=hv)
+    ptsd = _st.to_device("pts", pts)
+    H = Ts.shape[0]
     import torch
-    packed = torch.cat([counts.view(-1), best.view(-1)])
+    packed = torch.empty((H + 2,), dtype=torch.int32, device=ptsd.device)   # [counts | best index, best count]
+    counts, best, mask = ops.ransac_score(_st.to_device("T", Ts), ptsd, _st.to_device("lp", l_pix),
+                                          _st.to_device("rp", r_pix), K, M1, M2, hyp_valid=hv,
+                                          out={"counts": packed[:H].view(1, H), "best": packed[H:].view(1, 2)})
     host = _st.to_host("cb", packed)
     mask_h = _st.to_host("mask", mask).astype(bool)
     return host[:-2].copy(), int(host[-2]), int(host[-1]), mask_h

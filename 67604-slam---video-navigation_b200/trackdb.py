@@ -286,6 +286,17 @@ def build(seq, tables, link_factory=Link):
     n_matches = tables["n_matches"][:F].astype(np.int64)
     if (n_matches == 0).any():
         raise ZeroDivisionError("division by zero")          # database.py:26
+    if "db_track_id" in tables:   # dense columns straight from the device (slamfe_pack_db): nothing left to do
+        if F > 1:
+            if (n_links == 0).any():
+                raise IndexError("tuple index out of range")    # database.py:56 on an empty match list
+            if (tables["n_good"][:F - 1] < 4).any():            # ransac.py:95
+                raise ValueError("Cannot take a larger sample than population when 'replace=False'")
+        with np.errstate(invalid="ignore", divide="ignore"):
+            pct = 100 * (n_links / n_matches)
+        return SoATrackingDB(tables["db_link_off"].astype(np.int64), tables["db_x_left"].copy(),
+                             tables["db_x_right"].copy(), tables["db_y"].copy(), tables["db_feat"].copy(),
+                             tables["db_track_id"].copy(), pct.astype(np.float64), int(tables["n_tracks"][0]), link_factory)
     width = np.diff(l_off)
     within = np.arange(int(l_off[-1]), dtype=np.int64) - np.repeat(l_off[:-1], width)
     frame_of = np.repeat(np.arange(F, dtype=np.int64), width)
@@ -332,5 +343,6 @@ def create_db(frames, chunk_frames=576, h_max=256, seed=1, front_end=None, link_
     seq = frames if isinstance(frames, frontend.PackedSequence) else database.pack_frames(frames)
     fe = front_end or frontend.FrontEnd()
     tables, _, _ = fe.run_host(seq, chunk_frames=chunk_frames, track=True, h_max=h_max, seed=seed, full_ransac=True,
-                               track_ids=True)
+                               track_ids=True, pack_db=True, keys=("n_matches", "n_links"),
+                               track_keys=("n_good", "n_hyp", "best", "pose", "pose_status"))
     return build(seq, tables, link_factory=link_factory)

@@ -30,13 +30,11 @@ def triangulate_link_array(links_xyz: np.ndarray, p, q) -> np.ndarray:
     arr = np.ascontiguousarray(links_xyz, dtype=np.float64).reshape(-1, 3)
     if arr.shape[0] == 0:
         return np.zeros((0, 3))
-    dev = _st.to_device("links", arr)
     if ops.same_rows_stereo(p, q):
-        xyz = ops.triangulate_links(dev, p, q)
-    else:
-        import torch
-        pxy = torch.stack([dev[:, 0], dev[:, 2]], dim=1)
-        qxy = torch.stack([dev[:, 1], dev[:, 2]], dim=1)
+        xyz = ops.triangulate_links(_st.to_device("links", arr), p, q)
+    else:   # general P, Q: the (x_left, y) / (x_right, y) pixel pairs are laid out on the host
+        pxy = _st.to_device("pxy", np.ascontiguousarray(arr[:, [0, 2]]))
+        qxy = _st.to_device("qxy", np.ascontiguousarray(arr[:, [1, 2]]))
         xyz = ops.triangulate_dlt(pxy, qxy, p, q)
     return _st.to_host("xyz", xyz)
 

@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--frames", type=int, default=4541, help="frames per GPU (KITTI 00 has 4541)")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--impl", default="slamfe", choices=["slamfe", "reference"])
-    ap.add_argument("--workload", default="sequence", choices=["sequence", "ransac", "loop", "dense", "dropin"],
+    ap.add_argument("--workload", default="sequence", choices=["sequence", "ransac", "loop", "dense", "dropin", "createdb"],
                     help="sequence = BASELINE configs[1] (the headline line); the others are configs[2..4], see "
                          "bench_extra.py")
     ap.add_argument("--keyframes", type=int, default=450, help="--workload loop: number of keyframes")

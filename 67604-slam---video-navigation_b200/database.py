@@ -44,8 +44,15 @@ def pack_frames(frames, pin=True):
     """frames: iterable of (kp_left, kp_right, desc_left, desc_right) as
     `extract_kps_descs_matches` returns them (matching.py:38-45; keypoints as cv2.KeyPoint sequences or
     (n, 2) float arrays) -> frontend.PackedSequence."""
-    return frontend.pack_sequence([(np.ascontiguousarray(dl, dtype=np.uint8), np.ascontiguousarray(dr, dtype=np.uint8),
-                                    _keypoint_array(kl), _keypoint_array(kr)) for kl, kr, dl, dr in frames], pin=pin)
+    def desc(d):
+        d = np.asarray(d)
+        if d.dtype != np.uint8 or d.ndim != 2 or d.shape[1] != frontend.DESC_BYTES:
+            # e.g. SIFT's float32 (n, 128): casting would silently produce garbage (cv2 raises cv2.error here)
+            raise TypeError(f"descriptors must be (n, {frontend.DESC_BYTES}) uint8 (AKAZE MLDB), got {d.dtype} {d.shape}")
+        return np.ascontiguousarray(d)
+
+    return frontend.pack_sequence([(desc(dl), desc(dr), _keypoint_array(kl), _keypoint_array(kr))
+                                   for kl, kr, dl, dr in frames], pin=pin)
 
 
 def frames_from_tables(seq, tables):

@@ -179,18 +179,19 @@ def sharded_knn(q_dev, t_shard_dev, t_index_base, desc_bytes=None, best_only=Fal
 
 def gather_pair_tables(tables, n_units):
     """All-gather per-shard result tables of the frame-pair / candidate-block shardings.
-    `tables` maps name -> tensor whose leading dimension is this rank's unit count (frames,
-    candidate pairs, rows).  Returns name -> (world, max_units, ...) plus the per-rank unit counts;
-    one collective per table (+1 for the counts)."""
+    `tables` maps name -> tensor whose leading dimension is this rank's unit count (frames, candidate
+    pairs) or any other per-rank length (rows).  Returns name -> (world, max_len, ...) plus the per-rank
+    unit counts.  The true leading length of EVERY table is exchanged first (one small collective), so
+    ranks whose rows-per-unit differ still agree on the padded size."""
     import torch
     import torch.distributed as dist
     first = next(iter(tables.values()))
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return {k: v.unsqueeze(0) for k, v in tables.items()}, np.array([n_units], dtype=np.int64)
-    ln = torch.tensor([n_units], dtype=torch.int64, device=first.device)
-    lengths = _all_gather_stacked(ln).reshape(-1).cpu().numpy()
+    names = sorted(tables)
+    ln = torch.tensor([n_units] + [tables[k].shape[0] for k in names], dtype=torch.int64, device=first.device)
+    all_len = _all_gather_stacked(ln).cpu().numpy()          # (world, 1 + n_tables)
     out = {}
-    for k, v in tables.items():
-        per_unit = v.shape[0] // max(n_units, 1) if n_units else 1
-        out[k], _ = all_gather_padded(v, lengths=lengths * per_unit if v.shape[0] != n_units else lengths)
-    return out, lengths
+    for i, k in enumerate(names):
+        out[k], _ = all_gather_padded(tables[k], lengths=all_len[:, 1 + i])
+    return out, all_len[:, 0].astype(np.int64)

@@ -47,10 +47,22 @@ def replacements():
     }
 
 
-def patch(modules=None, batched_db=False, batched_loop=False, **pipeline_kw):
+def _akaze_feature():
+    """The detector of get_akaze_matcher_lr_matcher() (matching.py:19-21)."""
+    import cv2
+    return cv2.AKAZE_create(threshold=0.0008, nOctaves=4, nOctaveLayers=4)
+
+
+def patch(modules=None, batched_db=False, batched_loop=False, rebind_feature=True, **pipeline_kw):
     """Rebind every already-imported reference module (or the given {name: module} mapping).
     Also copies the reference's cameras into slamfe.ransac so both sides score with the same
     K, M1, M2.  Returns {module_name: [rebound attribute names]}; `unpatch(token)` restores.
+
+    The checked-in reference selects SIFT + L2 (matching.py:72; float32 128-d descriptors), which the
+    Hamming-only GPU matchers cannot serve: with rebind_feature=True (default) `matching.FEATURE` is rebound
+    to the AKAZE detector of the reference's own get_akaze_matcher_lr_matcher() (matching.py:19-21) whenever
+    the current FEATURE does not produce 8-bit descriptors; with rebind_feature=False such a configuration is
+    refused with a TypeError instead of failing later inside cv2.
 
     batched_db=True additionally replaces `database.create_db` (database.py:30, called by
     `database.run`, :92-98) with the batched whole-sequence builder of slamfe.database: frames are
@@ -67,6 +79,15 @@ def patch(modules=None, batched_db=False, batched_loop=False, **pipeline_kw):
     ref_ransac = mods.get("final_project.algorithms.ransac")
     if ref_ransac is not None and hasattr(ref_ransac, "K"):
         ransac.set_cameras(ref_ransac.K, ref_ransac.M1, ref_ransac.M2)
+    ref_matching = mods.get("final_project.algorithms.matching")
+    feature = getattr(ref_matching, "FEATURE", None) if ref_matching is not None else None
+    if feature is not None and hasattr(feature, "descriptorType") and feature.descriptorType() != 0:   # CV_8U == 0
+        if not rebind_feature:
+            raise TypeError("the reference's matching.FEATURE produces non-binary descriptors (SIFT/L2, matching.py:72); "
+                            "slamfe implements the AKAZE/Hamming configuration (matching.py:19-24)")
+        saved.append((ref_matching, "FEATURE", feature))
+        ref_matching.FEATURE = _akaze_feature()
+        done.setdefault("final_project.algorithms.matching", []).append("FEATURE")
     for mod_name, attrs in _REBINDS.items():
         mod = mods.get(mod_name)
         if mod is None:

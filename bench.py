@@ -359,6 +359,34 @@ def main():
                "ms_per_step": float(e_ms.item()) / args.steps,
                "api": f"FrontEnd.run_host(PackedSequence, chunk_frames={args.chunk_frames}, track=True)",
                "gpu_launches_per_step": fe2.last_launches, "ransac_pairs_rerun_at_full_count": fe2.last_truncated}
+        # what the link itself delivers: the same bytes as plain pinned copies, no kernels (per rank, all
+        # ranks at once: at N > 1 the ranks share the host's memory system and PCIe root complexes)
+        dev_in = {k: torch.empty_like(v, device=dev) for k, v in pinned_in.items()}
+        outs = {k: fe2._out[k] for k in frontend.RESULT_KEYS}
+        pin_out = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in outs.items()}
+        barrier()
+        t0 = time.perf_counter()
+        for k, v in pinned_in.items():
+            dev_in[k].copy_(v, non_blocking=True)
+        torch.cuda.synchronize()
+        t_h2d = time.perf_counter() - t0
+        barrier()
+        t0 = time.perf_counter()
+        for k, v in outs.items():
+            pin_out[k].copy_(v, non_blocking=True)
+        torch.cuda.synchronize()
+        t_d2h = time.perf_counter() - t0
+        b_in = sum(v.numel() * v.element_size() for v in pinned_in.values())
+        b_out = sum(v.numel() * v.element_size() for v in outs.values())
+        link = torch.tensor([b_in / t_h2d / 1e9, b_out / t_d2h / 1e9], device=dev, dtype=torch.float64)
+        if world > 1:
+            tdist.all_reduce(link, op=tdist.ReduceOp.MIN)
+        e2e["pcie"] = {"h2d_gbs_per_rank_min": float(link[0].item()), "d2h_gbs_per_rank_min": float(link[1].item()),
+                       "h2d_ms_at_that_rate": b_in / float(link[0].item()) / 1e6,
+                       "note": "plain pinned copies of the step's inputs / result tables, all ranks concurrently, "
+                               "slowest rank; the e2e step cannot be shorter than the H2D time: the inputs are "
+                               "61-byte descriptors of both images (485 KB per frame) and cannot be made smaller"}
+        del dev_in, pin_out, outs
         # the host pipeline (chunked, 4 streams) must deliver exactly the tables of the resident run
         torch.cuda.synchronize()
         resident = {k: out[k].cpu().numpy() for k in e2e_tables if k in out}

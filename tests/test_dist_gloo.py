@@ -78,6 +78,15 @@ def _worker_body(rank, world, port, q_out):
     allbest = np.concatenate([tabs["best"][k, :lens[k]].numpy() for k in range(world)])
     ref = np.array([int(ora.match(pool[i], pool[j])[1].min()) for i, j in pairs])
     res["loop"] = bool(np.array_equal(allbest, ref) and lens.sum() == len(pairs))
+    # row tables whose rows-per-unit differ between ranks: the true lengths are exchanged
+    rows_mine = [np.full(int(sizes[i]), 100 * i + j, np.int32) for i, j in pairs[cb[rank]:cb[rank + 1]]]
+    tab = torch.from_numpy(np.concatenate(rows_mine) if rows_mine else np.zeros(0, np.int32))
+    tabs2, lens2 = sdist.gather_pair_tables({"rows": tab, "best": torch.tensor(best, dtype=torch.int32)}, len(best))
+    want_rows = [np.concatenate([np.full(int(sizes[i]), 100 * i + j, np.int32) for i, j in pairs[cb[k]:cb[k + 1]]])
+                 for k in range(world)]
+    res["ragged_rows"] = bool(all(np.array_equal(tabs2["rows"][k, :len(want_rows[k])].numpy(), want_rows[k])
+                                  for k in range(world)) and np.array_equal(lens2, lens)
+                              and tabs2["rows"].shape[1] == max(len(w_) for w_ in want_rows))
     work = (sizes[pairs[:, 0]] * sizes[pairs[:, 1]]).astype(np.float64)
     share = np.array([work[cb[k]:cb[k + 1]].sum() for k in range(world)]) / work.sum()
     res["balanced"] = bool(abs(share[0] - 0.5) < 0.15)

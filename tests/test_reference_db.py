@@ -275,3 +275,39 @@ def test_patch_batched_db_rebinds_create_db_on_the_real_reference(monkeypatch):
     finally:
         patch.unpatch(tok)
     assert ref.database.create_db is original
+
+
+def test_patch_rebinds_a_non_binary_feature_and_pack_frames_validates(monkeypatch):
+    """the checked-in reference selects SIFT (matching.py:72).  patch() rebinds matching.FEATURE to
+    the AKAZE detector of get_akaze_matcher_lr_matcher() (matching.py:19-21) or, with rebind_feature=False,
+    refuses; pack_frames rejects descriptors that are not (n, 61) uint8 instead of casting them."""
+    import sys
+    import cv2
+    ref = refshim.load()
+    from slamfe import database as sdb, patch
+    monkeypatch.setattr(patch, "replacements", lambda: {})
+    monkeypatch.setattr(patch, "_REBINDS", {})
+    mods = {k: v for k, v in sys.modules.items() if k.startswith("final_project")}
+    sift = cv2.SIFT_create()
+    monkeypatch.setattr(ref.matching, "FEATURE", sift)
+    token = patch.patch(mods)
+    try:
+        assert "FEATURE" in token["final_project.algorithms.matching"]
+        f = ref.matching.FEATURE
+        assert f is not sift and f.descriptorType() == 0 and f.descriptorSize() == 61
+        assert abs(f.getThreshold() - 0.0008) < 1e-9 and f.getNOctaves() == 4 and f.getNOctaveLayers() == 4
+    finally:
+        patch.unpatch(token)
+    assert ref.matching.FEATURE is sift
+    with pytest.raises(TypeError, match="non-binary"):
+        patch.patch(mods, rebind_feature=False)
+    akaze = cv2.AKAZE_create()
+    monkeypatch.setattr(ref.matching, "FEATURE", akaze)
+    token = patch.patch(mods)
+    assert ref.matching.FEATURE is akaze          # a binary detector is left alone
+    patch.unpatch(token)
+    pts = np.zeros((5, 2), np.float32)
+    with pytest.raises(TypeError, match="uint8"):
+        sdb.pack_frames([(pts, pts, np.zeros((5, 128), np.float32), np.zeros((5, 128), np.float32))], pin=False)
+    with pytest.raises(TypeError, match="uint8"):
+        sdb.pack_frames([(pts, pts, np.zeros((5, 32), np.uint8), np.zeros((5, 32), np.uint8))], pin=False)

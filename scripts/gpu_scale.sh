@@ -1,20 +1,15 @@
 #!/bin/bash
-# Bench workloads at N GPUs: gpurun --gpus N --timeout 600 -- 'bash scripts/gpu_scale.sh N "sequence loop"'
+# Default bench (sequence + loop / dense sub-records) at the box's GPU count.  Run as:
+#   gpurun --gpus N --timeout 900 -- 'bash scripts/gpu_scale.sh N'
 set -u
-N=${1:-2}
-WL=${2:-"sequence ransac loop dense"}
-for w in $WL; do
-  if [ "$N" = "1" ]; then
-    timeout 300 python bench.py --workload $w --gpus 1 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/scale_${w}_${N}gpu.json 2> gpurun_out/scale_${w}_${N}gpu.err
-  else
-    timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --workload $w --gpus $N --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/scale_${w}_${N}gpu.json 2> gpurun_out/scale_${w}_${N}gpu.err
-  fi
-  echo "$w rc=$?"
-  python - <<PY
+N=${1:-8}
+mkdir -p gpurun_out
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r02_scale_${N}gpu.json 2> gpurun_out/r02_scale_${N}gpu.err; echo "bench N=$N rc=$?"
+python - <<PY
 import json
-try:
-    d=json.loads(open('gpurun_out/scale_${w}_${N}gpu.json').read().strip().splitlines()[-1])
-    print('$w', 'N', d['n_gpus'], 'value', d['value'], d['unit'], 'ms', round(d['ms_per_step'],2), 'e2e', d['e2e']['value'], d['scaling'])
-except Exception as e: print('$w parse failed', e)
+txt=open('gpurun_out/r02_scale_${N}gpu.json').read()
+d=json.loads([l for l in txt.splitlines() if l.startswith('{')][-1])
+print('N',d['n_gpus'],'value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],d['e2e']['ms_per_step'],d['e2e'].get('pcie'))
+for k,v in d['extra'].items():
+    print(k,v['value'],'ms',v['ms_per_step'],'e2e',v['e2e']['value'],json.dumps(v['parity'])[:400])
 PY
-done

@@ -19,7 +19,7 @@ MAX_DESC_BYTES = 64
 MATCH_BEST_ONLY = 1
 MATCH_COMPACT_KEYS = 2
 MATCH_MMA = 4
-ABI_VERSION = 203   # SLAMFE_ABI_VERSION of include/slamfe.h this binding was written against
+ABI_VERSION = 204   # SLAMFE_ABI_VERSION of include/slamfe.h this binding was written against
 
 # name -> (restype, argtypes); mirrors include/slamfe.h one to one
 _SIGNATURES = {
@@ -57,6 +57,7 @@ _SIGNATURES = {
                                          c_void_p, c_uint64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "slamfe_track_ids": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64] + [c_void_p] * 7),
     "slamfe_pack_db": (c_int, [c_void_p] * 8 + [c_int, c_void_p, c_int] + [c_void_p] * 7),
+    "slamfe_gate_candidates": (c_int, [c_void_p, c_int] + [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "slamfe_pnp_refit": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                  c_int, c_void_p, c_int, ctypes.c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "slamfe_peak_kernel": (c_int, [c_int, c_int, c_int, c_int, c_void_p, POINTER(c_int), c_void_p]),

@@ -13,7 +13,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libslamfe.so")
-SOURCES = ["hamming.cu", "hamming_mma.cu", "stereo.cu", "triangulate.cu", "ransac.cu", "ransac_gen.cu", "tracking.cu", "trackdb.cu", "refit.cu", "peaks.cu"]
+SOURCES = ["hamming.cu", "hamming_mma.cu", "stereo.cu", "triangulate.cu", "ransac.cu", "ransac_gen.cu", "tracking.cu", "trackdb.cu", "refit.cu", "gating.cu", "peaks.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

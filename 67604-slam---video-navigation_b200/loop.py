@@ -24,6 +24,9 @@ from .ransac import calc_ransac_iteration
 
 INLIERS_THRESHOLD = 120   # loop_closure.py:17
 LOOP_INLIERS_PERCENT = 40  # loop_closure.py:425
+MAHALANOBIS_THRESHOLD = 220   # loop_closure.py:15
+MAX_CANDIDATES = 15           # loop_closure.py:18
+KEY_FRAME_GAP = 10            # loop_closure.py:20
 
 
 class CandidateVerifier:
@@ -244,3 +247,73 @@ def consensus_matches(reference_key_frame, candidates_index_lst, data_base):
             return cand, matches, rel_T
     _, _, rel_T = _candidate_result(res, len(candidates) - 1, links[0], ver)
     return None, [], rel_T
+
+
+# ------------------------------------------------------------------------------------------------
+# Candidate gating (loop_closure.py:164-228) on arrays: the GTSAM objects stay with the caller
+# ------------------------------------------------------------------------------------------------
+class CovarianceGraph:
+    """The covariance graph of backend/loop/graph.py (undirected, edge weight det(cov)) as arrays, plus the
+    keyframe poses: what get_good_candidates needs from the pose graph.  Nodes are keyframe INDICES
+    0..K-1 (positions in the reference's index_list); `add_edge` mirrors Graph.add_edge (:15-25; adding an
+    existing edge replaces it, as update_edge does)."""
+
+    def __init__(self, n_nodes):
+        self.n_nodes = int(n_nodes)
+        self._edges = {}          # (min, max) -> cov (6, 6)
+
+    def add_edge(self, v1, v2, cov):
+        self._edges[(min(int(v1), int(v2)), max(int(v1), int(v2)))] = np.array(cov, dtype=np.float64).reshape(6, 6)
+
+    def remove_edge(self, v1, v2):
+        return self._edges.pop((min(int(v1), int(v2)), max(int(v1), int(v2))), None) is not None
+
+    def arrays(self):
+        """CSR adjacency + per-edge weight / covariance.  Neighbours are listed in insertion order of the
+        edges, as the reference's dict-of-dicts iterates them."""
+        E = len(self._edges)
+        ends = np.array(list(self._edges), dtype=np.int32).reshape(E, 2)
+        cov = np.array(list(self._edges.values()), dtype=np.float64).reshape(E, 36)
+        w = np.array([np.linalg.det(c.reshape(6, 6)) for c in cov], dtype=np.float64)     # graph.py:11-13
+        deg = np.zeros(self.n_nodes + 1, dtype=np.int64)
+        for a, b in ends:
+            deg[a + 1] += 1
+            deg[b + 1] += 1
+        off = np.cumsum(deg).astype(np.int32)
+        fill = off[:-1].astype(np.int64).copy()
+        node = np.zeros(2 * E, dtype=np.int32)
+        edge = np.zeros(2 * E, dtype=np.int32)
+        for e, (a, b) in enumerate(ends):
+            node[fill[a]], edge[fill[a]] = b, e
+            fill[a] += 1
+            node[fill[b]], edge[fill[b]] = a, e
+            fill[b] += 1
+        return off, node, edge, w, cov
+
+
+def gate_distances(poses, graph: CovarianceGraph, queries, gap=KEY_FRAME_GAP):
+    """Mahalanobis distance of every earlier keyframe to each query keyframe (check_candidate,
+    loop_closure.py:164-196), all queries in one launch.  poses: (K, 3, 4) or (K, 4, 4) camera-to-world.
+    Returns (dist (Q, K) float64 numpy: +inf where not a candidate, hops (Q, K))."""
+    torch = _cabi.require_cuda()
+    P = np.ascontiguousarray(np.asarray(poses, dtype=np.float64)[:, :3, :4]).reshape(-1, 12)
+    off, node, edge, w, cov = graph.arrays()
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    q = np.ascontiguousarray(np.asarray(queries, dtype=np.int32).reshape(-1))
+    dist, hops = ops.gate_candidates(dev(P), dev(off), dev(node), dev(edge), dev(w), dev(cov), dev(q), gap)
+    return dist.cpu().numpy(), hops.cpu().numpy()
+
+
+def select_candidates(dist_row, index_list=None, threshold=MAHALANOBIS_THRESHOLD, max_candidates=MAX_CANDIDATES):
+    """get_good_candidates' selection (loop_closure.py:214-228): distances below the threshold, ascending
+    (stable: ties keep index order, as list.sort), the best `max_candidates`; mapped through index_list."""
+    d = np.asarray(dist_row, dtype=np.float64)
+    cand = np.nonzero(d < threshold)[0]
+    cand = cand[np.argsort(d[cand], kind="stable")][:max_candidates]
+    return [int(index_list[c]) if index_list is not None else int(c) for c in cand]
+
+
+def get_good_candidates(c_n_index, poses, graph, index_list=None, gap=KEY_FRAME_GAP):
+    """loop_closure.py:199-228 on arrays: the candidate keyframes of keyframe c_n_index."""
+    dist, _ = gate_distances(poses, graph, [c_n_index], gap=gap)
+    return select_candidates(dist[0], index_list)

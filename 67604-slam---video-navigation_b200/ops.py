@@ -329,6 +329,22 @@ def pack_db(o, l_off, r_off, pts_l, pts_r, n_frames, desc_bytes, track_id=None, 
     return res
 
 
+def gate_candidates(poses, adj_off, adj_node, adj_edge, edge_w, edge_cov, queries, gap):
+    """Mahalanobis gating distances (slamfe_gate_candidates; loop_closure.py:164-228) for the query
+    keyframes `queries` (int32 CUDA) against all earlier keyframes.  Returns (dist (Q, K) float64 with +inf
+    where i is no candidate, hops (Q, K) int32)."""
+    torch = _torch()
+    dev = poses.device
+    K, Q = poses.shape[0], queries.shape[0]
+    dist = torch.empty((Q, K), dtype=torch.float64, device=dev)
+    hops = torch.empty((Q, K), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(load_library().slamfe_gate_candidates(
+            ptr(poses.contiguous()), K, ptr(adj_off), ptr(adj_node), ptr(adj_edge), ptr(edge_w), ptr(edge_cov.contiguous()),
+            ptr(queries), Q, int(gap), ptr(dist), ptr(hops), stream_handle()), "slamfe_gate_candidates")
+    return dist, hops
+
+
 def pnp_refit(T, best, pts, l_pix, mask, K, pt_off=None, pt_cnt=None, n_frames=1, max_iter=20, tol=1e-12, out=None):
     """Refit of the pose on the consensus set (ransac.py:185-193) for n_frames problems in one launch
     (slamfe_pnp_refit): T / best / mask as returned by ransac_hypotheses / ransac_score.

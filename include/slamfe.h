@@ -51,7 +51,7 @@ typedef void *slamfe_stream_t;
 
 /* ABI version of this header: bumped whenever an entry point is added or a signature changes.  The loader
  * (_cabi.load_library) refuses a library whose slamfe_version() differs. */
-#define SLAMFE_ABI_VERSION 203
+#define SLAMFE_ABI_VERSION 204
 int slamfe_version(void);
 const char *slamfe_error_string(int code);
 
@@ -325,6 +325,25 @@ int slamfe_pack_db(const int32_t *l_off, const int32_t *r_off, const int32_t *n_
                    const int32_t *match_t, const float *pts_left, const float *pts_right, const uint8_t *feat,
                    int desc_bytes, const int32_t *track_id, int n_frames, int32_t *link_off, float *x_left,
                    float *x_right, double *y, uint8_t *feat_out, int32_t *track_out, slamfe_stream_t stream);
+
+/*
+ * Loop-closure candidate gating (get_good_candidates / check_candidate, backend/loop/loop_closure.py:164-228)
+ * for n_queries query keyframes in one launch.  For query n = queries[q] and every keyframe i < n - gap:
+ * shortest path i -> n in the covariance graph (backend/loop/graph.py:57-97; edge weight edge_w = det(cov),
+ * Dijkstra order (distance, node), strict-< relaxation), covariance = sum of edge_cov along the path in path
+ * order (loop_closure.py:103-137), distance = sqrt(xi^T cov^-1 xi) with xi = Pose3::Logmap(pose_n^-1 pose_i)
+ * (= sqrt(2 * BetweenFactorPose3(c_n, c_i, Pose3(), Gaussian(cov)).error(result)), :185-188; GTSAM tangent
+ * order rotation, translation).  The GTSAM objects stay with the caller and arrive as arrays:
+ *   poses (n_nodes, 12) fp64 camera-to-world [R|t] per keyframe;  the undirected graph as CSR over nodes
+ *   (adj_off (n_nodes+1), adj_node / adj_edge (2E)) with edge_w (E,) and edge_cov (E, 36).
+ *   dist_out (n_queries, n_nodes) fp64: the distance, +inf where i is no candidate (i >= n - gap, or
+ *   unreachable), NaN where the summed covariance is not positive definite;  hops_out (same shape, int32 or
+ *   NULL): edges on the path, -1 where no candidate.   n_nodes <= 1024.
+ */
+int slamfe_gate_candidates(const double *poses, int n_nodes, const int32_t *adj_off, const int32_t *adj_node,
+                           const int32_t *adj_edge, const double *edge_w, const double *edge_cov,
+                           const int32_t *queries, int n_queries, int gap, double *dist_out, int32_t *hops_out,
+                           slamfe_stream_t stream);
 
 /*
  * PnP refit on the consensus set: the final solve of ransac_pnp (final_project/algorithms/ransac.py:185-193,

@@ -552,3 +552,97 @@ def cv2_knn2(q, t):
             idx2[i, k] = x.trainIdx
             dist2[i, k] = int(x.distance)
     return idx2, dist2
+
+
+# ---------------------------------------------------------------------------------------------------
+# Loop-closure candidate gating (backend/loop/loop_closure.py:140-228, backend/loop/graph.py)
+# ---------------------------------------------------------------------------------------------------
+def so3_logmap(R):
+    """GTSAM SO3::Logmap (published algorithm; gtsam is not installed here — pinned against scipy.linalg.logm
+    by tests/test_oracle.py)."""
+    tr = np.trace(R)
+    if tr + 1.0 < 1e-3:
+        k = int(np.argmax(np.diag(R)))
+        d = R[k, k]
+        w = (np.pi / np.sqrt(2.0 + 2.0 * d)) * (R[:, k] + np.eye(3)[k])
+        skew = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+        return -w if skew[k] < 0 else w
+    tr3 = tr - 3.0
+    mag = np.arccos((tr - 1.0) / 2.0) / (2.0 * np.sin(np.arccos((tr - 1.0) / 2.0))) if tr3 < -1e-7 else 0.5 - tr3 / 12.0
+    return mag * np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+
+
+def pose3_logmap(R, t):
+    """GTSAM Pose3::Logmap: (rotation vector, V^-1 t)."""
+    w = so3_logmap(R)
+    th = np.linalg.norm(w)
+    if th < 1e-10:
+        return np.concatenate([w, t])
+    W = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]) / th
+    WT = W @ t
+    u = t - (0.5 * th) * WT + (1 - th / (2.0 * np.tan(0.5 * th))) * (W @ WT)
+    return np.concatenate([w, u])
+
+
+def dijkstra_path(adj, start, end):
+    """backend/loop/graph.py:57-97 restated: heapq Dijkstra, (distance, node) order, strict-< relaxation.
+    adj: {node: {neighbour: weight}}."""
+    import heapq
+    if start == end:
+        return [start]
+    pq = [(0, start)]
+    dist = {v: float("inf") for v in adj}
+    dist[start] = 0
+    pred = {v: None for v in adj}
+    while pq:
+        d, u = heapq.heappop(pq)
+        if u == end:
+            break
+        if d > dist[u]:
+            continue
+        for v, w in adj[u].items():
+            nd = d + w
+            if nd < dist[v]:
+                dist[v], pred[v] = nd, u
+                heapq.heappush(pq, (nd, v))
+    if dist[end] == float("inf"):
+        return None
+    path, v = [], end
+    while v is not None:
+        path.insert(0, v)
+        v = pred[v]
+    return path
+
+
+def gate_distances(poses, edges, n, gap=10, graph_cls=None):
+    """check_candidate (loop_closure.py:164-196) for query keyframe n against every i < n - gap.
+    poses (K, 3, 4) camera-to-world; edges: list of (v1, v2, cov (6,6)).  With graph_cls (the reference's own
+    Graph class, backend/loop/graph.py) the shortest paths come from the unmodified reference."""
+    K = len(poses)
+    if graph_cls is not None:
+        g = graph_cls()
+        for a, b, c in edges:
+            g.add_edge(a, b, np.array(c, dtype=np.float64))
+        path_of = lambda i: g.get_shortest_path(i, n)
+        cov_of = lambda a, b: g.get_cov(a, b)
+    else:
+        adj, covs = {}, {}
+        for a, b, c in edges:
+            w = np.linalg.det(np.asarray(c, dtype=np.float64))
+            adj.setdefault(a, {})[b] = w
+            adj.setdefault(b, {})[a] = w
+            covs[(a, b)] = covs[(b, a)] = np.asarray(c, dtype=np.float64)
+        path_of = lambda i: dijkstra_path(adj, i, n)
+        cov_of = lambda a, b: covs[(a, b)]
+    out = np.full(K, np.inf)
+    Rn, tn = poses[n][:3, :3], poses[n][:3, 3]
+    for i in range(0, n - gap):
+        path = path_of(i)
+        if path is None:
+            continue
+        cov = None
+        for a, b in zip(path[:-1], path[1:]):
+            cov = np.array(cov_of(a, b), dtype=np.float64) if cov is None else cov + cov_of(a, b)
+        xi = pose3_logmap(Rn.T @ poses[i][:3, :3], Rn.T @ (poses[i][:3, 3] - tn))
+        out[i] = np.sqrt(xi @ np.linalg.solve(cov, xi))
+    return out

@@ -217,3 +217,44 @@ def test_loop_closure_pose_needs_no_host_solve(slamfe, golden, monkeypatch):
             assert np.linalg.norm(dR - dR.T) / (2 * np.sqrt(2)) < 5e-3 and np.linalg.norm(Pg[:3, 3] - Pc[:3, 3]) < 0.05
             checked += 1
     assert checked >= 1
+
+
+def test_candidate_gating_vs_oracle(slamfe, oracle):
+    """slamfe_gate_candidates (get_good_candidates / check_candidate, loop_closure.py:164-228) for many query
+    keyframes in one launch, against the oracle's restatement (pinned on the CPU against scipy's matrix
+    logarithm and the unmodified reference's Graph class): same shortest paths (hop counts), Mahalanobis
+    distances to 1e-9, the same <= 15 candidates below the threshold in the same order."""
+    from slamfe import loop
+    import sys
+    sys.path.insert(0, __import__("os").path.dirname(__file__))
+    from test_oracle import _random_pose_graph
+    rng = np.random.default_rng(96)
+    poses, edges = _random_pose_graph(rng, K=300, n_loops=8)
+    g = loop.CovarianceGraph(len(poses))
+    for a, b, c in edges:
+        g.add_edge(a, b, c)
+    queries = [12, 40, 41, 150, 151, 299] + rng.integers(11, 300, 30).tolist()
+    dist, hops = loop.gate_distances(poses, g, queries)
+    adj = {}
+    for a, b, c in edges:
+        w = np.linalg.det(c)
+        adj.setdefault(a, {})[b] = w; adj.setdefault(b, {})[a] = w
+    shortcuts = 0
+    for q, n in enumerate(queries):
+        want = oracle.gate_distances(poses, edges, n)
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isfinite(dist[q]), fin)
+        assert np.allclose(dist[q][fin], want[fin], rtol=1e-9, atol=0), (n, np.abs(dist[q][fin] / want[fin] - 1).max())
+        for i in (0, max(0, n - 11)):
+            if i < n - loop.KEY_FRAME_GAP:
+                path = oracle.dijkstra_path(adj, i, n)
+                assert hops[q, i] == len(path) - 1
+                shortcuts += len(path) - 1 < n - i
+        assert (hops[q][~fin] == -1).all()
+        sw = np.sort(want[fin])
+        thr = float((sw[len(sw) // 2 - 1] + sw[len(sw) // 2]) / 2) if len(sw) > 1 else 1.0   # splits this graph, hits no value
+        got_sel = loop.select_candidates(dist[q], threshold=thr)
+        ref = sorted([(want[i], i) for i in np.nonzero(want < thr)[0]])[:loop.MAX_CANDIDATES]
+        assert got_sel == [i for _, i in ref] and len(got_sel) <= loop.MAX_CANDIDATES
+    assert shortcuts > 0                                     # the loop edges are used by some shortest paths
+    assert loop.get_good_candidates(5, poses, g) == []      # nothing is KEY_FRAME_GAP behind keyframe 5

@@ -330,3 +330,67 @@ def test_track_ids_restatement_on_the_48_frame_reference_run(golden):
     for f in range(F):
         assert np.array_equal(ids[f], g[f"track_ids{f}"]), f
     assert sum(int((a >= 0).sum()) for a in ids) == int(g["n_links_total"])
+
+
+def _random_pose_graph(rng, K=120, n_loops=5):
+    """A keyframe chain with a few loop edges, random-walk poses and SPD 6x6 edge covariances."""
+    from slamfe import synth
+    poses = np.zeros((K, 3, 4))
+    R, t = np.eye(3), np.zeros(3)
+    for k in range(K):
+        poses[k] = np.hstack([R, t[:, None]])
+        R = R @ synth._rodrigues(rng.normal(0, 0.05, 3))
+        t = t + R @ np.array([0.0, 0.0, 1.0]) * rng.uniform(5, 15) + rng.normal(0, 0.2, 3)
+    def spd(scale):
+        a = rng.normal(0, 1, (6, 6))
+        return (a @ a.T + 6 * np.eye(6)) * scale
+    edges = [(k, k + 1, spd(rng.uniform(1e-3, 3e-3))) for k in range(K - 1)]
+    for _ in range(n_loops):
+        a, b = sorted(rng.choice(K, 2, replace=False).tolist())
+        if b - a > 1:
+            edges.append((a, b, spd(rng.uniform(2e-4, 8e-4))))
+    return poses, edges
+
+
+def test_gating_restatement_against_scipy_and_the_reference_graph(oracle):
+    """Candidate gating (loop_closure.py:164-228): gtsam is not installed, so the SE(3) logarithm is pinned
+    against scipy.linalg.logm of the homogeneous matrix (an independent algorithm) and the shortest paths
+    against the UNMODIFIED reference's Graph class (backend/loop/graph.py), which imports without gtsam."""
+    from scipy.linalg import logm
+    from slamfe import synth
+    rng = np.random.default_rng(95)
+    for scale in (1e-9, 1e-3, 0.3, 1.5, 3.0):
+        for _ in range(6):
+            R = synth._rodrigues(rng.normal(0, 1, 3) * scale / np.sqrt(3))
+            t = rng.normal(0, 5, 3)
+            T = np.eye(4); T[:3, :3] = R; T[:3, 3] = t
+            L = np.real(logm(T))
+            want = np.array([L[2, 1], L[0, 2], L[1, 0], L[0, 3], L[1, 3], L[2, 3]])
+            got = oracle.pose3_logmap(R, t)
+            assert np.allclose(got, want, rtol=1e-7, atol=1e-9), (scale, got, want)
+    from oracle import refshim
+    poses, edges = _random_pose_graph(rng)
+    mine = oracle.gate_distances(poses, edges, 110)
+    assert np.isfinite(mine[:100]).all() and np.isinf(mine[100:]).all()
+    if refshim.available():
+        import importlib
+        sys_path_added = False
+        import sys
+        if "/root/reference" not in sys.path:
+            sys.path.insert(0, "/root/reference"); sys_path_added = True
+        try:
+            Graph = importlib.import_module("final_project.backend.loop.graph").Graph
+        finally:
+            if sys_path_added:
+                sys.path.remove("/root/reference")
+        ref = oracle.gate_distances(poses, edges, 110, graph_cls=Graph)
+        assert np.array_equal(ref, mine)                     # same paths, same summation order
+        g = Graph()
+        adj = {}
+        for a, b, c in edges:
+            g.add_edge(a, b, c)
+            w = np.linalg.det(c)
+            adj.setdefault(a, {})[b] = w; adj.setdefault(b, {})[a] = w
+        for _ in range(200):
+            a, b = rng.choice(len(poses), 2, replace=False).tolist()
+            assert g.get_shortest_path(a, b) == oracle.dijkstra_path(adj, a, b)

@@ -84,7 +84,7 @@ def frames_from_tables(seq, tables):
         yield out
 
 
-def create_db(frames, db, link_factory=None, chunk_frames=576, h_max=256, seed=1, front_end=None):
+def create_db(frames, db, link_factory=None, chunk_frames=288, h_max=256, seed=1, front_end=None):
     """database.py:30-89 for a whole sequence.  `frames` as for pack_frames (or a PackedSequence),
     `db` a TrackingDB-like object, `link_factory` the reference's Link class (default: the stand-in
     above).  Returns db.  Raises where the reference does: IndexError for a frame pair without any

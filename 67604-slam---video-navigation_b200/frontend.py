@@ -192,6 +192,7 @@ class FrontEnd:
         self.launches_per_run = 4
         self.last_launches = 0
         self.last_truncated = 0   # pairs whose RANSAC iteration count exceeded h_max in the last run
+        self.trace = None         # set to [] to collect (stage, chunk, start event, end event) of run_host
 
     def _buffers(self, L, R, F, dev):
         torch = _cabi.require_cuda()
@@ -400,7 +401,7 @@ class FrontEnd:
             self._pinned_out = None
         return self._in
 
-    def run_host(self, seq: PackedSequence, chunk_frames=576, device="cuda", keys=RESULT_KEYS, track=False,
+    def run_host(self, seq: PackedSequence, chunk_frames=288, device="cuda", keys=RESULT_KEYS, track=False,
                  h_max=256, seed=1, full_ransac=True, track_ids=False, track_keys=TRACK_KEYS, pack_db=False):
         """Pinned host inputs -> pinned host result tables, copies overlapped with the kernels.
 
@@ -485,16 +486,29 @@ class FrontEnd:
             n = f1 - f0
             a, b = int(l_off[f0]), int(l_off[f1])
             ra, rb = int(r_off[f0]), int(r_off[f1])
+            tr = self.trace
+
+            def mark(stream):
+                if tr is None:
+                    return None
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                return e
+
             with torch.cuda.stream(s_in):
+                e0 = mark(s_in)
                 for k, lo, hi in (("desc_l", a, b), ("pts_l", a, b), ("desc_r", ra, rb), ("pts_r", ra, rb)):
                     src = seq.tensors[k][lo:hi]
                     din[k][lo:hi].copy_(src, non_blocking=True)
                     h2d += src.numel() * src.element_size()
-                ev_in = torch.cuda.Event()
+                ev_in = torch.cuda.Event(enable_timing=tr is not None)
                 ev_in.record(s_in)
+                if tr is not None:
+                    tr.append(("h2d", c, e0, ev_in))
             (l0, l1), (r0, r1), (q0, q1), (t0, t1), (lp0, lp1), (rp0, rp1) = index[c]
             with torch.cuda.stream(s_cmp):
                 s_cmp.wait_event(ev_in)
+                e0 = mark(s_cmp)
                 view = {k: o[k][a:b] for k in ("lr_row_keys", "match_t", "link_src", "links", "feat", "xyz")}
                 view["lr_col_keys"] = o["lr_col_keys"][ra:rb]
                 view["n_matches"], view["n_links"] = o["n_matches"][f0:f1], o["n_links"][f0:f1]
@@ -536,10 +550,13 @@ class FrontEnd:
                         trk["inlier_fwd"][int(l_off[F - 1]):].zero_()
                 if f0 == 0:
                     o["bwd_keys"][:int(l_off[1])].fill_(-1)
-                ev_cmp = torch.cuda.Event()
+                ev_cmp = torch.cuda.Event(enable_timing=tr is not None)
                 ev_cmp.record(s_cmp)
+                if tr is not None:
+                    tr.append(("compute", c, e0, ev_cmp))
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_cmp)
+                e0 = mark(s_out)
                 # complete after this chunk: per-row tables of its frames, forward keys up to f1-2
                 fa = int(l_off[max(f0 - 1, 0)])
                 fb = b if f1 == F else int(l_off[f1 - 1])
@@ -555,9 +572,11 @@ class FrontEnd:
                     if hi > lo:
                         hout[k][lo:hi].copy_(o[k][lo:hi], non_blocking=True)
                         d2h += (hi - lo) * o[k][0:1].numel() * o[k].element_size()
-                ev = torch.cuda.Event()
+                ev = torch.cuda.Event(enable_timing=tr is not None)
                 ev.record(s_out)
                 ev_done.append(ev)
+                if tr is not None:
+                    tr.append(("d2h", c, e0, ev))
         ev_done[-1].synchronize()
         for s in self._streams:
             cur.wait_stream(s)

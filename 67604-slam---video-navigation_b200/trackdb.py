@@ -336,7 +336,7 @@ def build(seq, tables, link_factory=Link):
                          link_factory)
 
 
-def create_db(frames, chunk_frames=576, h_max=256, seed=1, front_end=None, link_factory=Link):
+def create_db(frames, chunk_frames=288, h_max=256, seed=1, front_end=None, link_factory=Link):
     """database.py:30-89 for a whole sequence, straight into the flat store: pack -> FrontEnd.run_host
     (track + track ids on the device) -> build().  `frames` as for database.pack_frames."""
     from . import database, frontend

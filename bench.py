@@ -64,7 +64,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-frames", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--chunk-frames", type=int, default=576, help="frames per chunk of the host pipeline (e2e)")
+    ap.add_argument("--chunk-frames", type=int, default=288, help="frames per chunk of the host pipeline (e2e)")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the loop-closure (configs[3]) and dense (configs[4]) strong-scaling sub-records")
     ap.add_argument("--extra-steps", type=int, default=3, help="timed steps of each sub-record")

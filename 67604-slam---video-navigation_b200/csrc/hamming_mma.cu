@@ -55,28 +55,47 @@ namespace slamfe {
 namespace {
 
 constexpr int MQ = 128;                 // query rows per UMMA tile (M)
-constexpr int QT = 2;                   // query tiles per CTA
-constexpr int CQ = MQ * QT;             // query rows per CTA
-constexpr int NT = 128;                 // train rows per stage = UMMA N
 constexpr int KCH = 32;                 // 16-byte K chunks per row (512 K positions)
-constexpr int LBO = NT * 16;            // bytes between consecutive K chunks of the B tile
-constexpr int B_STAGE = KCH * LBO;      // 65536
-constexpr int NB = 2;                   // B (and raw) stages
-constexpr int ND = 2;                   // accumulators (one per query tile; see above)
-constexpr int RAW_STAGE = NT * SLAMFE_MAX_DESC_BYTES + 16;
-constexpr int N_EPI_WARPS = 8, N_EXP_WARPS = 4;
-constexpr int MMA_WARP = N_EPI_WARPS + N_EXP_WARPS;
-constexpr int THREADS = (MMA_WARP + 1) * 32;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t TMEM_A = ND * NT;    // columns 256..511 hold the two query tiles
+constexpr int kDefaultGeometry = 0;
 
-struct __align__(16) Smem {
-    uint8_t b[NB][B_STAGE];
-    uint8_t raw[NB][RAW_STAGE];
-    uint32_t scratch[N_EPI_WARPS][32 * 32];  // per-warp 32 rows x 64 packed distances, chunk-swizzled
-    uint32_t colmin[QT][2][NT];              // per query tile, double buffered over stages
-    uint64_t raw_full[NB], b_full[NB], b_empty[NB], d_full[ND], d_empty[ND], a_ready;
-    uint32_t tmem_base;
+// Geometry of one instantiation.  QT query tiles of 128 rows per CTA (their +-1 tiles live in TMEM as A
+// operands), train stages of NT rows (= UMMA N), two accumulators of NT columns:
+//   <2, 128>  256 query rows per CTA: a train row is expanded once per 256 queries; the two tiles'
+//             accumulators double-buffer each other; column minima by shared-memory transpose or redux
+//   <1, 192>  128 query rows per CTA, N = 192: fewer, larger MMAs (a tcgen05.mma with A in TMEM costs
+//             ~83 + 0.2 N cycles on this part: 109 at N = 128, 122 at N = 192) at twice the expansion work
+//             per pair; the accumulators alternate between stages; column minima by redux only (no room
+//             for the transpose scratch next to 2 x 96 KB of B stages)
+template <int QT_, int NT_, bool REDUX_>
+struct Geo {
+    static constexpr int QT = QT_, NT = NT_;
+    static constexpr bool REDUX = REDUX_;
+    static constexpr int CQ = MQ * QT;               // query rows per CTA
+    static constexpr int LBO = NT * 16;              // bytes between consecutive K chunks of the B tile
+    static constexpr int B_STAGE = KCH * LBO;
+    static constexpr int NB = 2;                     // B (and raw) stages
+    static constexpr int RAW_STAGE = NT * SLAMFE_MAX_DESC_BYTES + 16;
+    static constexpr int N_EPI_WARPS = 4 * QT, N_EXP_WARPS = NT / 32;
+    static constexpr int MMA_WARP = N_EPI_WARPS + N_EXP_WARPS;
+    static constexpr int THREADS = (MMA_WARP + 1) * 32;
+    static constexpr int NCH = NT / 64;              // 64-column chunks of an accumulator
+    static constexpr uint32_t TMEM_A = 2 * NT;       // first column of the query tiles
+    static constexpr uint32_t IDESC = (2u << 4)                                 // D format S32
+                                      | (1u << 7)                               // A signed 8-bit
+                                      | (0u << 10)                              // B unsigned 8-bit
+                                      | (static_cast<uint32_t>(NT >> 3) << 17)  // N
+                                      | (static_cast<uint32_t>(MQ >> 4) << 24); // M; both operands K-major
+    static_assert(2 * NT + 128 * QT <= 512, "TMEM: two accumulators + the query tiles");
+    static_assert(NT % 64 == 0 && NT % 32 == 0, "stage = whole 64-column chunks");
+    struct __align__(16) Smem {
+        uint8_t b[NB][B_STAGE];
+        uint8_t raw[NB][RAW_STAGE];
+        uint32_t scratch[REDUX ? 1 : N_EPI_WARPS][REDUX ? 4 : 32 * 32];  // per-warp 32 x 64 packed distances, swizzled
+        uint32_t colmin[QT][2][NT];                                      // per query tile, double buffered over stages
+        uint64_t raw_full[NB], b_full[NB], b_empty[NB], d_full[2], d_empty[2], a_ready;
+        uint32_t tmem_base;
+    };
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
@@ -150,12 +169,6 @@ __device__ __forceinline__ void tmem_ld64_packed(uint32_t taddr, uint32_t (&v)[3
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-constexpr uint32_t kIdesc = (2u << 4)                               // D format S32
-                            | (1u << 7)                             // A signed 8-bit
-                            | (0u << 10)                            // B unsigned 8-bit
-                            | (static_cast<uint32_t>(NT >> 3) << 17)  // N
-                            | (static_cast<uint32_t>(MQ >> 4) << 24); // M; both operands K-major
-
 // bits s, s+8, s+16, s+24 of w as four 0/1 bytes
 __device__ __forceinline__ uint32_t spread(uint32_t w, int s) { return (w >> s) & 0x01010101u; }
 // the same four bits as 0x80 / 0 bytes; `mul` = 1 << (7 - s) lives in a register so that the shift is an
@@ -191,10 +204,13 @@ __device__ __forceinline__ bool elect_one()
 __device__ __forceinline__ int acc_of(int s, int t, int n_tiles) { return n_tiles == 2 ? t : (s & 1); }
 __device__ __forceinline__ int acc_use(int s, int n_tiles) { return n_tiles == 2 ? s : (s >> 1); }
 
-// grid = (query tiles of 256 rows, train slices, problems)
-template <bool COL, bool TOP2>
-__global__ void __launch_bounds__(THREADS, 1) hamming_mma_kernel(const HammingParams p)
+// grid = (query tiles of G::CQ rows, train slices, problems)
+template <class G, bool COL, bool TOP2>
+__global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const HammingParams p)
 {
+    constexpr int QT = G::QT, NT = G::NT, CQ = G::CQ, LBO = G::LBO, NB = G::NB;
+    constexpr int N_EPI_WARPS = G::N_EPI_WARPS, MMA_WARP = G::MMA_WARP, THREADS = G::THREADS;
+    using Smem = typename G::Smem;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
 
@@ -219,15 +235,15 @@ __global__ void __launch_bounds__(THREADS, 1) hamming_mma_kernel(const HammingPa
     const int n_stage = (te - tb + NT - 1) / NT;
     const int ws = p.desc_bytes >> 2;   // input word whose byte 3 holds the 8 spare K positions
     const int n_k = ws + 1;             // MMA K steps: 32 K positions = 4 descriptor bytes each
-    const int n_tiles = (nq - qt0 > MQ) ? 2 : 1;
+    const int n_tiles = (QT == 2 && nq - qt0 > MQ) ? 2 : 1;
 
     if (tid == 0) {
         for (int i = 0; i < NB; ++i) {
             mbar_init(&sm.raw_full[i], 1);
-            mbar_init(&sm.b_full[i], N_EXP_WARPS * 32);
+            mbar_init(&sm.b_full[i], G::N_EXP_WARPS * 32);
             mbar_init(&sm.b_empty[i], 1);
         }
-        for (int i = 0; i < ND; ++i) {
+        for (int i = 0; i < 2; ++i) {
             mbar_init(&sm.d_full[i], 1);
             mbar_init(&sm.d_empty[i], 128);
         }
@@ -292,7 +308,7 @@ __global__ void __launch_bounds__(THREADS, 1) hamming_mma_kernel(const HammingPa
                             a[s] = spread(w[k], s) * 0xFEu | 0x01010101u;  // bit 0 -> +1, bit 1 -> -1
                             if (k == ws) a[s] = (a[s] & 0x00FFFFFFu) | spare[s];
                         }
-                        tmem_st8(tmem + lane_base + TMEM_A + tile * 128 + 8 * k, a);
+                        tmem_st8(tmem + lane_base + G::TMEM_A + tile * 128 + 8 * k, a);
                     }
                 }
                 tmem_wait_st();
@@ -300,42 +316,43 @@ __global__ void __launch_bounds__(THREADS, 1) hamming_mma_kernel(const HammingPa
                 mbar_arrive(&sm.a_ready);
             }
             uint32_t b1 = KEY_NONE, b2 = KEY_NONE;
-            const uint32_t scr_addr = smem_u32(sm.scratch[warp]);
+            const uint32_t scr_addr = smem_u32(sm.scratch[G::REDUX ? 0 : warp]);
             const uint32_t rbase = static_cast<uint32_t>(qt0 + tile * MQ + quarter * 32);
             for (int s = 0; s < n_stage; ++s) {
                 const int acc = acc_of(s, tile, n_tiles), use = acc_use(s, n_tiles);
                 const int rows = stage_rows(s);
                 mbar_wait(&sm.d_full[acc], use & 1);
                 tc_fence_after();
-                uint32_t v[2][32];
-                tmem_ld64_packed(tmem + lane_base + acc * NT, v[0]);
-                tmem_ld64_packed(tmem + lane_base + acc * NT + 64, v[1]);
-                tmem_wait_ld();
-                tc_fence_before();
-                mbar_arrive(&sm.d_empty[acc]);  // the accumulator may be overwritten
                 const uint32_t jstage = static_cast<uint32_t>(p.t_index_base + tb + s * NT);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (h == 1 && rows <= 64) break;  // warp-uniform: the second half holds no valid train row
-                    if (COL) {
+#pragma unroll 1
+                for (int h = 0; h < G::NCH; ++h) {
+                    const bool last = (h == G::NCH - 1) || (rows <= 64 * (h + 1));  // warp-uniform
+                    uint32_t v[32];
+                    tmem_ld64_packed(tmem + lane_base + acc * NT + 64 * h, v);
+                    tmem_wait_ld();
+                    if (last) {  // every column this stage needs has been read: the accumulator may be overwritten
+                        tc_fence_before();
+                        mbar_arrive(&sm.d_empty[acc]);
+                    }
+                    if (COL && !G::REDUX) {
                         // scratch[row = lane][32 words], 16-byte chunk i stored at chunk i ^ (lane & 7):
                         // conflict-free both for these row-wise STS.128 and for the column-wise LDS.32 below
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const uint32_t a = scr_addr + lane * 128 + ((i ^ (lane & 7)) << 4);
-                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v[h][4 * i]),
-                                         "r"(v[h][4 * i + 1]), "r"(v[h][4 * i + 2]), "r"(v[h][4 * i + 3])
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v[4 * i]), "r"(v[4 * i + 1]),
+                                         "r"(v[4 * i + 2]), "r"(v[4 * i + 3])
                                          : "memory");
                         }
                     }
-                    // ---- row minima: key16 = acc + column = (d << 7) | column-in-half ----
+                    // ---- row minima: key16 = acc + column = (d << 7) | column-in-chunk ----
                     const uint32_t jh = jstage + 64u * h;
                     if (!TOP2) {
                         uint32_t m = 0xFFFFFFFFu;
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
-                            const uint32_t k0 = add_imad(v[h][j], one, ((2u * j + 1u) << 16) | (2u * j));
-                            const uint32_t k1 = add_imad(v[h][j + 1], one, ((2u * j + 3u) << 16) | (2u * j + 2u));
+                            const uint32_t k0 = add_imad(v[j], one, ((2u * j + 1u) << 16) | (2u * j));
+                            const uint32_t k1 = add_imad(v[j + 1], one, ((2u * j + 3u) << 16) | (2u * j + 2u));
                             m = __vimin3_u16x2(m, k0, k1);
                         }
                         const uint32_t k16 = min(m & 0xFFFFu, m >> 16);
@@ -344,7 +361,7 @@ __global__ void __launch_bounds__(THREADS, 1) hamming_mma_kernel(const HammingPa
                         uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;  // per 16-bit half: best and second best
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const uint32_t k = add_imad(v[h][j], one, ((2u * j + 1u) << 16) | (2u * j));
+                            const uint32_t k = add_imad(v[j], one, ((2u * j + 1u) << 16) | (2u * j));
                             m2 = __vminu2(m2, __vmaxu2(m1, k));
                             m1 = __vminu2(m1, k);
                         }
@@ -355,24 +372,36 @@ __global__ void __launch_bounds__(THREADS, 1) hamming_mma_kernel(const HammingPa
                                         b1, b2);
                     }
                     if (COL) {
-                        // ---- column minima over this warp's 32 query rows: lane = train column pair ----
-                        __syncwarp();
+                        // ---- column minima over this warp's 32 query rows; lane l ends up with the packed
+                        //      minima of train columns 2l, 2l+1 of the chunk: key16 = (d << 5) | row-in-warp ----
                         uint32_t m = 0xFFFFFFFFu;
+                        if (G::REDUX) {
+                            // acc = d << 7, so acc >> 2 per half (bits 0-1 of every half are zero: both halves
+                            // shift together).  redux.min over the packed word is exact for its HIGH half.
+                            const uint32_t lane2 = (static_cast<uint32_t>(lane) << 16) | lane;
 #pragma unroll
-                        for (int r = 0; r < 32; r += 2) {
-                            uint32_t x0, x1;
-                            const uint32_t a0 = scr_addr + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2));
-                            const uint32_t a1 =
-                                scr_addr + (r + 1) * 128 + ((((lane >> 2) ^ ((r + 1) & 7)) << 4) | ((lane & 3) << 2));
-                            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x0) : "r"(a0) : "memory");
-                            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x1) : "r"(a1) : "memory");
-                            // key16 = (d << 5) | row: acc = d << 7, so acc >> 2 per half; both halves shift
-                            // together because bits 0-1 of every half are zero
-                            const uint32_t k0 = add_imad(x0 >> 2, one, (static_cast<uint32_t>(r) << 16) | r);
-                            const uint32_t k1 = add_imad(x1 >> 2, one, (static_cast<uint32_t>(r + 1) << 16) | (r + 1));
-                            m = __vimin3_u16x2(m, k0, k1);
+                            for (int j = 0; j < 32; ++j) {
+                                const uint32_t k = add_imad(v[j] >> 2, one, lane2);
+                                const uint32_t hi = __reduce_min_sync(0xFFFFFFFFu, k);
+                                const uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, __byte_perm(k, 0, 0x1032));
+                                if (lane == j) m = __byte_perm(hi, lo, 0x3276);  // [hi.hi16 | lo.hi16]
+                            }
+                        } else {
+                            __syncwarp();
+#pragma unroll
+                            for (int r = 0; r < 32; r += 2) {
+                                uint32_t x0, x1;
+                                const uint32_t a0 = scr_addr + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2));
+                                const uint32_t a1 =
+                                    scr_addr + (r + 1) * 128 + ((((lane >> 2) ^ ((r + 1) & 7)) << 4) | ((lane & 3) << 2));
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x0) : "r"(a0) : "memory");
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x1) : "r"(a1) : "memory");
+                                const uint32_t k0 = add_imad(x0 >> 2, one, (static_cast<uint32_t>(r) << 16) | r);
+                                const uint32_t k1 = add_imad(x1 >> 2, one, (static_cast<uint32_t>(r + 1) << 16) | (r + 1));
+                                m = __vimin3_u16x2(m, k0, k1);
+                            }
+                            __syncwarp();  // the scratch is rewritten by the next chunk / stage
                         }
-                        __syncwarp();  // the scratch is rewritten by the next half / stage
 #pragma unroll
                         for (int hh = 0; hh < 2; ++hh) {
                             const uint32_t k16 = hh ? (m >> 16) : (m & 0xFFFFu);
@@ -381,6 +410,7 @@ __global__ void __launch_bounds__(THREADS, 1) hamming_mma_kernel(const HammingPa
                                 atomicMin(&sm.colmin[tile][s & 1][c], ((k16 >> 5) << KEY_IDX_BITS) + rbase + (k16 & 31u));
                         }
                     }
+                    if (last) break;
                 }
                 if (COL) {
                     // the 4 warps of this query tile merge: one global atomicMin per train row, tile and stage
@@ -388,9 +418,9 @@ __global__ void __launch_bounds__(THREADS, 1) hamming_mma_kernel(const HammingPa
                         asm volatile("bar.sync 1, 128;" ::: "memory");
                     else
                         asm volatile("bar.sync 2, 128;" ::: "memory");
-                    if (row_in_tile < rows) {
-                        atomicMin(p.col_keys + t_row0 + tb + s * NT + row_in_tile, sm.colmin[tile][s & 1][row_in_tile]);
-                        sm.colmin[tile][s & 1][row_in_tile] = KEY_NONE;  // reused in stage s + 2, after the barrier of s + 1
+                    for (int c = row_in_tile; c < rows; c += 128) {
+                        atomicMin(p.col_keys + t_row0 + tb + s * NT + c, sm.colmin[tile][s & 1][c]);
+                        sm.colmin[tile][s & 1][c] = KEY_NONE;  // reused in stage s + 2, after the barrier of s + 1
                     }
                 }
             }
@@ -484,20 +514,20 @@ __global__ void __launch_bounds__(THREADS, 1) hamming_mma_kernel(const HammingPa
             const int b = s % NB;
             mbar_wait(&sm.b_full[b], (s / NB) & 1);
             if (leader && s + NB < n_stage) issue_tma(s + NB);  // every expander has finished reading raw[b]
-            const uint64_t desc_b = desc0 + static_cast<uint64_t>(b * (B_STAGE >> 4));
+            const uint64_t desc_b = desc0 + static_cast<uint64_t>(b * (G::B_STAGE >> 4));
             for (int t = 0; t < n_tiles; ++t) {
                 const int acc = acc_of(s, t, n_tiles), use = acc_use(s, n_tiles);
                 mbar_wait(&sm.d_empty[acc], (use & 1) ^ 1);
                 tc_fence_after();
                 if (leader) {
-                    const uint32_t d_addr = tmem + acc * NT, a_addr = tmem + TMEM_A + t * 128;
+                    const uint32_t d_addr = tmem + acc * NT, a_addr = tmem + G::TMEM_A + t * 128;
                     if (n_k == 16) {
 #pragma unroll
                         for (int k = 0; k < 16; ++k)
-                            umma_i8_ts(d_addr, a_addr + 8 * k, desc_b + static_cast<uint64_t>(k * (2 * LBO >> 4)), kIdesc, k > 0);
+                            umma_i8_ts(d_addr, a_addr + 8 * k, desc_b + static_cast<uint64_t>(k * (2 * LBO >> 4)), G::IDESC, k > 0);
                     } else {
                         for (int k = 0; k < n_k; ++k)
-                            umma_i8_ts(d_addr, a_addr + 8 * k, desc_b + static_cast<uint64_t>(k * (2 * LBO >> 4)), kIdesc, k > 0);
+                            umma_i8_ts(d_addr, a_addr + 8 * k, desc_b + static_cast<uint64_t>(k * (2 * LBO >> 4)), G::IDESC, k > 0);
                     }
                     if (t == n_tiles - 1) umma_commit(&sm.b_empty[b]);
                     umma_commit(&sm.d_full[acc]);
@@ -513,17 +543,41 @@ __global__ void __launch_bounds__(THREADS, 1) hamming_mma_kernel(const HammingPa
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 
-template <bool COL, bool TOP2>
+template <class G, bool COL, bool TOP2>
 int launch_mma(const HammingParams &p, dim3 grid, cudaStream_t stream)
 {
     static bool configured = false;  // per instantiation; racing threads set the same value
+    constexpr int smem = static_cast<int>(sizeof(typename G::Smem));
+    static_assert(smem <= 227 * 1024, "shared memory per CTA");
     if (!configured) {
-        SLAMFE_CUDA_OK(cudaFuncSetAttribute(hamming_mma_kernel<COL, TOP2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(sizeof(Smem))));
+        SLAMFE_CUDA_OK(cudaFuncSetAttribute(hamming_mma_kernel<G, COL, TOP2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    hamming_mma_kernel<COL, TOP2><<<grid, THREADS, sizeof(Smem), stream>>>(p);
+    hamming_mma_kernel<G, COL, TOP2><<<grid, G::THREADS, smem, stream>>>(p);
     return launch_status();
+}
+
+template <class G>
+int run_geometry(HammingParams p, int n_problems, int max_nq, int max_nt, bool top2, cudaStream_t stream)
+{
+    // One CTA per SM (all 512 TMEM columns).  When the query tiles alone do not fill the machine the train
+    // set is cut into slices (grid.y); their results merge exactly through atomicMin / the CAS pair merge,
+    // as in the INT kernel.
+    const int sms = sm_count();
+    const int stages_total = (max_nt + G::NT - 1) / G::NT;
+    const long long ctas = static_cast<long long>((max_nq + G::CQ - 1) / G::CQ) * n_problems;
+    int slices = 1;
+    if (ctas < 2LL * sms) {
+        const int want = static_cast<int>((2LL * sms + ctas - 1) / ctas);
+        slices = max(1, min(want, stages_total / 4));
+    }
+    const int stages_per_slice = (stages_total + slices - 1) / slices;
+    p.t_slice = stages_per_slice * G::NT;
+    const int n_slices = (stages_total + stages_per_slice - 1) / stages_per_slice;
+    const dim3 grid((max_nq + G::CQ - 1) / G::CQ, n_slices, n_problems);
+    if (grid.y > 65535u || grid.z > 65535u) return SLAMFE_ERANGE;
+    if (p.col_keys) return top2 ? launch_mma<G, true, true>(p, grid, stream) : launch_mma<G, true, false>(p, grid, stream);
+    return top2 ? launch_mma<G, false, true>(p, grid, stream) : launch_mma<G, false, false>(p, grid, stream);
 }
 
 }  // namespace
@@ -532,24 +586,16 @@ bool hamming_mma_supports(int desc_bytes) { return desc_bytes >= 1 && desc_bytes
 
 int run_hamming_mma(HammingParams p, int n_problems, int max_nq, int max_nt, bool top2, cudaStream_t stream)
 {
-    // One CTA per SM (all 512 TMEM columns).  When the query tiles alone do not fill the machine the train
-    // set is cut into slices (grid.y); their results merge exactly through atomicMin / the CAS pair merge,
-    // as in the INT kernel.
-    const int sms = sm_count();
-    const int stages_total = (max_nt + NT - 1) / NT;
-    const long long ctas = static_cast<long long>((max_nq + CQ - 1) / CQ) * n_problems;
-    int slices = 1;
-    if (ctas < 2LL * sms) {
-        const int want = static_cast<int>((2LL * sms + ctas - 1) / ctas);
-        slices = max(1, min(want, stages_total / 4));
+    // SLAMFE_MMA_GEOMETRY (development A/B, read once): 0 = <2,128> transpose, 1 = <2,128> redux, 2 = <1,192> redux
+    static const int geometry = [] {
+        const char *v = getenv("SLAMFE_MMA_GEOMETRY");
+        return v && *v ? atoi(v) : kDefaultGeometry;
+    }();
+    switch (geometry) {
+        case 1: return run_geometry<Geo<2, 128, true>>(p, n_problems, max_nq, max_nt, top2, stream);
+        case 2: return run_geometry<Geo<1, 192, true>>(p, n_problems, max_nq, max_nt, top2, stream);
+        default: return run_geometry<Geo<2, 128, false>>(p, n_problems, max_nq, max_nt, top2, stream);
     }
-    const int stages_per_slice = (stages_total + slices - 1) / slices;
-    p.t_slice = stages_per_slice * NT;
-    const int n_slices = (stages_total + stages_per_slice - 1) / stages_per_slice;
-    const dim3 grid((max_nq + CQ - 1) / CQ, n_slices, n_problems);
-    if (grid.y > 65535u || grid.z > 65535u) return SLAMFE_ERANGE;
-    if (p.col_keys) return top2 ? launch_mma<true, true>(p, grid, stream) : launch_mma<true, false>(p, grid, stream);
-    return top2 ? launch_mma<false, true>(p, grid, stream) : launch_mma<false, false>(p, grid, stream);
 }
 
 }  // namespace slamfe

@@ -334,3 +334,45 @@ def test_real_akaze_descriptors_through_the_dropin_matchers(slamfe, golden):
     assert [[m.trainIdx for m in p] for p in knn] == g["knn_idx"].tolist()
     assert [[int(m.distance) for m in p] for p in knn] == g["knn_dist"].tolist()
     assert int(g["n_exact_ties"]) >= 0
+
+
+def test_tensor_core_and_int_kernels_agree_on_random_shapes(slamfe, oracle):
+    """Fuzz: the tcgen05 kernel (int8 contraction, packed 16-bit keys, spare-K popc / invalid-row markers) and
+    the INT kernel (XOR / carry-save POPC) must produce IDENTICAL key tables — rows, second neighbours and
+    column minima — on random sizes around every tile boundary (128 / 256 query rows, 64 / 128 train rows),
+    every descriptor width the tensor kernel takes (1..63 bytes), padded strides, misaligned bases and heavy
+    duplication; a sample is also checked against the C oracle."""
+    import torch
+    from slamfe import ops
+    rng = np.random.default_rng(97)
+    edges = [1, 2, 31, 63, 64, 65, 127, 128, 129, 191, 192, 193, 255, 256, 257, 383, 384, 385, 511, 513]
+    for case in range(70):
+        nq = int(rng.choice(edges)) if rng.random() < 0.6 else int(rng.integers(1, 900))
+        nt = int(rng.choice(edges)) if rng.random() < 0.6 else int(rng.integers(1, 900))
+        db = int(rng.integers(1, 64)) if case % 3 else 61
+        stride = db if rng.random() < 0.5 else int(rng.integers(db, 65))
+        lead_q, lead_t = int(rng.integers(0, 3)), int(rng.integers(0, 3))
+        Q = rng.integers(0, 256, (nq + lead_q, stride), dtype=np.uint8)
+        T = rng.integers(0, 256, (nt + lead_t, stride), dtype=np.uint8)
+        if rng.random() < 0.5 and nt > 1:   # duplicates: ties on distance, decided by index
+            T[rng.integers(lead_t, lead_t + nt, nt // 2)] = T[rng.integers(lead_t, lead_t + nt, nt // 2)]
+        if rng.random() < 0.3:              # near-identical rows: small distances incl. d = 0
+            T[lead_t:lead_t + min(nq, nt), :db] = Q[lead_q:lead_q + min(nq, nt), :db]
+        qd, td = torch.from_numpy(Q).cuda()[lead_q:], torch.from_numpy(T).cuda()[lead_t:]
+        cols, best_only = bool(rng.random() < 0.6), bool(rng.random() < 0.5)
+        base = int(rng.integers(0, 1000)) if rng.random() < 0.3 else 0
+        res = {}
+        for kind in ("mma", "int"):
+            old = ops.set_matcher_kernel(kind)
+            try:
+                res[kind] = ops.hamming_top2(qd, td, desc_bytes=db, want_cols=cols, t_index_base=base, best_only=best_only)
+            finally:
+                ops.set_matcher_kernel(old)
+        tag = (case, nq, nt, db, stride, cols, best_only, base)
+        assert torch.equal(res["mma"][0], res["int"][0]), tag
+        if cols:
+            assert torch.equal(res["mma"][1], res["int"][1]), tag
+        if case % 7 == 0 and not best_only:
+            oi, od = oracle.knn2(np.ascontiguousarray(Q[lead_q:, :db]), np.ascontiguousarray(T[lead_t:, :db]))
+            ki, kd = ops.keys_to_numpy(res["mma"][0].cpu().numpy())
+            assert np.array_equal(ki, np.where(oi >= 0, oi + base, -1)) and np.array_equal(kd, od), tag

@@ -47,6 +47,7 @@
 // Facts pinned on a B200 by scripts/probe_tcgen05.cu (profiles/r02_probe_tcgen05.log): descriptor
 // field meaning (LBO = K-chunk stride, SBO = 8-row stride), TMEM A layout (4 K-bytes per column),
 // exactness, MMA cycles at the issue floor, TMEM read bandwidth.
+#include <cstdlib>
 #include "common.cuh"
 #include "hamming_params.cuh"
 
@@ -67,7 +68,7 @@ constexpr int kDefaultGeometry = 0;
 //             ~83 + 0.2 N cycles on this part: 109 at N = 128, 122 at N = 192) at twice the expansion work
 //             per pair; the accumulators alternate between stages; column minima by redux only (no room
 //             for the transpose scratch next to 2 x 96 KB of B stages)
-template <int QT_, int NT_, bool REDUX_>
+template <int QT_, int NT_, bool REDUX_, int EXP_SPLIT_ = 1>
 struct Geo {
     static constexpr int QT = QT_, NT = NT_;
     static constexpr bool REDUX = REDUX_;
@@ -76,9 +77,12 @@ struct Geo {
     static constexpr int B_STAGE = KCH * LBO;
     static constexpr int NB = 2;                     // B (and raw) stages
     static constexpr int RAW_STAGE = NT * SLAMFE_MAX_DESC_BYTES + 16;
-    static constexpr int N_EPI_WARPS = 4 * QT, N_EXP_WARPS = NT / 32;
+    static constexpr int EXP_SPLIT = EXP_SPLIT_;       // expander threads per train row (2 measured slower than 1:
+                                                       // the expansion is bound by shared pipes, not by latency)
+    static constexpr int N_EPI_WARPS = 4 * QT, N_EXP_WARPS = NT / 32 * EXP_SPLIT;
     static constexpr int MMA_WARP = N_EPI_WARPS + N_EXP_WARPS;
-    static constexpr int THREADS = (MMA_WARP + 1) * 32;
+    static constexpr int TMA_WARP = MMA_WARP + 1;
+    static constexpr int THREADS = (TMA_WARP + 1) * 32;
     static constexpr int NCH = NT / 64;              // 64-column chunks of an accumulator
     static constexpr uint32_t TMEM_A = 2 * NT;       // first column of the query tiles
     static constexpr uint32_t IDESC = (2u << 4)                                 // D format S32
@@ -101,6 +105,24 @@ struct Geo {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Wait with back-off for waiters that have slack (epilogue on d_full, TMA producer): a plain try_wait spin
+// loop competes for issue slots with the expander warp on the same scheduler (measured: the expansion of a
+// stage took 2350 cycles with spinning neighbours, the MMAs it feeds 2048).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity, unsigned ns)
+{
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(ns);
+    }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -269,7 +291,7 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
     auto stage_tma_rows = [&](int s) {
         if (reinterpret_cast<uintptr_t>(stage_src(s)) & 15) return 0;
         const int rows = stage_rows(s);
-        return rows - rows % p.tma_quantum;
+        return rows & ~(p.tma_quantum - 1);   // the quantum is a power of two (16 / gcd(stride, 16))
     };
 
     if (warp < N_EPI_WARPS) {
@@ -321,7 +343,7 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
             for (int s = 0; s < n_stage; ++s) {
                 const int acc = acc_of(s, tile, n_tiles), use = acc_use(s, n_tiles);
                 const int rows = stage_rows(s);
-                mbar_wait(&sm.d_full[acc], use & 1);
+                mbar_wait_relaxed(&sm.d_full[acc], use & 1, 128);
                 tc_fence_after();
                 const uint32_t jstage = static_cast<uint32_t>(p.t_index_base + tb + s * NT);
 #pragma unroll 1
@@ -445,67 +467,81 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
         }
     } else if (warp < MMA_WARP) {
         // ============================== expander warps ==============================
-        const int r = tid - N_EPI_WARPS * 32;   // this thread's train row within every stage
+        constexpr int WPT = W / G::EXP_SPLIT;                // input words per thread
+        const int e = tid - N_EPI_WARPS * 32;
+        const int r = e % NT;                                // this thread's train row within every stage
+        const int k_lo = (e / NT) * WPT;                     // ... and its share of the row's 16 input words
         uint32_t mul[8];
 #pragma unroll
         for (int s = 0; s < 8; ++s) mul[s] = (1u << (7 - s)) * static_cast<uint32_t>(p.desc_bytes > 0);
+        const uint32_t last_mask = word_mask(p.desc_bytes, ws);   // the word that holds the descriptor's tail + the spare byte
         for (int s = 0; s < n_stage; ++s) {
             const int b = s % NB;
             const uint32_t ph = (s / NB) & 1;
             const int rows = stage_rows(s), trows = stage_tma_rows(s);
             if (trows > 0) mbar_wait(&sm.raw_full[b], ph);
             mbar_wait(&sm.b_empty[b], ph ^ 1);
-            uint32_t w[W];
+            uint32_t w[WPT];
             if (r >= rows) {
 #pragma unroll
-                for (int k = 0; k < W; ++k) w[k] = 0;
+                for (int k = 0; k < WPT; ++k) w[k] = 0;
             } else if (r < trows) {
-                const int o = r * p.t_stride;  // any alignment: LDS.32 + funnel shift
+                const int o = r * p.t_stride + 4 * k_lo;  // any alignment: LDS.32 + funnel shift
                 const uint32_t *raw32 = reinterpret_cast<const uint32_t *>(sm.raw[b]) + (o >> 2);
                 const int sh = (o & 3) * 8;
                 uint32_t lo = raw32[0];
 #pragma unroll
-                for (int k = 0; k < W; ++k) {
+                for (int k = 0; k < WPT; ++k) {
                     // words past the descriptor hold stale bytes of the staging buffer (never past its end:
-                    // RAW_STAGE has 16 bytes of slack); word_mask clears them
+                    // RAW_STAGE has 16 bytes of slack); they are masked / skipped below
                     const uint32_t hi = raw32[k + 1];
-                    w[k] = __funnelshift_r(lo, hi, sh) & word_mask(p.desc_bytes, k);
+                    w[k] = __funnelshift_r(lo, hi, sh);
                     lo = hi;
                 }
             } else {  // rows the bulk copy could not take (misaligned source / tail): read global memory
-                load_desc_global(stage_src(s) + static_cast<size_t>(r) * p.t_stride, p.desc_bytes, w);
+                uint32_t wf[W];
+                load_desc_global(stage_src(s) + static_cast<size_t>(r) * p.t_stride, p.desc_bytes, wf);
+#pragma unroll
+                for (int k = 0; k < WPT; ++k) w[k] = wf[(G::EXP_SPLIT == 1 ? 0 : k_lo) + k];
             }
             uint8_t *dst = sm.b[b] + r * 16;
             // valid rows carry 0x80 on the four popc positions, invalid rows on the four marker positions
             const uint32_t spare_lo = (r < rows) ? 0x80000000u : 0u, spare_hi = (r < rows) ? 0u : 0x80000000u;
+            auto put = [&](int kk, uint32_t wk, uint32_t slo, uint32_t shi) {
+                uint8_t *d = dst + 2 * kk * LBO;
+                *reinterpret_cast<uint4 *>(d) = make_uint4(spread80(wk, mul[0]) | slo, spread80(wk, mul[1]) | slo,
+                                                           spread80(wk, mul[2]) | slo, spread80(wk, mul[3]) | slo);
+                *reinterpret_cast<uint4 *>(d + LBO) = make_uint4(spread80(wk, mul[4]) | shi, spread80(wk, mul[5]) | shi,
+                                                                 spread80(wk, mul[6]) | shi, spread80(wk, mul[7]) | shi);
+            };
+            if (n_k == W) {   // descriptors of 60..63 bytes (AKAZE: 61): word 15 is the tail word, no per-word tests
 #pragma unroll
-            for (int k = 0; k < W; ++k) {
-                if (k < n_k) {
-                    const uint32_t slo = (k == ws) ? spare_lo : 0u, shi = (k == ws) ? spare_hi : 0u;
-                    uint8_t *d = dst + 2 * k * LBO;
-                    *reinterpret_cast<uint4 *>(d) = make_uint4(spread80(w[k], mul[0]) | slo, spread80(w[k], mul[1]) | slo,
-                                                               spread80(w[k], mul[2]) | slo, spread80(w[k], mul[3]) | slo);
-                    *reinterpret_cast<uint4 *>(d + LBO) =
-                        make_uint4(spread80(w[k], mul[4]) | shi, spread80(w[k], mul[5]) | shi,
-                                   spread80(w[k], mul[6]) | shi, spread80(w[k], mul[7]) | shi);
+                for (int k = 0; k < WPT; ++k) {
+                    const bool tail = (G::EXP_SPLIT == 1) ? (k == W - 1) : (k == WPT - 1 && k_lo + WPT == W);
+                    if (tail)
+                        put(k_lo + k, w[k] & last_mask, spare_lo, spare_hi);
+                    else
+                        put(k_lo + k, w[k], 0u, 0u);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < WPT; ++k) {
+                    const int kk = k_lo + k;
+                    if (kk < ws)
+                        put(kk, w[k], 0u, 0u);
+                    else if (kk == ws)
+                        put(kk, w[k] & last_mask, spare_lo, spare_hi);
                 }
             }
             fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(&sm.b_full[b]);
         }
-    } else {
-        // ============================== TMA + MMA issue (whole warp, one elected lane issues) ===========
+    } else if (warp == MMA_WARP) {
+        // ============================== MMA issue (whole warp, one elected lane issues) ===========
+        // This thread does nothing but wait and issue: tcgen05.mma blocks when the tensor pipe's queue is
+        // full, so every cycle it spends elsewhere (TMA bookkeeping used to cost ~800 cycles per stage here)
+        // is a cycle the queue can run dry.
         const bool leader = elect_one();
-        auto issue_tma = [&](int s) {
-            const int trows = stage_tma_rows(s);
-            if (trows > 0) {
-                const uint32_t bytes = static_cast<uint32_t>(trows) * p.t_stride;
-                mbar_arrive_expect_tx(&sm.raw_full[s % NB], bytes);
-                tma_load_1d(sm.raw[s % NB], stage_src(s), bytes, &sm.raw_full[s % NB]);
-            }
-        };
-        if (leader)
-            for (int s = 0; s < min(NB, n_stage); ++s) issue_tma(s);
         mbar_wait(&sm.a_ready, 0);
         tc_fence_after();
         // K-step k of a B stage: descriptor start address advances by 2 chunks = 2 * LBO bytes
@@ -513,7 +549,6 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
         for (int s = 0; s < n_stage; ++s) {
             const int b = s % NB;
             mbar_wait(&sm.b_full[b], (s / NB) & 1);
-            if (leader && s + NB < n_stage) issue_tma(s + NB);  // every expander has finished reading raw[b]
             const uint64_t desc_b = desc0 + static_cast<uint64_t>(b * (G::B_STAGE >> 4));
             for (int t = 0; t < n_tiles; ++t) {
                 const int acc = acc_of(s, t, n_tiles), use = acc_use(s, n_tiles);
@@ -533,6 +568,20 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                     umma_commit(&sm.d_full[acc]);
                 }
                 __syncwarp();
+            }
+        }
+    } else {
+        // ============================== TMA producer (one elected lane) ===========
+        // raw[b] is free again once every expander has arrived on b_full[b] for the stage that used it
+        if (elect_one()) {
+            for (int s = 0; s < n_stage; ++s) {
+                if (s >= NB) mbar_wait_relaxed(&sm.b_full[s % NB], ((s - NB) / NB) & 1, 256);
+                const int trows = stage_tma_rows(s);
+                if (trows > 0) {
+                    const uint32_t bytes = static_cast<uint32_t>(trows) * p.t_stride;
+                    mbar_arrive_expect_tx(&sm.raw_full[s % NB], bytes);
+                    tma_load_1d(sm.raw[s % NB], stage_src(s), bytes, &sm.raw_full[s % NB]);
+                }
             }
         }
     }
@@ -586,7 +635,8 @@ bool hamming_mma_supports(int desc_bytes) { return desc_bytes >= 1 && desc_bytes
 
 int run_hamming_mma(HammingParams p, int n_problems, int max_nq, int max_nt, bool top2, cudaStream_t stream)
 {
-    // SLAMFE_MMA_GEOMETRY (development A/B, read once): 0 = <2,128> transpose, 1 = <2,128> redux, 2 = <1,192> redux
+    // SLAMFE_MMA_GEOMETRY (development A/B, read once): 0 = <2,128> transpose, 1 = <2,128> redux, 2 = <1,192> redux,
+    // 3 = <2,128> transpose with two expander threads per train row
     static const int geometry = [] {
         const char *v = getenv("SLAMFE_MMA_GEOMETRY");
         return v && *v ? atoi(v) : kDefaultGeometry;
@@ -594,6 +644,7 @@ int run_hamming_mma(HammingParams p, int n_problems, int max_nq, int max_nt, boo
     switch (geometry) {
         case 1: return run_geometry<Geo<2, 128, true>>(p, n_problems, max_nq, max_nt, top2, stream);
         case 2: return run_geometry<Geo<1, 192, true>>(p, n_problems, max_nq, max_nt, top2, stream);
+        case 3: return run_geometry<Geo<2, 128, false, 2>>(p, n_problems, max_nq, max_nt, top2, stream);
         default: return run_geometry<Geo<2, 128, false>>(p, n_problems, max_nq, max_nt, top2, stream);
     }
 }

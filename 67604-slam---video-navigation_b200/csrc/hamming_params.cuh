@@ -38,13 +38,21 @@ __device__ __forceinline__ void load_desc_global(const uint8_t *src, int desc_by
             w[k] = v;
         }
     } else {
+        // misaligned row (cv2's 61-byte stride): aligned 32-bit loads of the words that hold at least one
+        // descriptor byte + funnel shifts (64 byte loads per row made the CTA prologue latency-bound).  A word
+        // is only read when it contains a valid byte, so nothing outside the allocation's granule is touched.
+        const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+        const uint32_t *s32 = reinterpret_cast<const uint32_t *>(a & ~static_cast<uintptr_t>(3));
+        const int sh = static_cast<int>(a & 3) * 8;
+        const int n_need = (static_cast<int>(a & 3) + desc_bytes + 3) >> 2;   // aligned words holding descriptor bytes
+        uint32_t lo = __ldg(s32);
 #pragma unroll
         for (int k = 0; k < W; ++k) {
-            uint32_t v = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-                if (4 * k + b < desc_bytes) v |= static_cast<uint32_t>(__ldg(src + 4 * k + b)) << (8 * b);
-            w[k] = v;
+            const uint32_t hi = (k + 1 < n_need) ? __ldg(s32 + k + 1) : 0u;
+            const int rem = desc_bytes - 4 * k;
+            const uint32_t m = rem >= 4 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << (8 * rem)) - 1u));
+            w[k] = __funnelshift_r(lo, hi, sh) & m;
+            lo = hi;
         }
     }
 }

@@ -240,6 +240,174 @@ __global__ void __launch_bounds__(128) mma_rate(int N, uint32_t idesc, int ts, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// rate3: the issue loop of the shipped matcher — one elected lane, 16 unrolled TS-mode MMAs per group with
+// precomputed descriptors, `nacc` accumulators used round robin per group — to separate the cost of the
+// tcgen05.mma itself from the cost of a slow issuing thread (rate / rate2 above)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool elect_one_lane()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__global__ void __launch_bounds__(128) mma_rate_tight(int N, uint32_t idesc, int groups, int nacc, long long *cycles)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < N * 512 / 16; i += 128) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tb = tmem_base_s;
+    if (warp == 1) {
+        const bool leader = elect_one_lane();
+        const uint32_t lbo = N * 16;
+        const uint64_t desc0 = make_desc(smem_u32(smem), lbo, 128);
+        const uint32_t a0 = tb + 512 - 128;            // A tile in the last 128 columns
+        const long long t0 = clock64();
+        for (int g = 0; g < groups; ++g) {
+            const uint32_t dd = tb + (g % nacc) * N;
+            if (leader) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    mma_ts<0>(dd, a0 + 8 * k, desc0 + (uint64_t)(k * (2 * lbo >> 4)), idesc, k > 0);
+            }
+            __syncwarp();
+        }
+        if (leader) umma_commit(&bar);
+        __syncwarp();
+        mbar_wait(&bar, 0);
+        const long long t1 = clock64();
+        if (leader) cycles[blockIdx.x] = t1 - t0;
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+static uint32_t make_idesc(int kind, int a_signed, int b_signed, int M, int N);
+static void run_rate_tight(int N, int nacc, int sms)
+{
+    const int groups = 512;
+    long long *dc;
+    CK(cudaMalloc(&dc, sizeof(long long) * sms));
+    const int smem = N * 512;
+    const uint32_t idesc = make_idesc(0, 1, 0, 128, N);
+    CK(cudaFuncSetAttribute(mma_rate_tight, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int rep = 0; rep < 2; ++rep) {
+        mma_rate_tight<<<sms, 128, smem>>>(N, idesc, groups, nacc, dc);
+        CK(cudaDeviceSynchronize());
+    }
+    std::vector<long long> c(sms);
+    CK(cudaMemcpy(c.data(), dc, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (auto v : c) mx = v > mx ? v : mx;
+    printf("rate3 (tight issue, TS, i8) N=%d nacc=%d : %.1f cycles/MMA, %.2f pairs/clk/SM (K=512)\n", N, nacc,
+           (double)mx / (groups * 16), 128.0 * N / ((double)mx / groups));
+    cudaFree(dc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// rate4: the tight MMA loop of rate3 (N = 128, two accumulators) while OTHER warps of the CTA keep a second
+// resource busy: mode 1 = tcgen05.ld of accumulator columns (what the epilogue does), mode 2 = STS.128
+// streams into shared memory (what the expanders do), mode 3 = both.  What slows the tensor pipe?
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(416) mma_rate_contended(int N, uint32_t idesc, int groups, int mode, int n_ld_warps,
+                                                           int n_st_warps, long long *cycles, uint32_t *sink)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ volatile int stop;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < N * 512 / 16; i += 416) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        stop = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tb = tmem_base_s;
+    if (warp == 12) {
+        const bool leader = elect_one_lane();
+        const uint32_t lbo = N * 16;
+        const uint64_t desc0 = make_desc(smem_u32(smem), lbo, 128);
+        const uint32_t a0 = tb + 512 - 128;
+        const long long t0 = clock64();
+        for (int g = 0; g < groups; ++g) {
+            const uint32_t dd = tb + (g & 1) * N;
+            if (leader) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    mma_ts<0>(dd, a0 + 8 * k, desc0 + (uint64_t)(k * (2 * lbo >> 4)), idesc, k > 0);
+            }
+            __syncwarp();
+        }
+        if (leader) umma_commit(&bar);
+        __syncwarp();
+        mbar_wait(&bar, 0);
+        const long long t1 = clock64();
+        if (leader) { cycles[blockIdx.x] = t1 - t0; stop = 1; }
+    } else if (warp < n_ld_warps && (mode & 1)) {
+        uint32_t acc = 0;
+        while (!stop) {
+            uint32_t v[32];
+            LD32(tb + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 64, v);
+            wait_ld();
+            for (int j = 0; j < 32; ++j) acc ^= v[j];
+        }
+        sink[blockIdx.x * 416 + tid] = acc;
+    } else if (warp >= 8 && warp < 8 + n_st_warps && (mode & 2)) {
+        uint8_t *dst = smem + N * 512 + (warp - 8) * 16384 + lane * 16;   // private 16 KB per warp
+        uint32_t x = tid;
+        while (!stop) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(dst + k * 512)), "r"(x), "r"(x + 1),
+                             "r"(x + 2), "r"(x + 3) : "memory");
+            ++x;
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+static void run_rate_contended(int mode, int n_ld, int n_st, int sms)
+{
+    const int N = 128, groups = 512;
+    long long *dc; uint32_t *sink;
+    CK(cudaMalloc(&dc, sizeof(long long) * sms));
+    CK(cudaMalloc(&sink, 4 * sms * 416));
+    const int smem = N * 512 + 4 * 16384;
+    const uint32_t idesc = make_idesc(0, 1, 0, 128, N);
+    CK(cudaFuncSetAttribute(mma_rate_contended, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int rep = 0; rep < 2; ++rep) {
+        mma_rate_contended<<<sms, 416, smem>>>(N, idesc, groups, mode, n_ld, n_st, dc, sink);
+        CK(cudaDeviceSynchronize());
+    }
+    std::vector<long long> c(sms);
+    CK(cudaMemcpy(c.data(), dc, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (auto v : c) mx = v > mx ? v : mx;
+    printf("rate4 N=128 mode=%d (ld warps %d, st warps %d): %.1f cycles/MMA\n", mode, (mode & 1) ? n_ld : 0,
+           (mode & 2) ? n_st : 0, (double)mx / (groups * 16));
+    cudaFree(dc); cudaFree(sink);
+}
+
+// ------------------------------------------------------------------------------------------------
 // ldtm: nwarps warps read 32 lanes x 32 columns per instruction, `batch` loads per wait
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ldtm_rate(int iters, int batch, long long *cycles, uint32_t *sink)
@@ -457,6 +625,18 @@ int main(int argc, char **argv)
             for (int nacc = 1; nacc <= 256 / N && nacc <= 4; nacc *= 2) run_rate(0, 1, N, sms, nacc);
         run_rate(0, 1, 192, sms, 1);
         run_rate(0, 0, 64, sms, 1); run_rate(0, 0, 64, sms, 4);
+        return 0;
+    }
+    if (!strcmp(mode, "rate3")) {
+        for (int N = 64; N <= 256; N += 64)
+            for (int nacc = 1; nacc <= 2 && nacc * N <= 384; ++nacc) run_rate_tight(N, nacc, sms);
+        return 0;
+    }
+    if (!strcmp(mode, "rate4")) {
+        run_rate_contended(0, 0, 0, sms);
+        run_rate_contended(1, 4, 0, sms); run_rate_contended(1, 8, 0, sms);
+        run_rate_contended(2, 0, 2, sms); run_rate_contended(2, 0, 4, sms);
+        run_rate_contended(3, 8, 4, sms);
         return 0;
     }
     if (!strcmp(mode, "ldtm")) {

@@ -346,16 +346,19 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                 mbar_wait_relaxed(&sm.d_full[acc], use & 1, 128);
                 tc_fence_after();
                 const uint32_t jstage = static_cast<uint32_t>(p.t_index_base + tb + s * NT);
-#pragma unroll 1
+                // read every 64-column chunk that holds a valid train row, then hand the accumulator back to
+                // the tensor core BEFORE folding: the MMAs of the next stage never wait for this warp's arithmetic
+                uint32_t vv[G::NCH][32];
+#pragma unroll
+                for (int h = 0; h < G::NCH; ++h)
+                    if (h == 0 || 64 * h < rows) tmem_ld64_packed(tmem + lane_base + acc * NT + 64 * h, vv[h]);
+                tmem_wait_ld();
+                tc_fence_before();
+                mbar_arrive(&sm.d_empty[acc]);
+#pragma unroll
                 for (int h = 0; h < G::NCH; ++h) {
-                    const bool last = (h == G::NCH - 1) || (rows <= 64 * (h + 1));  // warp-uniform
-                    uint32_t v[32];
-                    tmem_ld64_packed(tmem + lane_base + acc * NT + 64 * h, v);
-                    tmem_wait_ld();
-                    if (last) {  // every column this stage needs has been read: the accumulator may be overwritten
-                        tc_fence_before();
-                        mbar_arrive(&sm.d_empty[acc]);
-                    }
+                    if (h > 0 && 64 * h >= rows) break;  // warp-uniform
+                    uint32_t (&v)[32] = vv[h];
                     if (COL && !G::REDUX) {
                         // scratch[row = lane][32 words], 16-byte chunk i stored at chunk i ^ (lane & 7):
                         // conflict-free both for these row-wise STS.128 and for the column-wise LDS.32 below
@@ -432,7 +435,6 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                                 atomicMin(&sm.colmin[tile][s & 1][c], ((k16 >> 5) << KEY_IDX_BITS) + rbase + (k16 & 31u));
                         }
                     }
-                    if (last) break;
                 }
                 if (COL) {
                     // the 4 warps of this query tile merge: one global atomicMin per train row, tile and stage
@@ -541,20 +543,19 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
         // This thread does nothing but wait and issue: tcgen05.mma blocks when the tensor pipe's queue is
         // full, so every cycle it spends elsewhere (TMA bookkeeping used to cost ~800 cycles per stage here)
         // is a cycle the queue can run dry.
-        const bool leader = elect_one();
-        mbar_wait(&sm.a_ready, 0);
-        tc_fence_after();
-        // K-step k of a B stage: descriptor start address advances by 2 chunks = 2 * LBO bytes
-        const uint64_t desc0 = umma_desc(smem_u32(sm.b[0]), LBO, 128);
-        for (int s = 0; s < n_stage; ++s) {
-            const int b = s % NB;
-            mbar_wait(&sm.b_full[b], (s / NB) & 1);
-            const uint64_t desc_b = desc0 + static_cast<uint64_t>(b * (G::B_STAGE >> 4));
-            for (int t = 0; t < n_tiles; ++t) {
-                const int acc = acc_of(s, t, n_tiles), use = acc_use(s, n_tiles);
-                mbar_wait(&sm.d_empty[acc], (use & 1) ^ 1);
-                tc_fence_after();
-                if (leader) {
+        if (elect_one()) {
+            mbar_wait(&sm.a_ready, 0);
+            tc_fence_after();
+            // K-step k of a B stage: descriptor start address advances by 2 chunks = 2 * LBO bytes
+            const uint64_t desc0 = umma_desc(smem_u32(sm.b[0]), LBO, 128);
+            for (int s = 0; s < n_stage; ++s) {
+                const int b = s % NB;
+                mbar_wait(&sm.b_full[b], (s / NB) & 1);
+                const uint64_t desc_b = desc0 + static_cast<uint64_t>(b * (G::B_STAGE >> 4));
+                for (int t = 0; t < n_tiles; ++t) {
+                    const int acc = acc_of(s, t, n_tiles), use = acc_use(s, n_tiles);
+                    mbar_wait(&sm.d_empty[acc], (use & 1) ^ 1);
+                    tc_fence_after();
                     const uint32_t d_addr = tmem + acc * NT, a_addr = tmem + G::TMEM_A + t * 128;
                     if (n_k == 16) {
 #pragma unroll
@@ -567,7 +568,6 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                     if (t == n_tiles - 1) umma_commit(&sm.b_empty[b]);
                     umma_commit(&sm.d_full[acc]);
                 }
-                __syncwarp();
             }
         }
     } else {

@@ -259,6 +259,14 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
     const int n_k = ws + 1;             // MMA K steps: 32 K positions = 4 descriptor bytes each
     const int n_tiles = (QT == 2 && nq - qt0 > MQ) ? 2 : 1;
 
+    // epilogue threads: start fetching their query row now, its HBM latency overlaps the TMEM allocation and
+    // the barrier set-up below
+    uint32_t wq[W];
+    const bool is_epi = warp < N_EPI_WARPS && (warp >> 2) < n_tiles;
+    if (is_epi) {
+        const int row_q = qt0 + (warp >> 2) * MQ + (warp & 3) * 32 + lane;
+        load_desc_global(p.q + static_cast<size_t>(q_row0 + min(row_q, nq - 1)) * p.q_stride, p.desc_bytes, wq);
+    }
     if (tid == 0) {
         for (int i = 0; i < NB; ++i) {
             mbar_init(&sm.raw_full[i], 1);
@@ -302,12 +310,11 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
             const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;  // this warp's TMEM lanes
             const int row_in_tile = quarter * 32 + lane;
             const int row = qt0 + tile * MQ + row_in_tile;
-            const int src_row = min(row, nq - 1);  // rows past the end mirror the last row (results not written;
-                                                   // for column minima they lose every tie to the real row)
+            // rows past the end mirror the last row (min(row, nq - 1) at kernel entry): their results are not
+            // written, and for column minima they lose every tie to the real row
             const uint32_t one = static_cast<uint32_t>(p.desc_bytes > 0);  // opaque 1: keeps key adds on the FMA pipe
             {
-                uint32_t w[W];
-                load_desc_global(p.q + static_cast<size_t>(q_row0 + src_row) * p.q_stride, p.desc_bytes, w);
+                uint32_t (&w)[W] = wq;   // fetched at kernel entry
                 uint32_t pq = 0;
 #pragma unroll
                 for (int k = 0; k < W; ++k) pq += __popc(w[k]);
@@ -548,26 +555,39 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
             tc_fence_after();
             // K-step k of a B stage: descriptor start address advances by 2 chunks = 2 * LBO bytes
             const uint64_t desc0 = umma_desc(smem_u32(sm.b[0]), LBO, 128);
-            for (int s = 0; s < n_stage; ++s) {
-                const int b = s % NB;
-                mbar_wait(&sm.b_full[b], (s / NB) & 1);
+            // The (stage, tile) jobs are issued back to back.  tcgen05.mma blocks while the tensor pipe's short
+            // queue is full, so the barriers of job j + 1 are waited for in the MIDDLE of issuing job j (12 of 16
+            // K-steps queued: the wait and the commits hide behind them) — waiting between jobs left the pipe
+            // idle for ~250 cycles per tile (measured with clock64 in this thread: issue 1786 + waits 311 + 470
+            // other per 2048 cycles of MMA work).
+            const int n_jobs = n_stage * n_tiles;
+            auto wait_job = [&](int j) {   // everything job j needs: its B stage (first tile only) and its accumulator
+                const int s = j / n_tiles, t = j - s * n_tiles;
+                if (t == 0) mbar_wait(&sm.b_full[s % NB], (s / NB) & 1);
+                mbar_wait(&sm.d_empty[acc_of(s, t, n_tiles)], (acc_use(s, n_tiles) & 1) ^ 1);
+                tc_fence_after();
+            };
+            wait_job(0);
+            for (int j = 0; j < n_jobs; ++j) {
+                const int s = j / n_tiles, t = j - s * n_tiles;
+                const int b = s % NB, acc = acc_of(s, t, n_tiles);
                 const uint64_t desc_b = desc0 + static_cast<uint64_t>(b * (G::B_STAGE >> 4));
-                for (int t = 0; t < n_tiles; ++t) {
-                    const int acc = acc_of(s, t, n_tiles), use = acc_use(s, n_tiles);
-                    mbar_wait(&sm.d_empty[acc], (use & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t d_addr = tmem + acc * NT, a_addr = tmem + G::TMEM_A + t * 128;
-                    if (n_k == 16) {
+                const uint32_t d_addr = tmem + acc * NT, a_addr = tmem + G::TMEM_A + t * 128;
+                if (n_k == 16) {
 #pragma unroll
-                        for (int k = 0; k < 16; ++k)
-                            umma_i8_ts(d_addr, a_addr + 8 * k, desc_b + static_cast<uint64_t>(k * (2 * LBO >> 4)), G::IDESC, k > 0);
-                    } else {
-                        for (int k = 0; k < n_k; ++k)
-                            umma_i8_ts(d_addr, a_addr + 8 * k, desc_b + static_cast<uint64_t>(k * (2 * LBO >> 4)), G::IDESC, k > 0);
-                    }
-                    if (t == n_tiles - 1) umma_commit(&sm.b_empty[b]);
-                    umma_commit(&sm.d_full[acc]);
+                    for (int k = 0; k < 12; ++k)
+                        umma_i8_ts(d_addr, a_addr + 8 * k, desc_b + static_cast<uint64_t>(k * (2 * LBO >> 4)), G::IDESC, k > 0);
+                    if (j + 1 < n_jobs) wait_job(j + 1);
+#pragma unroll
+                    for (int k = 12; k < 16; ++k)
+                        umma_i8_ts(d_addr, a_addr + 8 * k, desc_b + static_cast<uint64_t>(k * (2 * LBO >> 4)), G::IDESC, 1);
+                } else {
+                    for (int k = 0; k < n_k; ++k)
+                        umma_i8_ts(d_addr, a_addr + 8 * k, desc_b + static_cast<uint64_t>(k * (2 * LBO >> 4)), G::IDESC, k > 0);
+                    if (j + 1 < n_jobs) wait_job(j + 1);
                 }
+                if (t == n_tiles - 1) umma_commit(&sm.b_empty[b]);
+                umma_commit(&sm.d_full[acc]);
             }
         }
     } else {

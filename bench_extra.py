@@ -73,6 +73,10 @@ def matcher_roofline(kernel_role, pairs_per_launch, launch_ms, peak_popc_g, sm_m
             "peak_source": ("2 x bf16_tflops of MEASURED_PEAKS.json (int8 dense = twice the bf16 rate; the file "
                             "has no int8 figure)" if peaks else "fallback 2 x 1647.8 TF"),
             "mma_issue_floor_gdesc_pairs_per_s": floor / 1e9, "frac_of_mma_issue_floor": pairs_s / floor,
+            "peak_caveat": "MEASURED_PEAKS.json's bf16 figure is cuBLAS under its own power limit (SM clock median "
+                           "1327 MHz under load there); this kernel holds the full clock, so frac against 2 x that "
+                           "figure can exceed 1 — frac_of_mma_issue_floor (16 descriptor pairs/clk/SM, reached by "
+                           "scripts/probe_tcgen05.cu rate3) is the hardware bound",
             "note": "achieved = 2 ops x 8*desc_bytes MACs per descriptor pair (one MAC per descriptor bit; the "
                     "kernel pads K to 512).  d = popc(q) + (1-2q).t accumulates exactly in int32, keys are "
                     "bit-identical to the XOR/POPC kernel.  The binding resource is not the tensor pipe but the "

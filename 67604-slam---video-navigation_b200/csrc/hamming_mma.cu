@@ -191,9 +191,7 @@ __device__ __forceinline__ void tmem_ld64_packed(uint32_t taddr, uint32_t (&v)[3
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// bits s, s+8, s+16, s+24 of w as four 0/1 bytes
-__device__ __forceinline__ uint32_t spread(uint32_t w, int s) { return (w >> s) & 0x01010101u; }
-// the same four bits as 0x80 / 0 bytes; `mul` = 1 << (7 - s) lives in a register so that the shift is an
+// bits s, s+8, s+16, s+24 of w as four 0x80 / 0 bytes; `mul` = 1 << (7 - s) lives in a register so that the shift is an
 // IMAD on the FMA pipe (ptxas would turn a constant power of two into an ALU shift)
 __device__ __forceinline__ uint32_t spread80(uint32_t w, uint32_t mul)
 {
@@ -328,14 +326,25 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                 }
 #pragma unroll
                 for (int s = 4; s < 8; ++s) spare[s] = 127u << 24;
+                // +-1 bytes: bit s of every byte moves to the byte's msb (IMAD by 1 << (7 - s), FMA pipe), PRMT
+                // replicates it over the byte (0xFF / 0x00), OR 1 makes it -1 / +1: 2 ALU-pipe ops per 4 positions
+                uint32_t mul[8];
+#pragma unroll
+                for (int s = 0; s < 8; ++s) mul[s] = (1u << (7 - s)) * one;
 #pragma unroll
                 for (int k = 0; k < W; ++k) {
                     if (k < n_k) {
                         uint32_t a[8];
 #pragma unroll
                         for (int s = 0; s < 8; ++s) {
-                            a[s] = spread(w[k], s) * 0xFEu | 0x01010101u;  // bit 0 -> +1, bit 1 -> -1
-                            if (k == ws) a[s] = (a[s] & 0x00FFFFFFu) | spare[s];
+                            uint32_t t, m;
+                            asm("mad.lo.u32 %0, %1, %2, 0;" : "=r"(t) : "r"(w[k]), "r"(mul[s]));
+                            asm("prmt.b32 %0, %1, %1, 0xBA98;" : "=r"(m) : "r"(t));   // sign-replicate every byte
+                            a[s] = m | 0x01010101u;                                    // bit 0 -> +1, bit 1 -> -1
+                        }
+                        if (k == ws) {
+#pragma unroll
+                            for (int s = 0; s < 8; ++s) a[s] = (a[s] & 0x00FFFFFFu) | spare[s];
                         }
                         tmem_st8(tmem + lane_base + G::TMEM_A + tile * 128 + 8 * k, a);
                     }

@@ -29,7 +29,7 @@ __global__ void stereo_filter_kernel(const float2 *__restrict__ pl, const float2
     mask[i] = stereo_inlier(a.x, a.y, b.x, b.y) ? 1 : 0;
 }
 
-constexpr int SL_THREADS = 256;
+constexpr int SL_THREADS = 512;   // one CTA per frame: the tile loop is latency-bound (4 barriers per tile), so fewer, wider tiles
 
 struct StereoLinksParams {
     const uint2 *row_keys;
@@ -112,10 +112,19 @@ __global__ void __launch_bounds__(SL_THREADS) stereo_links_kernel(const StereoLi
             for (int e = tid; e < total * 16; e += SL_THREADS) {
                 const int k = e >> 4, w = e & 15;
                 const uint8_t *src = p.desc + static_cast<size_t>(l0 + chunk_src[k]) * p.l_stride + 4 * w;
+                // bytes [4w, 4w + 4) of a row at any alignment: the one or two aligned words that hold them
+                // (a word is only read when it contains a valid descriptor byte), funnel shift, tail mask
+                const int valid = min(4, p.desc_bytes - 4 * w);
                 uint32_t v = 0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (4 * w + b < p.desc_bytes) v |= static_cast<uint32_t>(__ldg(src + b)) << (8 * b);
+                if (valid > 0) {
+                    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+                    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(a & ~static_cast<uintptr_t>(3));
+                    const int mis = static_cast<int>(a & 3);
+                    const uint32_t lo = __ldg(s32);
+                    const uint32_t hi = (mis + valid > 4) ? __ldg(s32 + 1) : 0u;
+                    v = __funnelshift_r(lo, hi, mis * 8);
+                    if (valid < 4) v &= (1u << (8 * valid)) - 1u;
+                }
                 reinterpret_cast<uint32_t *>(p.feat)[static_cast<size_t>(l0 + base + k) * 16 + w] = v;
             }
         }

@@ -58,6 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(REPO_ROOT, "include"), "-I", CSRC]
+    cmd += os.environ.get("SLAMFE_NVCC_DEFINES", "").split()   # development only, e.g. -DSLAMFE_MMA_DEV
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]

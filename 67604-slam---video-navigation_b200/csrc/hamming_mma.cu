@@ -58,7 +58,6 @@ namespace {
 constexpr int MQ = 128;                 // query rows per UMMA tile (M)
 constexpr int KCH = 32;                 // 16-byte K chunks per row (512 K positions)
 constexpr uint32_t TMEM_COLS = 512;
-constexpr int kDefaultGeometry = 0;
 
 // Geometry of one instantiation.  QT query tiles of 128 rows per CTA (their +-1 tiles live in TMEM as A
 // operands), train stages of NT rows (= UMMA N), two accumulators of NT columns:
@@ -664,18 +663,22 @@ bool hamming_mma_supports(int desc_bytes) { return desc_bytes >= 1 && desc_bytes
 
 int run_hamming_mma(HammingParams p, int n_problems, int max_nq, int max_nt, bool top2, cudaStream_t stream)
 {
-    // SLAMFE_MMA_GEOMETRY (development A/B, read once): 0 = <2,128> transpose, 1 = <2,128> redux, 2 = <1,192> redux,
-    // 3 = <2,128> transpose with two expander threads per train row
+#ifdef SLAMFE_MMA_DEV
+    // Development build only (-DSLAMFE_MMA_DEV, see scripts/README.md): the other instantiations of the template,
+    // chosen per process by SLAMFE_MMA_GEOMETRY for A/B runs (profiles/r02_mma_geometries.log).
+    //   0 = shipped, 1 = <2,128> redux column minima, 2 = <1,192> redux, 3 = <2,128> two expander threads per row
     static const int geometry = [] {
         const char *v = getenv("SLAMFE_MMA_GEOMETRY");
-        return v && *v ? atoi(v) : kDefaultGeometry;
+        return v && *v ? atoi(v) : 0;
     }();
     switch (geometry) {
         case 1: return run_geometry<Geo<2, 128, true>>(p, n_problems, max_nq, max_nt, top2, stream);
         case 2: return run_geometry<Geo<1, 192, true>>(p, n_problems, max_nq, max_nt, top2, stream);
         case 3: return run_geometry<Geo<2, 128, false, 2>>(p, n_problems, max_nq, max_nt, top2, stream);
-        default: return run_geometry<Geo<2, 128, false>>(p, n_problems, max_nq, max_nt, top2, stream);
+        default: break;
     }
+#endif
+    return run_geometry<Geo<2, 128, false, 1>>(p, n_problems, max_nq, max_nt, top2, stream);
 }
 
 }  // namespace slamfe

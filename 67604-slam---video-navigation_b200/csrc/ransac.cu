@@ -98,16 +98,33 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_score_kernel(const RansacPa
             const bool shared = s_shared[h];  // CTA-uniform
             bool maybe[RS_PP], left_in[RS_PP];
             double acc[RS_PP][3];
+            // (a) rows 1 and 2 and the v test alone: 13 of the left camera's 22 fp64-pipe operations.  A bad
+            // hypothesis puts v more than 2 px off for every point of the warp about three times out of
+            // four, and then row 0 and the u test are never computed.
             bool any = false;
+            double l2[RS_PP];
+            bool v_in[RS_PP];
+#pragma unroll
+            for (int k = 0; k < RS_PP; ++k) {
+                acc[k][1] = project_acc(M + 4, x[k], y[k], z[k]);
+                acc[k][2] = project_acc(M + 8, x[k], y[k], z[k]);
+                const double l1 = acc[k][1] + M[7];
+                l2[k] = acc[k][2] + M[11];
+                const RatioTest tv(l1, l2[k], ly[k], cly[k]);
+                maybe[k] = have[k] && !tv.surely_outside();
+                v_in[k] = tv.surely_inside();
+                any |= maybe[k];
+            }
+            if (!__any_sync(0xFFFFFFFFu, any)) continue;  // warp-uniform
+            // (b) row 0 and the u test
+            any = false;
 #pragma unroll
             for (int k = 0; k < RS_PP; ++k) {
                 acc[k][0] = project_acc(M + 0, x[k], y[k], z[k]);
-                acc[k][1] = project_acc(M + 4, x[k], y[k], z[k]);
-                acc[k][2] = project_acc(M + 8, x[k], y[k], z[k]);
-                const double l0 = acc[k][0] + M[3], l1 = acc[k][1] + M[7], l2 = acc[k][2] + M[11];
-                const RatioTest tv(l1, l2, ly[k], cly[k]), tu(l0, l2, lx[k], clx[k]);
-                maybe[k] = have[k] && !(tv.surely_outside() | tu.surely_outside());
-                left_in[k] = tv.surely_inside() & tu.surely_inside();
+                const double l0 = acc[k][0] + M[3];
+                const RatioTest tu(l0, l2[k], lx[k], clx[k]);
+                maybe[k] = maybe[k] && !tu.surely_outside();
+                left_in[k] = v_in[k] & tu.surely_inside();
                 any |= maybe[k];
             }
             if (!__any_sync(0xFFFFFFFFu, any)) continue;  // warp-uniform

@@ -14,11 +14,15 @@
 // quirks are kept: the right camera is K @ T @ [M2;0001] (ransac.py:39) and there is no
 // positive-depth test.  FP64-FMA-pipe bound (operands are reused H or N times), not HBM bound.
 //
-// Mapping: grid = (point tiles, hypothesis chunks, frames).  A thread owns one correspondence in
-// registers and walks the chunk's hypotheses, whose 2 x 3x4 projection matrices were computed
-// once per CTA into shared memory and are read with broadcast loads; votes are counted with
-// ballot + popc per warp.  The last CTA of a frame (ticket counter) picks the winner and
-// recomputes its mask with the same device function, so no second launch is needed.
+// Mapping: grid = (point tiles, hypothesis splits, frames).  A thread owns RS_PP correspondences in
+// registers for the CTA's whole life and walks the hypotheses of chunk blockIdx.y, blockIdx.y + gridDim.y, ...
+// (RS_HC per chunk); a chunk's 2 x 3x4 projection matrices are built by all 256 threads (4 per
+// hypothesis, one matrix column each) into one half of a double-buffered shared array — one barrier per
+// chunk — and read back with broadcast loads; votes are counted with ballot + popc per warp.  The host
+// picks the number of splits so that the grid still fills the GPU several times over: with thousands of
+// frames (loop-closure candidates) one CTA sweeps all hypotheses and its correspondence loads and
+// start-up are paid once, not once per 64 hypotheses.  The last CTA of a frame (ticket counter) picks the
+// winner and recomputes its mask with the same device function, so no second launch is needed.
 #include "common.cuh"
 #include "ransac_core.cuh"
 
@@ -42,39 +46,25 @@ struct RansacParams {
     uint8_t *best_mask;
 };
 
-__global__ void __launch_bounds__(RS_THREADS) ransac_score_kernel(const RansacParams p)
+__global__ void __launch_bounds__(RS_THREADS, 2) ransac_score_kernel(const RansacParams p)
 {
-    __shared__ alignas(16) double sM[RS_HC][24];
-    __shared__ int s_cnt[RS_HC];
-    __shared__ uint8_t s_valid[RS_HC];
-    __shared__ uint8_t s_shared[RS_HC];  // hypothesis' left/right matrices share their first three columns
+    __shared__ alignas(16) double sM[2][RS_HC][24];
+    __shared__ int s_cnt[3][RS_HC];  // three deep: a slot is flushed one barrier after its chunk and zeroed two after
+    __shared__ uint8_t s_shared[2][RS_HC];  // hypothesis' left/right matrices share their first three columns
     __shared__ unsigned long long s_red[RS_THREADS / 32];
     __shared__ int s_last, s_best;
+    static_assert(RS_HC == 64 && RS_THREADS == 4 * RS_HC, "one 64-bit mask per chunk, 4 threads per hypothesis");
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int f = blockIdx.z;
     const int p0 = p.pt_off ? p.pt_off[f] : 0;
     const int np = p.pt_cnt ? p.pt_cnt[f] : (p.pt_off ? p.pt_off[f + 1] - p0 : p.n_points);
-    const int h0 = blockIdx.y * RS_HC;
-    const int nh = min(RS_HC, p.H - h0);
     const size_t hbase = static_cast<size_t>(f) * p.H;
+    const int n_chunks = (p.H + RS_HC - 1) / RS_HC;
 
     if (blockIdx.x * RS_TILE < np) {  // CTA-uniform
-        if (tid < RS_HC) {
-            s_cnt[tid] = 0;
-            bool ok = tid < nh;
-            if (ok && p.hyp_valid) ok = p.hyp_valid[hbase + h0 + tid] != 0;
-            s_valid[tid] = ok;
-            bool shared = false;
-            if (ok) {
-                hypothesis_matrices(p.cam, p.T + (hbase + h0 + tid) * 12, &sM[tid][0], &sM[tid][12]);
-                shared = shares_rotation_columns(&sM[tid][0], &sM[tid][12]);
-            }
-            s_shared[tid] = shared;
-        }
         // RS_PP correspondences per thread, in registers for the whole hypothesis sweep
         double x[RS_PP], y[RS_PP], z[RS_PP], lx[RS_PP], ly[RS_PP], rx[RS_PP], ry[RS_PP];
-        double clx[RS_PP], cly[RS_PP], crx[RS_PP], cry[RS_PP];
         bool have[RS_PP];
 #pragma unroll
         for (int k = 0; k < RS_PP; ++k) {
@@ -87,69 +77,109 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_score_kernel(const RansacPa
                 lx[k] = p.l_pix[2 * g]; ly[k] = p.l_pix[2 * g + 1];
                 rx[k] = p.r_pix[2 * g]; ry[k] = p.r_pix[2 * g + 1];
             }
-            clx[k] = cert_of(lx[k]); cly[k] = cert_of(ly[k]); crx[k] = cert_of(rx[k]); cry[k] = cert_of(ry[k]);
+        }
+        // flush of the previous chunk's votes: slot and hypothesis of this thread's (j == 0 lanes only)
+        int prev_slot = -1, prev_hyp = 0, it = 0;
+        for (int c = blockIdx.y; c < n_chunks; c += gridDim.y, ++it) {
+            const int buf = it & 1, cb = it % 3;
+            const int h0 = c * RS_HC;
+            const int nh = min(RS_HC, p.H - h0);
+            // Valid hypotheses of the chunk, as a 64-bit mask every warp computes for itself (no barrier): the
+            // matrices go to shared memory COMPACTED, in order, so the sweep below has no per-hypothesis
+            // validity load or branch and makes no trip for an invalid one (a quarter of the P3P hypotheses).
+            unsigned long long valid;
+            {
+                bool v0 = lane < nh, v1 = lane + 32 < nh;
+                if (p.hyp_valid) {
+                    v0 = v0 && p.hyp_valid[hbase + h0 + lane] != 0;
+                    v1 = v1 && p.hyp_valid[hbase + h0 + 32 + lane] != 0;
+                }
+                valid = static_cast<unsigned long long>(__ballot_sync(0xFFFFFFFFu, v0)) |
+                        (static_cast<unsigned long long>(__ballot_sync(0xFFFFFFFFu, v1)) << 32);
+            }
+            const int n_valid = __popcll(valid);
+            const int hh = tid >> 2, j = tid & 3;  // thread (hh, j) builds column j of hypothesis hh's PL and PR
+            const bool ok = (valid >> hh) & 1;
+            const int slot = __popcll(valid & ((1ull << hh) - 1ull));
+            if (ok) {
+                double pl[3], pr[3];
+                hypothesis_matrix_column(p.cam, p.T + (hbase + h0 + hh) * 12, j, pl, pr);
+                bool same = true;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    sM[buf][slot][4 * i + j] = pl[i];
+                    sM[buf][slot][12 + 4 * i + j] = pr[i];
+                    same = same && (j == 3 || pl[i] == pr[i]);  // shares_rotation_columns, this column's part
+                }
+                // the 4 lanes of a hypothesis are converged here (ok is the same for all of them)
+                const uint32_t group = 0xFu << (lane & ~3);
+                const uint32_t sameb = __ballot_sync(group, same);
+                if (j == 0) {
+                    s_cnt[cb][slot] = 0;
+                    s_shared[buf][slot] = (sameb & group) == group;
+                }
+            }
+            __syncthreads();  // the matrices are visible, and every warp is done with the previous chunk
+            if (prev_slot >= 0 && s_cnt[(it + 2) % 3][prev_slot])
+                atomicAdd(p.counts + prev_hyp, s_cnt[(it + 2) % 3][prev_slot]);
+            prev_slot = (ok && j == 0) ? slot : -1;
+            prev_hyp = static_cast<int>(hbase) + h0 + hh;
+            for (int h = 0; h < n_valid; ++h) {
+                const double *M = &sM[buf][h][0];
+                // (a) rows 1 and 2 and a pruning test on v alone (surely_far: one FMA pair + a sign bit): 10 of
+                // the left camera's fp64-pipe operations per correspondence.  A bad hypothesis puts v more than
+                // 2 px off for every point of the warp half of the time, and then nothing else is computed for it.
+                double acc[RS_PP][3], ev[RS_PP], eu[RS_PP], l2[RS_PP];
+                bool maybe[RS_PP], any = false;
+#pragma unroll
+                for (int k = 0; k < RS_PP; ++k) {
+                    acc[k][1] = project_acc(M + 4, x[k], y[k], z[k]);
+                    acc[k][2] = project_acc(M + 8, x[k], y[k], z[k]);
+                    l2[k] = acc[k][2] + M[11];
+                    ev[k] = fma(-ly[k], l2[k], acc[k][1] + M[7]);
+                    maybe[k] = have[k] && !surely_far(ev[k], fabs(l2[k]));
+                    any |= maybe[k];
+                }
+                if (!__any_sync(0xFFFFFFFFu, any)) continue;  // warp-uniform
+                // (b) row 0 and the same pruning test on u
+                any = false;
+#pragma unroll
+                for (int k = 0; k < RS_PP; ++k) {
+                    acc[k][0] = project_acc(M + 0, x[k], y[k], z[k]);
+                    eu[k] = fma(-lx[k], l2[k], acc[k][0] + M[3]);
+                    maybe[k] = maybe[k] && !surely_far(eu[k], fabs(l2[k]));
+                    any |= maybe[k];
+                }
+                if (!__any_sync(0xFFFFFFFFu, any)) continue;  // warp-uniform
+                // (c) the certified tests on what is left (about one trip in ten gets here): left camera from
+                // the e / |den| at hand, then the right camera
+                const bool shared = s_shared[buf][h];  // CTA-uniform
+#pragma unroll
+                for (int k = 0; k < RS_PP; ++k) {
+                    const RatioTest lv(ev[k], fabs(l2[k]), cert_of(ly[k]), 0), lu(eu[k], fabs(l2[k]), cert_of(lx[k]), 0);
+                    const bool left_out = lv.surely_outside() | lu.surely_outside();
+                    const bool left_in = lv.surely_inside() & lu.surely_inside();
+                    double r0, r1, r2;
+                    if (shared) {  // same bits as the full rows: identical accumulators, right fourth column
+                        r0 = acc[k][0] + M[15]; r1 = acc[k][1] + M[19]; r2 = acc[k][2] + M[23];
+                    } else {
+                        r0 = project_row(M + 12, x[k], y[k], z[k]); r1 = project_row(M + 16, x[k], y[k], z[k]);
+                        r2 = project_row(M + 20, x[k], y[k], z[k]);
+                    }
+                    const RatioTest tv(r1, r2, ry[k], cert_of(ry[k])), tu(r0, r2, rx[k], cert_of(rx[k]));
+                    bool in = false;
+                    if (maybe[k] && !left_out && !(tv.surely_outside() | tu.surely_outside())) {
+                        in = (left_in & tv.surely_inside() & tu.surely_inside())
+                                 ? true
+                                 : agrees_exact(M, x[k], y[k], z[k], lx[k], ly[k], rx[k], ry[k]);
+                    }
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, in);
+                    if (lane == 0 && bal) atomicAdd(&s_cnt[cb][h], __popc(bal));
+                }
+            }
         }
         __syncthreads();
-        for (int h = 0; h < nh; ++h) {
-            if (!s_valid[h]) continue;  // CTA-uniform
-            const double *M = &sM[h][0];
-            // left camera first: most hypotheses of a RANSAC run are bad, and a warp whose points
-            // are all certainly outside on the left image skips the right camera altogether
-            const bool shared = s_shared[h];  // CTA-uniform
-            bool maybe[RS_PP], left_in[RS_PP];
-            double acc[RS_PP][3];
-            // (a) rows 1 and 2 and the v test alone: 13 of the left camera's 22 fp64-pipe operations.  A bad
-            // hypothesis puts v more than 2 px off for every point of the warp about three times out of
-            // four, and then row 0 and the u test are never computed.
-            bool any = false;
-            double l2[RS_PP];
-            bool v_in[RS_PP];
-#pragma unroll
-            for (int k = 0; k < RS_PP; ++k) {
-                acc[k][1] = project_acc(M + 4, x[k], y[k], z[k]);
-                acc[k][2] = project_acc(M + 8, x[k], y[k], z[k]);
-                const double l1 = acc[k][1] + M[7];
-                l2[k] = acc[k][2] + M[11];
-                const RatioTest tv(l1, l2[k], ly[k], cly[k]);
-                maybe[k] = have[k] && !tv.surely_outside();
-                v_in[k] = tv.surely_inside();
-                any |= maybe[k];
-            }
-            if (!__any_sync(0xFFFFFFFFu, any)) continue;  // warp-uniform
-            // (b) row 0 and the u test
-            any = false;
-#pragma unroll
-            for (int k = 0; k < RS_PP; ++k) {
-                acc[k][0] = project_acc(M + 0, x[k], y[k], z[k]);
-                const double l0 = acc[k][0] + M[3];
-                const RatioTest tu(l0, l2[k], lx[k], clx[k]);
-                maybe[k] = maybe[k] && !tu.surely_outside();
-                left_in[k] = v_in[k] & tu.surely_inside();
-                any |= maybe[k];
-            }
-            if (!__any_sync(0xFFFFFFFFu, any)) continue;  // warp-uniform
-#pragma unroll
-            for (int k = 0; k < RS_PP; ++k) {
-                double r0, r1, r2;
-                if (shared) {  // same bits as the full rows: identical accumulators, right fourth column
-                    r0 = acc[k][0] + M[15]; r1 = acc[k][1] + M[19]; r2 = acc[k][2] + M[23];
-                } else {
-                    r0 = project_row(M + 12, x[k], y[k], z[k]); r1 = project_row(M + 16, x[k], y[k], z[k]);
-                    r2 = project_row(M + 20, x[k], y[k], z[k]);
-                }
-                const RatioTest tv(r1, r2, ry[k], cry[k]), tu(r0, r2, rx[k], crx[k]);
-                bool in = false;
-                if (maybe[k] && !(tv.surely_outside() | tu.surely_outside())) {
-                    in = (left_in[k] & tv.surely_inside() & tu.surely_inside())
-                             ? true
-                             : agrees_exact(M, x[k], y[k], z[k], lx[k], ly[k], rx[k], ry[k]);
-                }
-                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, in);
-                if (lane == 0 && bal) atomicAdd(&s_cnt[h], __popc(bal));
-            }
-        }
-        __syncthreads();
-        if (tid < nh && s_cnt[tid]) atomicAdd(p.counts + hbase + h0 + tid, s_cnt[tid]);
+        if (prev_slot >= 0 && s_cnt[(it + 2) % 3][prev_slot]) atomicAdd(p.counts + prev_hyp, s_cnt[(it + 2) % 3][prev_slot]);
     }
 
     // ---- last CTA of this frame: winner + its mask ----
@@ -183,7 +213,7 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_score_kernel(const RansacPa
         p.best[2 * f] = idx;
         p.best[2 * f + 1] = cnt;
         s_best = idx;
-        if (idx >= 0) hypothesis_matrices(p.cam, p.T + (hbase + idx) * 12, &sM[0][0], &sM[0][12]);
+        if (idx >= 0) hypothesis_matrices(p.cam, p.T + (hbase + idx) * 12, &sM[0][0][0], &sM[0][0][12]);
     }
     __syncthreads();
     const int bi = s_best;
@@ -191,7 +221,7 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_score_kernel(const RansacPa
         uint8_t m = 0;
         if (bi >= 0) {
             const size_t g = static_cast<size_t>(p0 + k);
-            m = agrees(&sM[0][0], p.pts[3 * g], p.pts[3 * g + 1], p.pts[3 * g + 2], p.l_pix[2 * g], p.l_pix[2 * g + 1],
+            m = agrees(&sM[0][0][0], p.pts[3 * g], p.pts[3 * g + 1], p.pts[3 * g + 2], p.l_pix[2 * g], p.l_pix[2 * g + 1],
                        p.r_pix[2 * g], p.r_pix[2 * g + 1])
                     ? 1
                     : 0;
@@ -229,8 +259,16 @@ extern "C" int slamfe_ransac_score(const double *T, const uint8_t *hyp_valid, in
     for (int k = 0; k < 9; ++k) p.cam.K[k] = K[k];
     for (int k = 0; k < 12; ++k) { p.cam.M1[k] = M1[k]; p.cam.M2[k] = M2[k]; }
     p.counts = counts; p.best = best; p.work = work; p.best_mask = best_mask;
-    const dim3 grid(max(1, (max_points + RS_TILE - 1) / RS_TILE), max(1, (H + RS_HC - 1) / RS_HC), n_frames);
-    if (grid.y > 65535u || grid.z > 65535u) return SLAMFE_ERANGE;
+    // hypothesis splits: as few as still give every SM ~8 CTAs' worth of work in flight and to come
+    const int tiles = max(1, (max_points + RS_TILE - 1) / RS_TILE), n_chunks = max(1, (H + RS_HC - 1) / RS_HC);
+    const long long want = 16LL * sm_count();
+    const long long base = static_cast<long long>(tiles) * n_frames;
+    long long splits_ll = (want + base - 1) / base;
+    if (splits_ll < 1) splits_ll = 1;
+    if (splits_ll > n_chunks) splits_ll = n_chunks;
+    const int splits = static_cast<int>(splits_ll);
+    const dim3 grid(tiles, splits, n_frames);
+    if (grid.z > 65535u) return SLAMFE_ERANGE;
     ransac_score_kernel<<<grid, RS_THREADS, 0, s>>>(p);
     return launch_status();
 }

@@ -6,6 +6,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "hd.cuh"
 
@@ -17,35 +18,46 @@ struct RansacCams {
     double M2[12];
 };
 
-// out (3x4) = (K @ T) @ [M; 0 0 0 1], each dot product = sequential FMA over k (dgemm order).
+// Column j of out (3x4) = (K @ T) @ [M; 0 0 0 1] for both cameras, each dot product = sequential FMA
+// over k (dgemm order).  pl[i] = PL[i][j], pr[i] = PR[i][j].
+SLAMFE_HD_PLAIN void hypothesis_matrix_column(const RansacCams &c, const double *T, int j, double *pl, double *pr)
+{
+    const double h3 = (j == 3) ? 1.0 : 0.0;  // last row of [M; 0 0 0 1]
+    const double m1a = c.M1[j], m1b = c.M1[4 + j], m1c = c.M1[8 + j];
+    const double m2a = c.M2[j], m2b = c.M2[4 + j], m2c = c.M2[8 + j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double kt[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double acc = c.K[3 * i] * T[k];
+            acc = fma(c.K[3 * i + 1], T[4 + k], acc);
+            acc = fma(c.K[3 * i + 2], T[8 + k], acc);
+            kt[k] = acc;
+        }
+        double a = kt[0] * m1a;
+        a = fma(kt[1], m1b, a);
+        a = fma(kt[2], m1c, a);
+        pl[i] = fma(kt[3], h3, a);
+        double b = kt[0] * m2a;
+        b = fma(kt[1], m2b, b);
+        b = fma(kt[2], m2c, b);
+        pr[i] = fma(kt[3], h3, b);
+    }
+}
+
 SLAMFE_HD_PLAIN void hypothesis_matrices(const RansacCams &c, const double *T, double *PL, double *PR)
 {
-    double KT[12];
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 4; ++j) {
+        double pl[3], pr[3];
+        hypothesis_matrix_column(c, T, j, pl, pr);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            double acc = c.K[3 * i] * T[j];
-            acc = fma(c.K[3 * i + 1], T[4 + j], acc);
-            acc = fma(c.K[3 * i + 2], T[8 + j], acc);
-            KT[4 * i + j] = acc;
+        for (int i = 0; i < 3; ++i) {
+            PL[4 * i + j] = pl[i];
+            PR[4 * i + j] = pr[i];
         }
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const double h3 = (j == 3) ? 1.0 : 0.0;  // last row of [M; 0 0 0 1]
-            double a = KT[4 * i] * c.M1[j];
-            a = fma(KT[4 * i + 1], c.M1[4 + j], a);
-            a = fma(KT[4 * i + 2], c.M1[8 + j], a);
-            a = fma(KT[4 * i + 3], h3, a);
-            PL[4 * i + j] = a;
-            double b = KT[4 * i] * c.M2[j];
-            b = fma(KT[4 * i + 1], c.M2[4 + j], b);
-            b = fma(KT[4 * i + 2], c.M2[8 + j], b);
-            b = fma(KT[4 * i + 3], h3, b);
-            PR[4 * i + j] = b;
-        }
+    }
 }
 
 // One row of a 3x4 projection times [x y z 1]: the dgemm accumulation order of numpy's matmul.
@@ -101,12 +113,33 @@ SLAMFE_HD_NOINLINE bool agrees_exact(const double *M, double x, double y, double
 // cert = (|pix| + 8) * 2^-49 is hoisted out of the hypothesis loop.
 SLAMFE_HD double cert_of(double pix) { return (fabs(pix) + 8.0) * 0x1p-49; }
 
+// Cheap pruning test used before the certified one: with e = fma(-pix, den, num) = w*den and ad = |den|,
+//     far = (|e| - 2.001 |den| >= 0)   i.e.  |w| >= 2.001
+// decided on the SIGN BIT of one FMA (an integer test: two fp64-pipe operations per coordinate instead
+// of three and two compares).  The 0.1 % margin is ~10^12 times the rounding of e and of the FMA, so
+// far implies the reference's |num/den - pix| < 2 is false; den = 0 gives far (reference: inf or NaN, not an
+// inlier); a NaN with its sign bit set is not far and falls through to the certified / exact tests, which
+// reject it as well.
+SLAMFE_HD bool surely_far(double e, double ad)
+{
+    const double pv = fma(-2.001, ad, fabs(e));
+    long long bits;
+    memcpy(&bits, &pv, sizeof(bits));
+    return bits >= 0;
+}
+
 struct RatioTest {
     double diff, bound;
     SLAMFE_HD RatioTest(double num, double den, double pix, double cert)
     {
         const double e = fma(-pix, den, num);
         const double ad = fabs(den);
+        diff = fma(-2.0, ad, fabs(e));
+        bound = cert * ad;
+    }
+    // from e = fma(-pix, den, num) and ad = |den| already at hand (the pruning test computed them)
+    SLAMFE_HD RatioTest(double e, double ad, double cert, int)
+    {
         diff = fma(-2.0, ad, fabs(e));
         bound = cert * ad;
     }

@@ -50,3 +50,14 @@ extern "C" void ransac_host_matrices(const double *K, const double *M1, const do
     for (int k = 0; k < 12; ++k) { c.M1[k] = M1[k]; c.M2[k] = M2[k]; }
     hypothesis_matrices(c, T, PLPR, PLPR + 12);
 }
+
+// The pruning test of the kernel (surely_far) next to the reference's verdict for one coordinate:
+// out_far[i] = surely_far(fma(-pix, den, num), |den|), out_ref[i] = (|num/den - pix| < 2).
+extern "C" void ransac_host_far(const double *num, const double *den, const double *pix, long n,
+                                unsigned char *out_far, unsigned char *out_ref)
+{
+    for (long i = 0; i < n; ++i) {
+        out_far[i] = surely_far(fma(-pix[i], den[i], num[i]), fabs(den[i]));
+        out_ref[i] = fabs(num[i] / den[i] - pix[i]) < 2.0;
+    }
+}

@@ -124,6 +124,16 @@ class ScorerHost:
                                    *[o.ctypes.data_as(up) for o in outs])
         return tuple(o.astype(bool) for o in outs[:4]) + (outs[4],)
 
+    def far(self, num, den, pix):
+        """(far, ref) bool arrays: the kernel's pruning test and the reference's verdict per coordinate."""
+        dp, up = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ubyte)
+        c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        a, b, p_ = c(num), c(den), c(pix)
+        f, r = np.zeros(len(a), np.uint8), np.zeros(len(a), np.uint8)
+        self.lib.ransac_host_far(a.ctypes.data_as(dp), b.ctypes.data_as(dp), p_.ctypes.data_as(dp), ctypes.c_long(len(a)),
+                                 f.ctypes.data_as(up), r.ctypes.data_as(up))
+        return f.astype(bool), r.astype(bool)
+
     def matrices(self, T, K, M1, M2):
         dp = ctypes.POINTER(ctypes.c_double)
         c = lambda a: np.ascontiguousarray(a, dtype=np.float64)

@@ -258,3 +258,28 @@ def test_refit_host_build_degenerate_inputs():
     T_np, _ = ora.pnp_refit(T_seed, K, X, pix)
     ang, dt = _pose_err(T, T_np)
     assert status > 0 and ang < 1e-7 and dt < 1e-6
+
+
+def test_scorer_pruning_test_never_rejects_an_inlier(oracle):
+    """surely_far (csrc/ransac_core.cuh): the sign-bit test the scorer uses to skip hopeless (hypothesis,
+    point) pairs.  Wherever it fires, the reference's |num/den - pix| < 2 (ransac.py:45-56) is false — on
+    random magnitudes, on ratios within a few ulps of 2 and of 2.001, on den = 0, 0/0, inf and NaN."""
+    host = oracle.ScorerHost()
+    rng = np.random.default_rng(98)
+    n = 400000
+    den = rng.normal(0, 1, n) * 10.0 ** rng.integers(-6, 7, n)
+    pix = rng.uniform(-2000, 2000, n)
+    w = np.concatenate([rng.normal(0, 3, n // 2), rng.choice([2.0, -2.0, 2.001, -2.001], n // 2)])
+    w[n // 2:] *= 1 + rng.integers(-8, 9, n // 2) * 2.0 ** -52
+    num = (w + pix) * den
+    special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-310, -1e-310, 1e308])
+    num = np.concatenate([num, np.repeat(special, len(special)), [3.0, 0.0]])
+    den = np.concatenate([den, np.tile(special, len(special)), [0.0, 0.0]])
+    pix = np.concatenate([pix, np.full(len(special) ** 2, 17.25), [5.0, 5.0]])
+    with np.errstate(all="ignore"):
+        far, ref = host.far(num, den, pix)
+    assert not (far & ref).any()                       # never prunes what the reference accepts
+    assert far.sum() > 0.2 * len(far) and ref.sum() > 0.1 * len(far)
+    with np.errstate(all="ignore"):
+        wtrue = np.abs(num[:n] / den[:n] - pix[:n])
+    assert far[:n][wtrue > 2.01].all()                 # and does prune everything clearly outside

@@ -46,7 +46,7 @@ struct RansacParams {
     uint8_t *best_mask;
 };
 
-__global__ void __launch_bounds__(RS_THREADS, 2) ransac_score_kernel(const RansacParams p)
+__global__ void __launch_bounds__(RS_THREADS, 3) ransac_score_kernel(const RansacParams p)
 {
     __shared__ alignas(16) double sM[2][RS_HC][24];
     __shared__ int s_cnt[3][RS_HC];  // three deep: a slot is flushed one barrier after its chunk and zeroed two after

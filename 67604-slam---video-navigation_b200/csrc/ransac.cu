@@ -49,6 +49,7 @@ struct RansacParams {
 __global__ void __launch_bounds__(RS_THREADS, 3) ransac_score_kernel(const RansacParams p)
 {
     __shared__ alignas(16) double sM[2][RS_HC][24];
+    __shared__ alignas(16) float sF[2][RS_HC][16];  // fp32 pre-filter: PL rows 1, 2, 0 (4 each), A_1, A_2, A_0, unused
     __shared__ int s_cnt[3][RS_HC];  // three deep: a slot is flushed one barrier after its chunk and zeroed two after
     __shared__ uint8_t s_shared[2][RS_HC];  // hypothesis' left/right matrices share their first three columns
     __shared__ unsigned long long s_red[RS_THREADS / 32];
@@ -63,20 +64,27 @@ __global__ void __launch_bounds__(RS_THREADS, 3) ransac_score_kernel(const Ransa
     const int n_chunks = (p.H + RS_HC - 1) / RS_HC;
 
     if (blockIdx.x * RS_TILE < np) {  // CTA-uniform
-        // RS_PP correspondences per thread, in registers for the whole hypothesis sweep
-        double x[RS_PP], y[RS_PP], z[RS_PP], lx[RS_PP], ly[RS_PP], rx[RS_PP], ry[RS_PP];
+        // RS_PP correspondences per thread.  The sweep keeps only the fp32 pre-filter's view of them in registers
+        // (coordinates, left pixel, the two slack factors); the fp64 originals are re-read from global memory
+        // (L1) by the one trip in ten that gets past the filter.
+        float xf[RS_PP], yf[RS_PP], zf[RS_PP], lxf[RS_PP], lyf[RS_PP], pb[RS_PP], pbp[RS_PP];
         bool have[RS_PP];
 #pragma unroll
         for (int k = 0; k < RS_PP; ++k) {
             const int i = blockIdx.x * RS_TILE + k * RS_THREADS + tid;
             have[k] = i < np;
-            x[k] = y[k] = z[k] = lx[k] = ly[k] = rx[k] = ry[k] = 0.0;
+            double x = 0.0, y = 0.0, z = 0.0, lx = 0.0, ly = 0.0;
             if (have[k]) {
                 const size_t g = static_cast<size_t>(p0 + i);
-                x[k] = p.pts[3 * g]; y[k] = p.pts[3 * g + 1]; z[k] = p.pts[3 * g + 2];
-                lx[k] = p.l_pix[2 * g]; ly[k] = p.l_pix[2 * g + 1];
-                rx[k] = p.r_pix[2 * g]; ry[k] = p.r_pix[2 * g + 1];
+                x = p.pts[3 * g]; y = p.pts[3 * g + 1]; z = p.pts[3 * g + 2];
+                lx = p.l_pix[2 * g]; ly = p.l_pix[2 * g + 1];
             }
+            xf[k] = static_cast<float>(x); yf[k] = static_cast<float>(y); zf[k] = static_cast<float>(z);
+            lxf[k] = static_cast<float>(lx); lyf[k] = static_cast<float>(ly);
+            prune_point_bound(x, y, z, lx, ly, &pb[k], &pbp[k]);
+            // a slot past the end of the frame's correspondences: slack -inf, so the filter always drops it
+            // (the slack is a sum of products of these with positive factors, never inf - inf)
+            if (!have[k]) pb[k] = pbp[k] = -INFINITY;
         }
         // flush of the previous chunk's votes: slot and hypothesis of this thread's (j == 0 lanes only)
         int prev_slot = -1, prev_hyp = 0, it = 0;
@@ -104,19 +112,33 @@ __global__ void __launch_bounds__(RS_THREADS, 3) ransac_score_kernel(const Ransa
             if (ok) {
                 double pl[3], pr[3];
                 hypothesis_matrix_column(p.cam, p.T + (hbase + h0 + hh) * 12, j, pl, pr);
-                bool same = true;
+                bool same = true, finite = true;
+                double amax[3];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     sM[buf][slot][4 * i + j] = pl[i];
                     sM[buf][slot][12 + 4 * i + j] = pr[i];
                     same = same && (j == 3 || pl[i] == pr[i]);  // shares_rotation_columns, this column's part
+                    finite = finite && (fabs(pl[i]) <= 1e9);
+                    amax[i] = fabs(pl[i]);
                 }
+                sF[buf][slot][j] = static_cast<float>(pl[1]);
+                sF[buf][slot][4 + j] = static_cast<float>(pl[2]);
+                sF[buf][slot][8 + j] = static_cast<float>(pl[0]);
                 // the 4 lanes of a hypothesis are converged here (ok is the same for all of them)
                 const uint32_t group = 0xFu << (lane & ~3);
                 const uint32_t sameb = __ballot_sync(group, same);
+                const uint32_t finb = __ballot_sync(group, finite);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {  // row maxima over the 4 columns
+                    amax[i] = fmax(amax[i], __shfl_xor_sync(group, amax[i], 1));
+                    amax[i] = fmax(amax[i], __shfl_xor_sync(group, amax[i], 2));
+                }
                 if (j == 0) {
                     s_cnt[cb][slot] = 0;
                     s_shared[buf][slot] = (sameb & group) == group;
+                    const PruneHyp ph = prune_hyp_bound(amax, (finb & group) == group);
+                    sF[buf][slot][12] = ph.a1; sF[buf][slot][13] = ph.a2; sF[buf][slot][14] = ph.a0;
                 }
             }
             __syncthreads();  // the matrices are visible, and every warp is done with the previous chunk
@@ -125,53 +147,43 @@ __global__ void __launch_bounds__(RS_THREADS, 3) ransac_score_kernel(const Ransa
             prev_slot = (ok && j == 0) ? slot : -1;
             prev_hyp = static_cast<int>(hbase) + h0 + hh;
             for (int h = 0; h < n_valid; ++h) {
-                const double *M = &sM[buf][h][0];
-                // (a) rows 1 and 2 and a pruning test on v alone (surely_far: one FMA pair + a sign bit): 10 of
-                // the left camera's fp64-pipe operations per correspondence.  A bad hypothesis puts v more than
-                // 2 px off for every point of the warp half of the time, and then nothing else is computed for it.
-                double acc[RS_PP][3], ev[RS_PP], eu[RS_PP], l2[RS_PP];
+                const float *F = &sF[buf][h][0];
+                // (a) fp32 pre-filter (ransac_core.cuh) on the left image's v: rows 1 and 2.  A bad hypothesis
+                // puts v more than 2 px off for every point of the warp half of the time, and then nothing else
+                // is computed for it.
+                const float a1 = F[12], a2 = F[13];
+                float l2f[RS_PP], a2bp[RS_PP];
                 bool maybe[RS_PP], any = false;
 #pragma unroll
                 for (int k = 0; k < RS_PP; ++k) {
-                    acc[k][1] = project_acc(M + 4, x[k], y[k], z[k]);
-                    acc[k][2] = project_acc(M + 8, x[k], y[k], z[k]);
-                    l2[k] = acc[k][2] + M[11];
-                    ev[k] = fma(-ly[k], l2[k], acc[k][1] + M[7]);
-                    maybe[k] = have[k] && !surely_far(ev[k], fabs(l2[k]));
+                    const float l1f = prune_row(F, xf[k], yf[k], zf[k]);
+                    l2f[k] = prune_row(F + 4, xf[k], yf[k], zf[k]);
+                    a2bp[k] = a2 * pbp[k];
+                    maybe[k] = !prune_far(l1f, l2f[k], lyf[k], prune_slack(a1, pb[k], a2bp[k]));
                     any |= maybe[k];
                 }
                 if (!__any_sync(0xFFFFFFFFu, any)) continue;  // warp-uniform
-                // (b) row 0 and the same pruning test on u
+                // (b) the same on u: row 0
                 any = false;
+                const float a0 = F[14];
 #pragma unroll
                 for (int k = 0; k < RS_PP; ++k) {
-                    acc[k][0] = project_acc(M + 0, x[k], y[k], z[k]);
-                    eu[k] = fma(-lx[k], l2[k], acc[k][0] + M[3]);
-                    maybe[k] = maybe[k] && !surely_far(eu[k], fabs(l2[k]));
+                    const float l0f = prune_row(F + 8, xf[k], yf[k], zf[k]);
+                    maybe[k] = maybe[k] && !prune_far(l0f, l2f[k], lxf[k], prune_slack(a0, pb[k], a2bp[k]));
                     any |= maybe[k];
                 }
                 if (!__any_sync(0xFFFFFFFFu, any)) continue;  // warp-uniform
-                // (c) the certified tests on what is left (about one trip in ten gets here): left camera from
-                // the e / |den| at hand, then the right camera
+                // (c) fp64, bit-exact (about one trip in ten gets here): certified tests, exact fallback
+                const double *M = &sM[buf][h][0];
                 const bool shared = s_shared[buf][h];  // CTA-uniform
 #pragma unroll
                 for (int k = 0; k < RS_PP; ++k) {
-                    const RatioTest lv(ev[k], fabs(l2[k]), cert_of(ly[k]), 0), lu(eu[k], fabs(l2[k]), cert_of(lx[k]), 0);
-                    const bool left_out = lv.surely_outside() | lu.surely_outside();
-                    const bool left_in = lv.surely_inside() & lu.surely_inside();
-                    double r0, r1, r2;
-                    if (shared) {  // same bits as the full rows: identical accumulators, right fourth column
-                        r0 = acc[k][0] + M[15]; r1 = acc[k][1] + M[19]; r2 = acc[k][2] + M[23];
-                    } else {
-                        r0 = project_row(M + 12, x[k], y[k], z[k]); r1 = project_row(M + 16, x[k], y[k], z[k]);
-                        r2 = project_row(M + 20, x[k], y[k], z[k]);
-                    }
-                    const RatioTest tv(r1, r2, ry[k], cert_of(ry[k])), tu(r0, r2, rx[k], cert_of(rx[k]));
                     bool in = false;
-                    if (maybe[k] && !left_out && !(tv.surely_outside() | tu.surely_outside())) {
-                        in = (left_in & tv.surely_inside() & tu.surely_inside())
-                                 ? true
-                                 : agrees_exact(M, x[k], y[k], z[k], lx[k], ly[k], rx[k], ry[k]);
+                    if (maybe[k]) {  // implies the slot holds a correspondence
+                        const size_t g = static_cast<size_t>(p0 + blockIdx.x * RS_TILE + k * RS_THREADS + tid);
+                        in = agrees_rows(M, shared, __ldg(p.pts + 3 * g), __ldg(p.pts + 3 * g + 1), __ldg(p.pts + 3 * g + 2),
+                                         __ldg(p.l_pix + 2 * g), __ldg(p.l_pix + 2 * g + 1), __ldg(p.r_pix + 2 * g),
+                                         __ldg(p.r_pix + 2 * g + 1));
                     }
                     const uint32_t bal = __ballot_sync(0xFFFFFFFFu, in);
                     if (lane == 0 && bal) atomicAdd(&s_cnt[cb][h], __popc(bal));

@@ -113,21 +113,6 @@ SLAMFE_HD_NOINLINE bool agrees_exact(const double *M, double x, double y, double
 // cert = (|pix| + 8) * 2^-49 is hoisted out of the hypothesis loop.
 SLAMFE_HD double cert_of(double pix) { return (fabs(pix) + 8.0) * 0x1p-49; }
 
-// Cheap pruning test used before the certified one: with e = fma(-pix, den, num) = w*den and ad = |den|,
-//     far = (|e| - 2.001 |den| >= 0)   i.e.  |w| >= 2.001
-// decided on the SIGN BIT of one FMA (an integer test: two fp64-pipe operations per coordinate instead
-// of three and two compares).  The 0.1 % margin is ~10^12 times the rounding of e and of the FMA, so
-// far implies the reference's |num/den - pix| < 2 is false; den = 0 gives far (reference: inf or NaN, not an
-// inlier); a NaN with its sign bit set is not far and falls through to the certified / exact tests, which
-// reject it as well.
-SLAMFE_HD bool surely_far(double e, double ad)
-{
-    const double pv = fma(-2.001, ad, fabs(e));
-    long long bits;
-    memcpy(&bits, &pv, sizeof(bits));
-    return bits >= 0;
-}
-
 struct RatioTest {
     double diff, bound;
     SLAMFE_HD RatioTest(double num, double den, double pix, double cert)
@@ -137,27 +122,113 @@ struct RatioTest {
         diff = fma(-2.0, ad, fabs(e));
         bound = cert * ad;
     }
-    // from e = fma(-pix, den, num) and ad = |den| already at hand (the pruning test computed them)
-    SLAMFE_HD RatioTest(double e, double ad, double cert, int)
-    {
-        diff = fma(-2.0, ad, fabs(e));
-        bound = cert * ad;
-    }
     SLAMFE_HD bool surely_outside() const { return diff > bound; }
     SLAMFE_HD bool surely_inside() const { return diff < -bound; }
 };
 
+// The scorer's evaluation of one (hypothesis, correspondence): certified division-free tests, exact
+// fallback.  `shared` = shares_rotation_columns(M, M + 12): the right rows are then the left accumulators
+// plus the right fourth column (the same bits).  Left camera first: its verdict alone rejects most pairs.
+SLAMFE_HD bool agrees_rows(const double *M, bool shared, double x, double y, double z, double lx, double ly,
+                           double rx, double ry)
+{
+    const double a0 = project_acc(M + 0, x, y, z), a1 = project_acc(M + 4, x, y, z), a2 = project_acc(M + 8, x, y, z);
+    const double l2 = a2 + M[11];
+    const RatioTest t0(a1 + M[7], l2, ly, cert_of(ly)), t1(a0 + M[3], l2, lx, cert_of(lx));
+    if (t0.surely_outside() | t1.surely_outside()) return false;
+    double r0, r1, r2;
+    if (shared) {
+        r0 = a0 + M[15]; r1 = a1 + M[19]; r2 = a2 + M[23];
+    } else {
+        r0 = project_row(M + 12, x, y, z); r1 = project_row(M + 16, x, y, z); r2 = project_row(M + 20, x, y, z);
+    }
+    const RatioTest t2(r1, r2, ry, cert_of(ry)), t3(r0, r2, rx, cert_of(rx));
+    if (t2.surely_outside() | t3.surely_outside()) return false;
+    if (t0.surely_inside() & t1.surely_inside() & t2.surely_inside() & t3.surely_inside()) return true;
+    return agrees_exact(M, x, y, z, lx, ly, rx, ry);
+}
+
 SLAMFE_HD bool agrees(const double *M, double x, double y, double z, double lx, double ly, double rx,
                                        double ry)
 {
-    const double l0 = project_row(M + 0, x, y, z), l1 = project_row(M + 4, x, y, z), l2 = project_row(M + 8, x, y, z);
-    const double r0 = project_row(M + 12, x, y, z), r1 = project_row(M + 16, x, y, z),
-                 r2 = project_row(M + 20, x, y, z);
-    const RatioTest t0(l1, l2, ly, cert_of(ly)), t1(l0, l2, lx, cert_of(lx));
-    const RatioTest t2(r1, r2, ry, cert_of(ry)), t3(r0, r2, rx, cert_of(rx));
-    if (t0.surely_outside() | t1.surely_outside() | t2.surely_outside() | t3.surely_outside()) return false;
-    if (t0.surely_inside() & t1.surely_inside() & t2.surely_inside() & t3.surely_inside()) return true;
-    return agrees_exact(M, x, y, z, lx, ly, rx, ry);
+    return agrees_rows(M, false, x, y, z, lx, ly, rx, ry);
+}
+
+// ---- fp32 pre-filter -------------------------------------------------------------------------------
+// Most (hypothesis, correspondence) pairs of a RANSAC run are nowhere near agreement.  Before any fp64
+// work the scorer evaluates the LEFT camera in fp32 and drops a pair when that alone proves the
+// reference's verdict false; a warp whose pairs are all dropped does nothing else for the hypothesis.
+// The filter is one-sided: it may keep a pair (which then gets the full fp64 evaluation above), it never
+// drops one the reference accepts.
+//
+// Notation: m_i = row i of the left matrix PL (fp64, as the scorer holds it), X = (x, y, z, 1),
+// S_i = sum_j |m_ij X_j|, L_i = the row value the reference computes (fp64), u = 2^-24.
+//   * l~_i = prune_row(fp32(m_i), fp32(X)) is three FMAs on rounded inputs: every term passes through at
+//     most five factors (1 + d), |d| <= u, so |l~_i - L_i| <= 5.01 u S_i + (the reference's own 4 * 2^-53 S_i)
+//     < 2^-20 S_i.
+//   * e~ = fmaf(-fp32(pix), l~_2, l~_1) is one more rounding:  |e~ - (L_1 - pix L_2)| <= 1.13 * 2^-20 (S_1 + |pix| S_2).
+//   * S_i <= A_i B  with  A_i = max_j |m_ij|  and  B = |x| + |y| + |z| + 1.
+// The v test is  fmaf(-2.001f, |l~_2|, |e~|) >= slack_v,  slack_v = 2^-18 B (A_1 + (p + 2) A_2),  p = max(|lx|, |ly|)
+// (u: A_0 for A_1), evaluated in fp32 from factors that were each rounded UP by (1 + 2^-20).  The FMA of the
+// test rounds once, relative to its own result, so a true comparison means, in exact arithmetic,
+//     |e~| >= 2.0009 |l~_2| + 0.9999 slack_v,
+// and with the error bounds above (slack_v is at least 1.99 times what they need)
+//     |L_1 - pix L_2| >= 2.0009 |l~_2| + 2.01 * 2^-20 A_2 B >= (2 + 10^-6) |L_2|,
+// i.e. |L_1/L_2 - pix| >= 2 + 10^-6 exactly, which the reference's two roundings (division, subtraction:
+// <= 2^-52 (|L_1/L_2| + |pix|)) cannot bring below 2 for |pix| <= 10^9; L_2 = 0 gives inf or NaN, not an
+// inlier either.  Range guards make the rest of IEEE harmless: the factors are +inf (the test is then never
+// true) unless every |entry of PL|, B, |lx|, |ly| <= 10^9, which rules out fp32 overflow (|e~| < 10^28) and
+// NaN inputs; a 2^-60 floor on each A_i keeps the slack (>= 2^-78) far above anything fp32 underflow can
+// lose (<= 10^9 * 2^-140 with denormals, which this build keeps: no -ftz).  The comparison is an ordinary >=,
+// false on NaN.
+struct PruneHyp {
+    float a1, a2, a0;  // rounded-up row bounds A_1, A_2, A_0 (this order: the v test comes first)
+};
+SLAMFE_HD float prune_round_up(double v) { return static_cast<float>(v) * (1.0f + 0x1p-20f); }
+// amax[i] = max_j |PL[i][j]|; finite = every |entry| <= 1e9 (false if any is NaN)
+SLAMFE_HD PruneHyp prune_hyp_bound(const double *amax, bool finite)
+{
+    PruneHyp h;
+    if (!finite) {
+        h.a0 = h.a1 = h.a2 = INFINITY;
+    } else {
+        h.a0 = prune_round_up(fmax(amax[0], 0x1p-60));
+        h.a1 = prune_round_up(fmax(amax[1], 0x1p-60));
+        h.a2 = prune_round_up(fmax(amax[2], 0x1p-60));
+    }
+    return h;
+}
+SLAMFE_HD PruneHyp prune_hyp_bound_of(const double *PL)
+{
+    double amax[3] = {0.0, 0.0, 0.0};
+    bool finite = true;
+    for (int i = 0; i < 12; ++i) {
+        finite = finite && (fabs(PL[i]) <= 1e9);  // false on NaN
+        amax[i / 4] = fmax(amax[i / 4], fabs(PL[i]));
+    }
+    return prune_hyp_bound(amax, finite);
+}
+// b = 2^-18 B and bp = 2^-18 B (p + 2), rounded up; +inf outside the guarded range
+SLAMFE_HD void prune_point_bound(double x, double y, double z, double lx, double ly, float *b, float *bp)
+{
+    const double bb = fabs(x) + fabs(y) + fabs(z) + 1.0;
+    if (!(bb <= 1e9) || !(fabs(lx) <= 1e9) || !(fabs(ly) <= 1e9)) {  // NaN lands here too
+        *b = *bp = INFINITY;
+        return;
+    }
+    *b = prune_round_up(0x1p-18 * bb);
+    *bp = prune_round_up(0x1p-18 * bb * (fmax(fabs(lx), fabs(ly)) + 2.0));
+}
+// slack of one test: a = A_1 (v) or A_0 (u), a2bp = A_2 * bp (shared by the two tests)
+SLAMFE_HD float prune_slack(float a, float b, float a2bp) { return fmaf(a, b, a2bp); }
+SLAMFE_HD float prune_row(const float *m, float x, float y, float z)
+{
+    return fmaf(m[0], x, fmaf(m[1], y, fmaf(m[2], z, m[3])));
+}
+SLAMFE_HD bool prune_far(float num, float den, float pix, float slack)
+{
+    const float e = fmaf(-pix, den, num);
+    return fmaf(-2.001f, fabsf(den), fabsf(e)) >= slack;
 }
 
 }  // namespace slamfe

@@ -51,13 +51,34 @@ extern "C" void ransac_host_matrices(const double *K, const double *M1, const do
     hypothesis_matrices(c, T, PLPR, PLPR + 12);
 }
 
-// The pruning test of the kernel (surely_far) next to the reference's verdict for one coordinate:
-// out_far[i] = surely_far(fma(-pix, den, num), |den|), out_ref[i] = (|num/den - pix| < 2).
-extern "C" void ransac_host_far(const double *num, const double *den, const double *pix, long n,
-                                unsigned char *out_far, unsigned char *out_ref)
+// The kernel's fp32 pre-filter for n points and ONE hypothesis: out_far_v / out_far_u = the pair is dropped
+// by the v / u test, out_rows = agrees_rows() with the hypothesis' own `shared` flag (what the kernel counts
+// for the pairs it keeps), out_exact = the reference's verdict (agrees_exact).
+extern "C" void ransac_host_prune(const double *K, const double *M1, const double *M2, const double *T,
+                                  const double *pts, const double *lpix, const double *rpix, long n,
+                                  unsigned char *out_far_v, unsigned char *out_far_u, unsigned char *out_rows,
+                                  unsigned char *out_exact)
 {
+    RansacCams c;
+    for (int k = 0; k < 9; ++k) c.K[k] = K[k];
+    for (int k = 0; k < 12; ++k) { c.M1[k] = M1[k]; c.M2[k] = M2[k]; }
+    double M[24];
+    hypothesis_matrices(c, T, M, M + 12);
+    const bool shared = shares_rotation_columns(M, M + 12);
+    float F[12];
+    for (int k = 0; k < 12; ++k) F[k] = static_cast<float>(M[k]);
+    const PruneHyp ph = prune_hyp_bound_of(M);
     for (long i = 0; i < n; ++i) {
-        out_far[i] = surely_far(fma(-pix[i], den[i], num[i]), fabs(den[i]));
-        out_ref[i] = fabs(num[i] / den[i] - pix[i]) < 2.0;
+        const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+        const double lx = lpix[2 * i], ly = lpix[2 * i + 1], rx = rpix[2 * i], ry = rpix[2 * i + 1];
+        const float xf = static_cast<float>(x), yf = static_cast<float>(y), zf = static_cast<float>(z);
+        float b, bp;
+        prune_point_bound(x, y, z, lx, ly, &b, &bp);
+        const float a2bp = ph.a2 * bp;
+        const float l0 = prune_row(F, xf, yf, zf), l1 = prune_row(F + 4, xf, yf, zf), l2 = prune_row(F + 8, xf, yf, zf);
+        out_far_v[i] = prune_far(l1, l2, static_cast<float>(ly), prune_slack(ph.a1, b, a2bp));
+        out_far_u[i] = prune_far(l0, l2, static_cast<float>(lx), prune_slack(ph.a0, b, a2bp));
+        out_rows[i] = agrees_rows(M, shared, x, y, z, lx, ly, rx, ry);
+        out_exact[i] = agrees_exact(M, x, y, z, lx, ly, rx, ry);
     }
 }

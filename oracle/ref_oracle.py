@@ -124,15 +124,17 @@ class ScorerHost:
                                    *[o.ctypes.data_as(up) for o in outs])
         return tuple(o.astype(bool) for o in outs[:4]) + (outs[4],)
 
-    def far(self, num, den, pix):
-        """(far, ref) bool arrays: the kernel's pruning test and the reference's verdict per coordinate."""
+    def prune(self, T, pts, l_pix, r_pix, K, M1, M2):
+        """The kernel's fp32 pre-filter for one hypothesis: bool arrays (far_v, far_u, rows, exact) — dropped by
+        the v / u test, agrees_rows() (what the kernel counts for kept pairs), the reference's verdict."""
         dp, up = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ubyte)
         c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
-        a, b, p_ = c(num), c(den), c(pix)
-        f, r = np.zeros(len(a), np.uint8), np.zeros(len(a), np.uint8)
-        self.lib.ransac_host_far(a.ctypes.data_as(dp), b.ctypes.data_as(dp), p_.ctypes.data_as(dp), ctypes.c_long(len(a)),
-                                 f.ctypes.data_as(up), r.ctypes.data_as(up))
-        return f.astype(bool), r.astype(bool)
+        arrs = [c(K), c(M1), c(M2), c(T), c(pts), c(l_pix), c(r_pix)]
+        n = arrs[4].shape[0]
+        outs = [np.zeros(n, np.uint8) for _ in range(4)]
+        self.lib.ransac_host_prune(*[a.ctypes.data_as(dp) for a in arrs], ctypes.c_long(n),
+                                   *[o.ctypes.data_as(up) for o in outs])
+        return tuple(o.astype(bool) for o in outs)
 
     def matrices(self, T, K, M1, M2):
         dp = ctypes.POINTER(ctypes.c_double)

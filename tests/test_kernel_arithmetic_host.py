@@ -260,26 +260,84 @@ def test_refit_host_build_degenerate_inputs():
     assert status > 0 and ang < 1e-7 and dt < 1e-6
 
 
-def test_scorer_pruning_test_never_rejects_an_inlier(oracle):
-    """surely_far (csrc/ransac_core.cuh): the sign-bit test the scorer uses to skip hopeless (hypothesis,
-    point) pairs.  Wherever it fires, the reference's |num/den - pix| < 2 (ransac.py:45-56) is false — on
-    random magnitudes, on ratios within a few ulps of 2 and of 2.001, on den = 0, 0/0, inf and NaN."""
+def _prefilter_case(oracle, host, T, pts, lp, rp, K, M1, M2):
+    """Runs the host build of the fp32 pre-filter + agrees_rows for one hypothesis and checks what the kernel
+    relies on: a dropped pair is never one the reference accepts, and for every pair the kernel's count
+    (kept && agrees_rows) equals the reference's verdict.  Returns (dropped, reference verdict)."""
+    with np.errstate(all="ignore"):
+        far_v, far_u, rows, exact = host.prune(T, pts, lp, rp, K, M1, M2)
+    ref = _ref(oracle, T, pts, lp, rp, K, M1, M2)
+    dropped = far_v | far_u
+    assert np.array_equal(exact, ref)
+    assert not (dropped & ref).any()
+    assert np.array_equal(~dropped & rows, ref)
+    return dropped, ref
+
+
+@pytest.mark.parametrize("scale", [1.0, 1e-4, 1e5])
+def test_fp32_prefilter_never_drops_an_inlier_near_its_own_threshold(oracle, scale):
+    """The scorer's fp32 pre-filter (prune_* in csrc/ransac_core.cuh, derivation there) against the reference's
+    transformation_agreement (ransac.py:28-56): pixels placed around the reference's threshold (2 px), around
+    the filter's own (2.001 px +- its slack) and far away, at three scene scales, points behind the camera."""
+    from slamfe import synth
     host = oracle.ScorerHost()
+    K, M1, M2 = synth.cameras()
     rng = np.random.default_rng(98)
-    n = 400000
-    den = rng.normal(0, 1, n) * 10.0 ** rng.integers(-6, 7, n)
-    pix = rng.uniform(-2000, 2000, n)
-    w = np.concatenate([rng.normal(0, 3, n // 2), rng.choice([2.0, -2.0, 2.001, -2.001], n // 2)])
-    w[n // 2:] *= 1 + rng.integers(-8, 9, n // 2) * 2.0 ** -52
-    num = (w + pix) * den
-    special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-310, -1e-310, 1e308])
-    num = np.concatenate([num, np.repeat(special, len(special)), [3.0, 0.0]])
-    den = np.concatenate([den, np.tile(special, len(special)), [0.0, 0.0]])
-    pix = np.concatenate([pix, np.full(len(special) ** 2, 17.25), [5.0, 5.0]])
-    with np.errstate(all="ignore"):
-        far, ref = host.far(num, den, pix)
-    assert not (far & ref).any()                       # never prunes what the reference accepts
-    assert far.sum() > 0.2 * len(far) and ref.sum() > 0.1 * len(far)
-    with np.errstate(all="ignore"):
-        wtrue = np.abs(num[:n] / den[:n] - pix[:n])
-    assert far[:n][wtrue > 2.01].all()                 # and does prune everything clearly outside
+    n_drop = n_in = total = 0
+    for rep in range(6):
+        Ts, pts, _, _ = synth.pnp_problem(rng, 60000, 2)
+        pts = pts * scale
+        pts[::7, 2] *= -1.0
+        T = Ts[rep % 2].copy()
+        T[:, 3] *= scale
+        uvl, uvr = _project(T, pts, K, M1, M2)
+        n = len(pts)
+        off = np.concatenate([rng.choice([-2.0, 2.0], n // 3) * (1 + rng.integers(-8, 9, n // 3) * 2.0 ** -52),
+                              rng.choice([-1.0, 1.0], n // 3) * rng.uniform(1.99, 2.02, n // 3),
+                              rng.normal(0, 30, n - 2 * (n // 3))])
+        coord = rng.integers(0, 2, n)
+        lp = uvl + rng.uniform(-1.5, 1.5, (n, 2))
+        lp[np.arange(n), coord] = uvl[np.arange(n), coord] + off
+        rp = uvr + rng.uniform(-1.5, 1.5, (n, 2))
+        dropped, ref = _prefilter_case(oracle, host, T, pts, lp, rp, K, M1, M2)
+        n_drop += int(dropped.sum()); n_in += int(ref.sum()); total += n
+        # everything clearly outside on the left image is dropped (the filter does its job)
+        with np.errstate(all="ignore"):
+            clear = (np.abs(lp - uvl).max(axis=1) > 2.1) & np.isfinite(uvl).all(axis=1)
+        # (a scene shrunk to millimetres keeps the homogeneous "+ 1" of the bound B: conservative, less sharp; one
+        # blown up to 10^5 km trips the 10^9 range guard and is not filtered at all)
+        if scale <= 1.0:
+            assert dropped[clear].mean() > (0.999 if scale == 1.0 else 0.9)
+    assert (n_drop > 0.25 * total or scale > 1.0) and n_in > 0.1 * total
+
+
+def test_fp32_prefilter_random_magnitudes_and_degenerates(oracle):
+    """Magnitudes over 24 decades (fp32 underflow and the 1e9 range guards on both sides), z = 0, NaN, inf,
+    1e308, hypotheses with huge / tiny / NaN translations, a non-rectified rig."""
+    from slamfe import synth
+    host = oracle.ScorerHost()
+    K, M1, M2 = synth.cameras()
+    rng = np.random.default_rng(99)
+    kept_any = dropped_any = 0
+    for rep in range(10):
+        n = 50000
+        pts = rng.normal(0, 1, (n, 3)) * 10 ** rng.uniform(-12, 12, (n, 1))
+        tscale = [1.0, 1e-3, 1e3, 1e-30, 1e12, 1e-45, 1e6, 1.0, 1.0, 1.0][rep]
+        T = np.hstack([synth._rodrigues(rng.normal(0, 1.0, 3)), (rng.normal(0, 1, 3) * tscale)[:, None]])
+        if rep == 7:
+            T[1, 3] = np.nan
+        if rep == 8:
+            T[0, 3] = np.inf
+        uvl, uvr = _project(T, pts, K, M1, M2)
+        jit = 10 ** rng.uniform(-14, 2, (n, 1)) * rng.normal(0, 1, (n, 2))
+        lp = np.nan_to_num(uvl, nan=0.0, posinf=1e300, neginf=-1e300) + jit
+        rp = np.nan_to_num(uvr, nan=0.0, posinf=1e300, neginf=-1e300) + jit[:, ::-1]
+        pts[:6] = [[0, 0, 0], [1, 2, 0], [np.nan, 1, 5], [np.inf, 1, 5], [1e308, 1e308, 1e308], [1e-320, 1e-320, 1e-320]]
+        lp[6:13, 0] = [np.nan, np.inf, -np.inf, 1e308, -1e308, 1e-320, 3e9]
+        lp[13:15, 1] = [np.nan, 2e9]
+        dropped, ref = _prefilter_case(oracle, host, T, pts, lp, rp, K, M1, M2)
+        kept_any += int(ref.sum()); dropped_any += int(dropped.sum())
+    assert kept_any > 1000 and dropped_any > 1000
+    M2r = np.hstack([synth._rodrigues(np.array([0.0, 0.02, 0.0])), M2[:, 3:4]])
+    Ts, pts, lp, rp = synth.pnp_problem(rng, 20000, 1)
+    _prefilter_case(oracle, host, Ts[0], pts, lp, rp, K, M1, M2r)

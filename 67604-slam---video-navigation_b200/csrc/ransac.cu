@@ -46,7 +46,7 @@ struct RansacParams {
     uint8_t *best_mask;
 };
 
-__global__ void __launch_bounds__(RS_THREADS, 3) ransac_score_kernel(const RansacParams p)
+__global__ void __launch_bounds__(RS_THREADS, 4) ransac_score_kernel(const RansacParams p)
 {
     __shared__ alignas(16) double sM[2][RS_HC][24];
     __shared__ alignas(16) float sF[2][RS_HC][16];  // fp32 pre-filter: PL rows 1, 2, 0 (4 each), A_1, A_2, A_0, unused
@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) ransac_score_kernel(const Ransa
                 atomicAdd(p.counts + prev_hyp, s_cnt[(it + 2) % 3][prev_slot]);
             prev_slot = (ok && j == 0) ? slot : -1;
             prev_hyp = static_cast<int>(hbase) + h0 + hh;
+#pragma unroll 2
             for (int h = 0; h < n_valid; ++h) {
                 const float *F = &sF[buf][h][0];
                 // (a) fp32 pre-filter (ransac_core.cuh) on the left image's v: rows 1 and 2.  A bad hypothesis

@@ -153,7 +153,9 @@ class RansacWorkload(Workload):
                 "bound": "fp64", "achieved": fma / launch_ms / 1e6, "peak": peak_fp64_gfma, "unit": "GFMA64/s",
                 "frac": fma / launch_ms / 1e6 / peak_fp64_gfma, "traffic": None, "launch_ms": launch_ms,
                 "note": "algorithmic 24 fp64 FMA per (hypothesis, correspondence) (SURVEY 8d); the perspective "
-                        "divisions are replaced by certified multiplication-form tests; peak measured on this GPU "
+                        "divisions are replaced by certified multiplication-form tests, and a one-sided fp32 "
+                        "pre-filter drops hopeless pairs before any fp64 work (this workload's hypotheses are "
+                        "mostly good, so nearly every pair takes the fp64 path); peak measured on this GPU "
                         "(slamfe_peak_kernel mode 2); not HBM-bound: operands are reused H or N times",
                 "hyp_point_pairs_per_s": self.H * self.N * self.F / launch_ms * 1e3}
 
@@ -293,7 +295,7 @@ class LoopWorkload(Workload):
     def roofline(self, launch_ms, peak_popc):
         r = matcher_roofline("rows only, best-only, compact keys, via slamfe_hamming_top2_pairs", self._kernel_pairs,
                              launch_ms, peak_popc)
-        r["note"] += "; the RANSAC stages (hypotheses + scoring, fp64-bound) are the rest of a step"
+        r["note"] += "; the RANSAC stages (hypotheses + scoring, instruction-issue-bound behind an fp32 pre-filter) are the rest of a step"
         return r
 
     def cpu_baseline(self):

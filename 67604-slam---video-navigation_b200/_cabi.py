@@ -19,7 +19,7 @@ MAX_DESC_BYTES = 64
 MATCH_BEST_ONLY = 1
 MATCH_COMPACT_KEYS = 2
 MATCH_MMA = 4
-ABI_VERSION = 204   # SLAMFE_ABI_VERSION of include/slamfe.h this binding was written against
+ABI_VERSION = 205   # SLAMFE_ABI_VERSION of include/slamfe.h this binding was written against
 
 # name -> (restype, argtypes); mirrors include/slamfe.h one to one
 _SIGNATURES = {

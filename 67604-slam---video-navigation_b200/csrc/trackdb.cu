@@ -20,7 +20,7 @@ namespace {
 constexpr int TI_THREADS = 256;
 
 struct TrackIdParams {
-    const uint2 *fwd_keys;      // (L, 2) rows of frame f (link order): best key -> link index in frame f + 1
+    const uint32_t *fwd_keys;   // (L,) rows of frame f (link order): compact best key -> link index in frame f + 1
     const uint8_t *inlier_fwd;  // (L,) in_prev_cur of database.py:84-85
     const int32_t *l_off, *n_links;
     int n_frames;
@@ -30,7 +30,7 @@ struct TrackIdParams {
 __device__ __forceinline__ bool has_successor(const TrackIdParams &p, int f, int row, int &j)
 {
     if (f >= p.n_frames - 1 || !p.inlier_fwd[row]) return false;
-    const uint32_t k = p.fwd_keys[row].x;
+    const uint32_t k = p.fwd_keys[row];
     if (k == KEY_NONE) return false;
     j = static_cast<int>(k & KEY_IDX_MASK);
     return j < p.n_links[f + 1];
@@ -242,7 +242,7 @@ extern "C" int slamfe_track_ids(const uint32_t *fwd_keys, const uint8_t *inlier_
         return SLAMFE_EINVAL;
     if (n_frames > 65535 * 32) return SLAMFE_ERANGE;
     TrackIdParams p{};
-    p.fwd_keys = reinterpret_cast<const uint2 *>(fwd_keys);
+    p.fwd_keys = fwd_keys;
     p.inlier_fwd = inlier_fwd; p.l_off = l_off; p.n_links = n_links; p.n_frames = n_frames;
     p.pred = pred; p.rank = rank; p.head_cnt = head_cnt; p.head_base = head_base; p.track_id = track_id;
     p.n_tracks = n_tracks;

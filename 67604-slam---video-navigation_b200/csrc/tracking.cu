@@ -23,7 +23,7 @@ namespace {
 constexpr int TG_THREADS = 256;
 
 struct GatherParams {
-    const uint2 *fwd_keys;      // (L, 2): rows of frame t (link order), best key -> link index in frame t+1
+    const uint32_t *fwd_keys;   // (L,): rows of frame t (link order), compact best key -> link index in frame t+1
     const uint32_t *bwd_keys;   // (L,):   rows of frame t+1, best key -> link index in frame t
     const int32_t *l_off, *r_off, *n_links, *n_matches;
     const float2 *pl, *pr;      // keypoints (x, y) of the left / right images
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(TG_THREADS) track_gather_kernel(const GatherPa
         bool good = false;
         int t = -1;
         if (j < n_prev) {
-            const uint32_t k = p.fwd_keys[l0 + j].x;
+            const uint32_t k = p.fwd_keys[l0 + j];
             if (k != KEY_NONE) {
                 t = static_cast<int>(k & KEY_IDX_MASK);
                 if (t < n_cur) {
@@ -201,7 +201,7 @@ extern "C" int slamfe_track_gather(const uint32_t *fwd_keys, const uint32_t *bwd
     if (rc) return rc;
     for (int k = 4; k < 12; ++k)
         if (p.cam.P[k] != p.cam.Q[k]) return SLAMFE_EINVAL;  // links need a shared-row stereo pair
-    p.fwd_keys = reinterpret_cast<const uint2 *>(fwd_keys);
+    p.fwd_keys = fwd_keys;
     p.bwd_keys = bwd_keys;
     p.l_off = l_off; p.r_off = r_off; p.n_links = n_links; p.n_matches = n_matches;
     p.pl = reinterpret_cast<const float2 *>(pts_left);

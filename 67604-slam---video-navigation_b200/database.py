@@ -75,7 +75,7 @@ def frames_from_tables(seq, tables):
                "inliers_percent": 100 * (k / n_matches) if n_matches else None}
         if f > 0:
             plo = int(seq.l_off[f - 1])
-            keys = tables["fwd_keys"][plo:plo + prev_k, 0].view(np.uint32)
+            keys = tables["fwd_keys"][plo:plo + prev_k].view(np.uint32)
             out["fwd_idx"] = (keys & frontend._cabi.KEY_IDX_MASK).astype(np.int64)
             out["fwd_dist"] = (keys >> frontend._cabi.KEY_IDX_BITS).astype(np.float64)
             out["fwd_valid"] = keys != frontend._cabi.KEY_NONE

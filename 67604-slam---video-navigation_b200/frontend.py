@@ -125,7 +125,10 @@ def to_device(seq: PackedSequence, device="cuda", non_blocking=True) -> DeviceSe
         seq.n_frames, int(seq.n_l.max()) if seq.n_frames else 0, int(seq.n_r.max()) if seq.n_frames else 0)
 
 
-RESULT_KEYS = ("match_t", "n_matches", "n_links", "link_src", "links", "xyz", "fwd_keys", "bwd_keys")
+# Tables run_host / results_to_host bring back by default.  `links` (x_left, x_right, y per link) stays on the
+# device unless asked for: the host derives it from its own keypoints (links_from_tables), 12 bytes per row less.
+RESULT_KEYS = ("match_t", "n_matches", "n_links", "link_src", "xyz", "fwd_keys", "bwd_keys")
+ALL_RESULT_KEYS = RESULT_KEYS + ("links",)
 TRACK_KEYS = ("inlier_fwd", "best", "n_good", "n_hyp", "n_hyp_full", "pose", "pose_status")
 
 
@@ -206,7 +209,7 @@ class FrontEnd:
                 "links": torch.empty((L, 3), dtype=torch.float32, device=dev),
                 "feat": torch.empty((L, 64), dtype=torch.uint8, device=dev),
                 "xyz": torch.empty((L, 3), dtype=torch.float32, device=dev),
-                "fwd_keys": torch.empty((L, 2), **i32), "bwd_keys": torch.empty((L,), **i32),
+                "fwd_keys": torch.empty((L,), **i32), "bwd_keys": torch.empty((L,), **i32),
             }
             self._key = key
         return self._out
@@ -230,7 +233,7 @@ class FrontEnd:
         """Stage 4: problem p matches the filtered features of frame p (rows of feat_q) against
         those of frame p+1 (rows of feat_t); forward rows + backward columns from one pass."""
         ops.hamming_top2_batched(feat_q, q_off, feat_t, t_off, n_pairs, max_links, max_links, DESC_BYTES,
-                                 q_cnt=q_cnt, t_cnt=t_cnt, want_cols=True, best_only=True,
+                                 q_cnt=q_cnt, t_cnt=t_cnt, want_cols=True, best_only=True, compact=True,
                                  row_keys=fwd_keys, col_keys=bwd_keys)
 
     def run(self, ds: DeviceSequence):
@@ -619,6 +622,19 @@ class FrontEnd:
                     d2h += n_rows * v[0:1].numel() * v.element_size()
                 torch.cuda.current_stream(dev).synchronize()
         return tables, int(h2d), int(d2h)
+
+
+def links_from_tables(seq: PackedSequence, tables, f):
+    """The `links` rows of frame f — [x_left, x_right, (yl + yr) / 2] per link, float32 as the device table
+    holds them (tracking_database.py:243) — from the host's own keypoints and the match_t / link_src tables, so
+    the (L, 3) table need not travel back."""
+    lo, ro, k = int(seq.l_off[f]), int(seq.r_off[f]), int(tables["n_links"][f])
+    src = np.asarray(tables["link_src"][lo:lo + k], dtype=np.int64)
+    dst = np.asarray(tables["match_t"][lo:lo + int(seq.n_l[f])], dtype=np.int64)[src]
+    pl, pr = np.asarray(seq.pts_l[lo:lo + int(seq.n_l[f])]), np.asarray(seq.pts_r[ro:ro + int(seq.n_r[f])])
+    y = (pl[src, 1].astype(np.float64) + pr[dst, 1].astype(np.float64)) / 2
+    return np.stack([pl[src, 0], pr[dst, 0], y.astype(np.float32)], axis=1).astype(np.float32) if k else \
+        np.zeros((0, 3), np.float32)
 
 
 def descriptor_pairs(n_l, n_r, n_links=None) -> int:

@@ -277,7 +277,7 @@ def ransac_score(T, pts, l_pix, r_pix, K, M1, M2, hyp_valid=None, pt_off=None, n
 
 def track_ids(fwd_keys, inlier_fwd, l_off, n_links, n_frames, out=None):
     """Track id of every link row of a sequence (slamfe_track_ids; TrackingDB.add_frame's bookkeeping,
-    tracking_database.py:273-337).  fwd_keys (L, 2) / inlier_fwd (L,) as FrontEnd.track leaves them.
+    tracking_database.py:273-337).  fwd_keys (L,) compact best keys / inlier_fwd (L,) as FrontEnd.track leaves them.
     Returns (track_id (L,) int32 with -1 = NO_ID, n_tracks (1,) int32, head_base (n_frames + 1,) int32)."""
     torch = _torch()
     dev = fwd_keys.device

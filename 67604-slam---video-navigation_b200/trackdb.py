@@ -310,7 +310,7 @@ def build(seq, tables, link_factory=Link):
     np.cumsum(n_links, out=frame_off[1:])
     if F > 1:
         n_good = tables["n_good"][:F - 1]
-        keys = tables["fwd_keys"][rows[f_of < F - 1], 0].view(np.uint32) if len(rows) else np.zeros(0, np.uint32)
+        keys = tables["fwd_keys"][rows[f_of < F - 1]].view(np.uint32) if len(rows) else np.zeros(0, np.uint32)
         if (n_links[:-1] == 0).any() or (keys == _cabi.KEY_NONE).any():
             raise IndexError("tuple index out of range")    # database.py:56 on an empty match list
         if (n_good < 4).any():                                # ransac.py:95
@@ -322,7 +322,7 @@ def build(seq, tables, link_factory=Link):
         per_frame_idx, per_frame_inl = [], []
         for f in range(F - 1):
             a = int(l_off[f])
-            k = tables["fwd_keys"][a:a + int(n_links[f]), 0].view(np.uint32)
+            k = tables["fwd_keys"][a:a + int(n_links[f])].view(np.uint32)
             per_frame_idx.append(k & _cabi.KEY_IDX_MASK)
             per_frame_inl.append(tables["inlier_fwd"][a:a + int(n_links[f])])
         ids, n_tracks = track_ids_host(per_frame_idx, per_frame_inl, n_links)

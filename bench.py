@@ -283,7 +283,7 @@ def main():
         stride) — per left row [stereo match, best forward key], per frame [n_matches, n_links]."""
         if world == 1:
             return None
-        rows = torch.stack([o["match_t"][:n_rows_own], o["fwd_keys"][:n_rows_own, 0]], dim=1)
+        rows = torch.stack([o["match_t"][:n_rows_own], o["fwd_keys"][:n_rows_own]], dim=1)
         g_rows, _ = sdist.all_gather_padded(rows, lengths=row_lengths)
         summ = torch.stack([o["n_matches"][:F], o["n_links"][:F]], dim=1)
         g_frames, _ = sdist.all_gather_padded(summ, lengths=np.full(world, F))
@@ -526,7 +526,7 @@ def main():
                     if i + 1 < wlen and res[i + 1]["fwd_t"] is not None:
                         nxt = res[i + 1]
                         fi, fd = ops.keys_to_numpy(host["fwd_keys"][lo:lo + k])
-                        ok &= bool(np.array_equal(fi[:, 0], nxt["fwd_t"]) and np.array_equal(fd[:, 0], nxt["fwd_d"]))
+                        ok &= bool(np.array_equal(fi, nxt["fwd_t"]) and np.array_equal(fd, nxt["fwd_d"]))
                         lo1, k1n = int(seq_t["l_off"][f + 1]), len(nxt["inl"])
                         bi, _ = ops.keys_to_numpy(host["bwd_keys"][lo1:lo1 + k1n])
                         ok &= bool(np.array_equal(bi, nxt["bwd_t"]))

@@ -51,7 +51,7 @@ typedef void *slamfe_stream_t;
 
 /* ABI version of this header: bumped whenever an entry point is added or a signature changes.  The loader
  * (_cabi.load_library) refuses a library whose slamfe_version() differs. */
-#define SLAMFE_ABI_VERSION 204
+#define SLAMFE_ABI_VERSION 205
 int slamfe_version(void);
 const char *slamfe_error_string(int code);
 
@@ -238,6 +238,8 @@ int slamfe_ransac_score(const double *T, const uint8_t *hyp_valid, int H,
  *     (ransac.py:59-67, database.py:26,80); n_hyp_full[f] (optional, may be NULL) receives the
  *     UNCAPPED iteration count, so the caller can see which pairs h_max truncated (n_hyp_full[f] >
  *     h_max) and re-run those at their full count — the reference always runs the full count.
+ * fwd_keys (rows,) uint32: COMPACT best keys of the forward pass (SLAMFE_MATCH_BEST_ONLY | SLAMFE_MATCH_COMPACT_KEYS),
+ * bwd_keys (rows,) uint32: its column minima.
  * Row-indexed outputs use frame f's row offset l_off[f] as base and hold n_good[f] entries:
  *   good_j, good_t (L,) int32 link indices in frame f / f+1;  pts (L,3), lpix (L,2), rpix (L,2) fp64.
  * They are the pts / l_pix / r_pix (pt_off = l_off, pt_cnt = n_good) of slamfe_ransac_hypotheses and
@@ -299,7 +301,8 @@ int slamfe_ransac_hypotheses(const double *pts, const double *l_pix, const int32
 /*
  * Track ids of a whole sequence — the bookkeeping of TrackingDB.add_frame
  * (backend/database/tracking_database.py:273-337) over the tables of the tracking stages: link k of frame f
- * (row l_off[f] + k) continues into link j = index(fwd_keys[row][0]) of frame f + 1 when inlier_fwd[row] is set
+ * (row l_off[f] + k) continues into link j = index(fwd_keys[row]) of frame f + 1 when inlier_fwd[row] is set
+ * (fwd_keys (rows_total,): COMPACT best keys, SLAMFE_MATCH_BEST_ONLY | SLAMFE_MATCH_COMPACT_KEYS)
  * (in_prev_cur, database.py:84-85; mutual matches, hence one-to-one).  A link with an inlier successor and no
  * inlier predecessor starts a track; ids are issued as issue_trackId does (:196-198): frame pairs in order,
  * ascending previous-feature index inside a pair.

@@ -51,8 +51,7 @@ def test_sequence_pipeline_vs_oracle(slamfe, oracle):
         lo, k = seq.l_off[f], len(feats[f])
         fi, fd = ops.keys_to_numpy(host["fwd_keys"][lo:lo + k])
         oi, od = oracle.match(feats[f], feats[f + 1])  # the pipeline keeps the best neighbour only
-        assert np.array_equal(fi[:, 0], oi) and np.array_equal(fd[:, 0], od)
-        assert (fi[:, 1] == -1).all()
+        assert fi.shape == (k,) and np.array_equal(fi, oi) and np.array_equal(fd, od)   # compact keys: one per row
         lo1, k1 = seq.l_off[f + 1], len(feats[f + 1])
         obi, obd = oracle.match(feats[f + 1], feats[f])
         got_b = ops.keys_to_numpy(host["bwd_keys"][lo1:lo1 + k1])
@@ -71,11 +70,11 @@ def test_host_pipeline_equals_resident_run(slamfe, chunk):
     frames = make_sequence(rng, [700, 900, 40, 1100, 650, 800, 500])
     seq = frontend.pack_sequence(frames)
     fe = frontend.FrontEnd()
-    ref, _, _ = frontend.results_to_host(fe.run(frontend.to_device(seq)))
+    ref, _, _ = frontend.results_to_host(fe.run(frontend.to_device(seq)), keys=frontend.ALL_RESULT_KEYS)
     ref = {k: v.copy() for k, v in ref.items()}
     fe2 = frontend.FrontEnd()
     for _ in range(2):  # second pass reuses every buffer
-        got, h2d, d2h = fe2.run_host(seq, chunk_frames=chunk)
+        got, h2d, d2h = fe2.run_host(seq, chunk_frames=chunk, keys=frontend.ALL_RESULT_KEYS)
         assert h2d >= seq.h2d_bytes() and d2h > 0
         for f in range(seq.n_frames):
             lo, k = seq.l_off[f], ref["n_links"][f]
@@ -84,6 +83,9 @@ def test_host_pipeline_equals_resident_run(slamfe, chunk):
             assert np.array_equal(got["match_t"][lo:lo + n], ref["match_t"][lo:lo + n])
             for key in ("link_src", "links", "xyz", "fwd_keys", "bwd_keys"):
                 assert np.array_equal(got[key][lo:lo + k], ref[key][lo:lo + k]), (key, f)
+            # `links` is not in the default D2H set: the host derives it, bit for bit
+            assert np.array_equal(frontend.links_from_tables(seq, got, f), ref["links"][lo:lo + k]), f
+    assert "links" not in fe2.run_host(seq, chunk_frames=chunk)[0]
     torch.cuda.synchronize()
     # with the tracking stages: same samples (RNG keyed by global pair index), same tables
     trk = fe.track(frontend.to_device(seq), h_max=40, seed=9)
@@ -449,11 +451,11 @@ def test_48_frames_at_bench_size_against_the_reference_run(slamfe, golden):
         lo, k = int(seq.l_off[f]), int(n_links[f])
         src = tables["link_src"][lo:lo + k]
         assert np.array_equal(seq.pts_l[lo + src, 0], g[f"x_left{f}"])             # the same links in the same order
-        assert np.allclose(tables["links"][lo:lo + k, 2], g[f"y{f}"], rtol=0, atol=1e-4)
+        assert np.allclose(frontend.links_from_tables(seq, tables, f)[:, 2], g[f"y{f}"], rtol=0, atol=1e-4)
         assert abs(100 * k / tables["n_matches"][f] - g["inliers_percent"][f]) < 1e-9
         if f + 1 < F:
             idx, dist = ops.keys_to_numpy(tables["fwd_keys"][lo:lo + k])
-            assert np.array_equal(idx[:, 0], g[f"match_t{f + 1}"]) and np.array_equal(dist[:, 0], g[f"match_d{f + 1}"])
+            assert np.array_equal(idx, g[f"match_t{f + 1}"]) and np.array_equal(dist, g[f"match_d{f + 1}"])
             want = np.unpackbits(g[f"inliers{f + 1}"])[:k].astype(bool)
             got = tables["inlier_fwd"][lo:lo + k].astype(bool)
             ref_flags[lo:lo + k] = want
@@ -496,7 +498,7 @@ def test_track_ids_edge_cases(slamfe):
     inl = out["inlier_fwd"].cpu().numpy()
     n_links = out["n_links"].cpu().numpy()
     ids, n_tracks = trackdb.track_ids_host(
-        [fwd[int(seq.l_off[f]):int(seq.l_off[f]) + int(n_links[f]), 0].view(np.uint32) & 0x3FFFFF for f in range(3)],
+        [fwd[int(seq.l_off[f]):int(seq.l_off[f]) + int(n_links[f])].view(np.uint32) & 0x3FFFFF for f in range(3)],
         [inl[int(seq.l_off[f]):int(seq.l_off[f]) + int(n_links[f])] for f in range(3)], n_links)
     assert int(out["n_tracks"].item()) == n_tracks
     for f in range(4):

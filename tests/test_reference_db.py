@@ -37,7 +37,7 @@ def _oracle_tables(seq, frames, oracle, inlier_flags):
     from slamfe import _cabi
     L, F = seq.desc_l.shape[0], seq.n_frames
     t = {"match_t": np.full(L, -1, np.int32), "n_matches": np.zeros(F, np.int32), "n_links": np.zeros(F, np.int32),
-         "link_src": np.full(L, -1, np.int32), "fwd_keys": np.full((L, 2), -1, np.int32),
+         "link_src": np.full(L, -1, np.int32), "fwd_keys": np.full(L, -1, np.int32),
          "inlier_fwd": np.zeros(L, np.uint8)}
     feats = []
     for f, (pl, pr, dl, dr) in enumerate(frames):
@@ -51,7 +51,7 @@ def _oracle_tables(seq, frames, oracle, inlier_flags):
     for f in range(F - 1):
         lo, k = int(seq.l_off[f]), len(feats[f])
         fi, fd = oracle.match(feats[f], feats[f + 1])
-        t["fwd_keys"][lo:lo + k, 0] = ((fd.astype(np.uint32) << _cabi.KEY_IDX_BITS) | fi.astype(np.uint32)).view(np.int32)
+        t["fwd_keys"][lo:lo + k] = ((fd.astype(np.uint32) << _cabi.KEY_IDX_BITS) | fi.astype(np.uint32)).view(np.int32)
         t["inlier_fwd"][lo:lo + k] = inlier_flags[f + 1]
     return t
 
@@ -217,7 +217,7 @@ def test_soa_tracking_db_equals_the_reference_tracking_db(oracle, tmp_path):
     assert all(n.endswith(".npy") for n in zipfile.ZipFile(path).namelist())     # plain arrays, no pickle
     # --- the device table path: track ids supplied as a table (slamfe_track_ids' output format)
     ids, n_tracks = trackdb.track_ids_host(
-        [tables["fwd_keys"][int(seq.l_off[f]):int(seq.l_off[f]) + int(tables["n_links"][f]), 0].view(np.uint32) & 0x3FFFFF
+        [tables["fwd_keys"][int(seq.l_off[f]):int(seq.l_off[f]) + int(tables["n_links"][f])].view(np.uint32) & 0x3FFFFF
          for f in range(seq.n_frames - 1)],
         [tables["inlier_fwd"][int(seq.l_off[f]):int(seq.l_off[f]) + int(tables["n_links"][f])] for f in range(seq.n_frames - 1)],
         tables["n_links"])

@@ -214,7 +214,9 @@ int slamfe_triangulate_dlt_f64(const double *pxy, const double *qxy, int64_t n,
  *              hypothesis scored > 0 inliers
  *   best_mask  out (total_points,) uint8: inlier mask of the best hypothesis (ransac.py:112)
  *   work       scratch, (n_frames,) int32, zeroed by the call
- * fp64 throughout, association order ((K@T)@M_h)@X, IEEE division, strict < 2 (ransac.py:38-56).
+ * Every counted verdict is the reference's: fp64, association order ((K@T)@M_h)@X, IEEE division, strict < 2
+ * (ransac.py:38-56), evaluated division-free with a rounding certificate and the literal division as fallback;
+ * pairs that a one-sided fp32 pre-filter proves outside never reach the fp64 path (csrc/ransac_core.cuh).
  */
 int slamfe_ransac_score(const double *T, const uint8_t *hyp_valid, int H,
                         const double *pts, const double *l_pix, const double *r_pix,

@@ -260,21 +260,34 @@ class CovarianceGraph:
 
     def __init__(self, n_nodes):
         self.n_nodes = int(n_nodes)
-        self._edges = {}          # (min, max) -> cov (6, 6)
+        self._edges = {}          # (min, max) -> (cov for min->max, cov for max->min, weight)
 
-    def add_edge(self, v1, v2, cov):
-        self._edges[(min(int(v1), int(v2)), max(int(v1), int(v2)))] = np.array(cov, dtype=np.float64).reshape(6, 6)
+    def add_edge(self, v1, v2, cov, cov_back=None, weight=None):
+        """cov is added to a path that traverses the edge v1 -> v2, cov_back (default: cov) to one that
+        traverses it v2 -> v1 — the reference keeps direction-dependent covariances for consecutive keyframes
+        (loop_closure.py:264-279: cov_dict[str((i, i+1))] and cov_dict[str((i+1, i))]); weight defaults to
+        det(cov) (graph.py:11-13)."""
+        a, b = int(v1), int(v2)
+        c = np.array(cov, dtype=np.float64).reshape(6, 6)
+        cb = c if cov_back is None else np.array(cov_back, dtype=np.float64).reshape(6, 6)
+        w = float(np.linalg.det(c)) if weight is None else float(weight)
+        self._edges[(min(a, b), max(a, b))] = (c, cb, w) if a <= b else (cb, c, w)
 
     def remove_edge(self, v1, v2):
         return self._edges.pop((min(int(v1), int(v2)), max(int(v1), int(v2))), None) is not None
 
     def arrays(self):
-        """CSR adjacency + per-edge weight / covariance.  Neighbours are listed in insertion order of the
-        edges, as the reference's dict-of-dicts iterates them."""
+        """CSR adjacency + per-DIRECTED-edge weight / covariance (rows 2e: min -> max, 2e + 1: max -> min).
+        Neighbours are listed in insertion order of the edges, as the reference's dict-of-dicts iterates them.
+        The device Dijkstra runs from the query keyframe c_n outwards, the reference sums covariances along
+        the path c_i -> c_n: the adjacency entry "u lists v" therefore carries the row of the traversal v -> u."""
         E = len(self._edges)
         ends = np.array(list(self._edges), dtype=np.int32).reshape(E, 2)
-        cov = np.array(list(self._edges.values()), dtype=np.float64).reshape(E, 36)
-        w = np.array([np.linalg.det(c.reshape(6, 6)) for c in cov], dtype=np.float64)     # graph.py:11-13
+        cov = np.zeros((2 * E, 36), dtype=np.float64)
+        w = np.zeros(2 * E, dtype=np.float64)
+        for e, (c_ab, c_ba, wt) in enumerate(self._edges.values()):
+            cov[2 * e], cov[2 * e + 1] = c_ab.reshape(36), c_ba.reshape(36)
+            w[2 * e] = w[2 * e + 1] = wt
         deg = np.zeros(self.n_nodes + 1, dtype=np.int64)
         for a, b in ends:
             deg[a + 1] += 1
@@ -284,9 +297,9 @@ class CovarianceGraph:
         node = np.zeros(2 * E, dtype=np.int32)
         edge = np.zeros(2 * E, dtype=np.int32)
         for e, (a, b) in enumerate(ends):
-            node[fill[a]], edge[fill[a]] = b, e
+            node[fill[a]], edge[fill[a]] = b, 2 * e + 1      # hop a -> b from the query = traversal b -> a
             fill[a] += 1
-            node[fill[b]], edge[fill[b]] = a, e
+            node[fill[b]], edge[fill[b]] = a, 2 * e          # hop b -> a from the query = traversal a -> b
             fill[b] += 1
         return off, node, edge, w, cov
 
@@ -316,4 +329,60 @@ def select_candidates(dist_row, index_list=None, threshold=MAHALANOBIS_THRESHOLD
 def get_good_candidates(c_n_index, poses, graph, index_list=None, gap=KEY_FRAME_GAP):
     """loop_closure.py:199-228 on arrays: the candidate keyframes of keyframe c_n_index."""
     dist, _ = gate_distances(poses, graph, [c_n_index], gap=gap)
+    return select_candidates(dist[0], index_list)
+
+
+# -- the same behind the reference's own signature (GTSAM-typed arguments, duck-typed here) --------
+def traversal_covariance(a, b, cov_dict, marginals=None, symbol=None):
+    """The covariance get_relative_covariance_along_path (loop_closure.py:110-135) adds for the hop a -> b
+    (frame numbers): the cached str((a, b)) entry (consecutive keyframes, :264-279); otherwise what
+    get_relative_consecutive_covariance (:84-107) returns — the cached per-frame entry cov_dict[b] if there is
+    one (there is for every keyframe after init, :282,:286 — so a loop-closure edge contributes the covariance of
+    b given its PREDECESSOR keyframe: a quirk of the reference, kept), else the inverse of b's block of the
+    joint marginal information of (a, b)."""
+    k = str((a, b))
+    if k in cov_dict:
+        return np.asarray(cov_dict[k], dtype=np.float64)
+    if b in cov_dict:
+        return np.asarray(cov_dict[b], dtype=np.float64)
+    c1, c2 = symbol("c", a), symbol("c", b)
+    keys = [c1, c2]
+    try:  # gtsam.KeyVector when the real module is around (loop_closure.py:99-101)
+        import gtsam
+        kv = gtsam.KeyVector()
+        kv.append(c1)
+        kv.append(c2)
+        keys = kv
+    except Exception:
+        pass
+    return np.linalg.inv(np.asarray(marginals.jointMarginalInformation(keys).at(c2, c2), dtype=np.float64))
+
+
+def covariance_graph_from_reference(ref_graph, index_list, cov_dict, marginals=None, symbol=None):
+    """CovarianceGraph (nodes = positions in index_list) from the reference's `cov_dijkstra_graph`
+    (backend/loop/graph.py: adjacency dict in insertion order, weights as stored) and its
+    `relative_covariance_dict`, with the direction-dependent covariances of traversal_covariance."""
+    pos = {int(f): i for i, f in enumerate(index_list)}
+    g = CovarianceGraph(len(index_list))
+    for a, nbrs in ref_graph.graph.items():
+        for b, w in nbrs.items():
+            if a in pos and b in pos and (min(pos[a], pos[b]), max(pos[a], pos[b])) not in g._edges:
+                g.add_edge(pos[a], pos[b], traversal_covariance(a, b, cov_dict, marginals, symbol),
+                           cov_back=traversal_covariance(b, a, cov_dict, marginals, symbol), weight=w)
+    return g
+
+
+def get_good_candidates_typed(c_n_index, marginals, result, index_list, ref_graph, cov_dict, symbol=None):
+    """Drop-in for loop_closure.get_good_candidates(c_n_index, marginals, result, index_list)
+    (loop_closure.py:199-228; check_candidate :164-196): `result` needs atPose3(key).matrix(), `marginals`
+    jointMarginalInformation (only for edges the dictionaries do not cover); ref_graph / cov_dict are the
+    module globals cov_dijkstra_graph / relative_covariance_dict (loop_closure.py:27,30), read at call time by
+    patch(batched_gating=True).  All candidates of the keyframe are gated in one launch."""
+    if symbol is None:
+        import gtsam
+        symbol = gtsam.symbol
+    graph = covariance_graph_from_reference(ref_graph, index_list, cov_dict, marginals, symbol)
+    poses = np.stack([np.asarray(result.atPose3(symbol("c", int(f))).matrix(), dtype=np.float64)[:3, :4]
+                      for f in index_list])
+    dist, _ = gate_distances(poses, graph, [c_n_index], gap=KEY_FRAME_GAP)
     return select_candidates(dist[0], index_list)

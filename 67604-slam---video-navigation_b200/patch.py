@@ -53,7 +53,8 @@ def _akaze_feature():
     return cv2.AKAZE_create(threshold=0.0008, nOctaves=4, nOctaveLayers=4)
 
 
-def patch(modules=None, batched_db=False, batched_loop=False, rebind_feature=True, **pipeline_kw):
+def patch(modules=None, batched_db=False, batched_loop=False, rebind_feature=True, batched_gating=False,
+          **pipeline_kw):
     """Rebind every already-imported reference module (or the given {name: module} mapping).
     Also copies the reference's cameras into slamfe.ransac so both sides score with the same
     K, M1, M2.  Returns {module_name: [rebound attribute names]}; `unpatch(token)` restores.
@@ -71,7 +72,11 @@ def patch(modules=None, batched_db=False, batched_loop=False, rebind_feature=Tru
 
     batched_loop=True replaces `loop_closure.check_candidate_match` / `consensus_matches`
     (loop_closure.py:405-436, :572-599) with slamfe.loop's: all candidates of a keyframe are verified
-    in one device-resident batch (match + 888-hypothesis RANSAC-PnP each)."""
+    in one device-resident batch (match + 888-hypothesis RANSAC-PnP each).
+
+    batched_gating=True replaces `loop_closure.get_good_candidates` (loop_closure.py:199-228) with
+    slamfe.loop.get_good_candidates_typed bound to the module's own `cov_dijkstra_graph` /
+    `relative_covariance_dict` (read at call time): every earlier keyframe is gated in one launch."""
     from . import ransac
     rep = replacements()
     mods = modules if modules is not None else sys.modules
@@ -105,6 +110,17 @@ def patch(modules=None, batched_db=False, batched_loop=False, rebind_feature=Tru
                 saved.append((lcm, a, getattr(lcm, a)))
                 setattr(lcm, a, fn)
                 done.setdefault("final_project.backend.loop.loop_closure", []).append(a)
+    if batched_gating and lcm is not None and hasattr(lcm, "get_good_candidates"):
+        from . import loop as sloop
+
+        def get_good_candidates(c_n_index, marginals, result, index_list, _m=lcm):
+            sym = getattr(getattr(_m, "gtsam", None), "symbol", None)
+            return sloop.get_good_candidates_typed(c_n_index, marginals, result, index_list, _m.cov_dijkstra_graph,
+                                                   _m.relative_covariance_dict, symbol=sym)
+
+        saved.append((lcm, "get_good_candidates", lcm.get_good_candidates))
+        lcm.get_good_candidates = get_good_candidates
+        done.setdefault("final_project.backend.loop.loop_closure", []).append("get_good_candidates")
     if batched_db:
         dbm = mods.get("final_project.backend.database.database")
         if dbm is not None and hasattr(dbm, "create_db"):

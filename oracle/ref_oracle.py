@@ -658,3 +658,27 @@ def gate_distances(poses, edges, n, gap=10, graph_cls=None):
         xi = pose3_logmap(Rn.T @ poses[i][:3, :3], Rn.T @ (poses[i][:3, 3] - tn))
         out[i] = np.sqrt(xi @ np.linalg.solve(cov, xi))
     return out
+
+
+def gate_distances_typed(poses, adj, cov_dict, index_list, n, gap=10):
+    """get_good_candidates' distances (loop_closure.py:164-228) with the reference's own bookkeeping: `adj` is
+    cov_dijkstra_graph.graph ({frame: {frame: weight}}, insertion order), `cov_dict` relative_covariance_dict
+    (str((a, b)) entries for consecutive keyframes, :264-279, int entries per keyframe, :282,:286).  The
+    covariance of the hop a -> b is looked up as get_relative_covariance_along_path does (:121-130):
+    cov_dict[str((a, b))], else what get_relative_consecutive_covariance returns first (:94-97): cov_dict[b].
+    poses: (K, 3, 4) camera-to-world by POSITION in index_list.  Returns (K,) distances, inf where not a candidate."""
+    K = len(index_list)
+    out = np.full(K, np.inf)
+    Rn, tn = poses[n][:3, :3], poses[n][:3, 3]
+    for i in range(0, n - gap):
+        path = dijkstra_path(adj, index_list[i], index_list[n])
+        if path is None:
+            continue
+        cov = None
+        for a, b in zip(path[:-1], path[1:]):
+            c = np.asarray(cov_dict[str((a, b))] if str((a, b)) in cov_dict else cov_dict[b], dtype=np.float64)
+            cov = c.copy() if cov is None else cov + c
+        xi = pose3_logmap(Rn.T @ poses[i][:3, :3], Rn.T @ (poses[i][:3, 3] - tn))
+        out[i] = np.sqrt(xi @ np.linalg.solve(cov, xi))
+    return out
+

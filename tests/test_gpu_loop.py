@@ -258,3 +258,94 @@ def test_candidate_gating_vs_oracle(slamfe, oracle):
         assert got_sel == [i for _, i in ref] and len(got_sel) <= loop.MAX_CANDIDATES
     assert shortcuts > 0                                     # the loop edges are used by some shortest paths
     assert loop.get_good_candidates(5, poses, g) == []      # nothing is KEY_FRAME_GAP behind keyframe 5
+
+
+class _FakePose3:
+    def __init__(self, T):
+        self._T = np.vstack([T, [0, 0, 0, 1.0]])
+
+    def matrix(self):
+        return self._T
+
+
+class _FakeValues:
+    """result.atPose3(key) of gtsam.Values, keys = ('c', frame) tuples from the stand-in symbol()."""
+    def __init__(self, poses_by_frame):
+        self.p = poses_by_frame
+
+    def atPose3(self, key):
+        return _FakePose3(self.p[key[1]])
+
+
+class _FakeGraph:
+    """The reference's backend/loop/graph.py Graph, as far as the gating reads it (.graph, det weights)."""
+    def __init__(self):
+        self.graph = {}
+
+    def add_edge(self, a, b, cov):
+        w = np.linalg.det(cov)
+        self.graph.setdefault(a, {})[b] = w
+        self.graph.setdefault(b, {})[a] = w
+
+
+@pytest.mark.gpu
+def test_typed_gating_dropin_follows_the_reference_bookkeeping(slamfe, oracle):
+    """loop.get_good_candidates_typed — the drop-in behind loop_closure.get_good_candidates' own signature
+    (marginals, result, index_list) — on stand-ins for the GTSAM objects (gtsam is not in this image) and for
+    the module globals cov_dijkstra_graph / relative_covariance_dict filled as
+    init_dijksra_graph_relative_covariance_dict does (loop_closure.py:246-287): direction-dependent covariances
+    for consecutive keyframes, per-frame entries, loop-closure edges that only live in the graph.  Expected
+    distances: the oracle's restatement of check_candidate with the same dictionaries."""
+    from slamfe import loop
+    import sys
+    sys.path.insert(0, __import__("os").path.dirname(__file__))
+    from test_oracle import _random_pose_graph
+    rng = np.random.default_rng(197)
+    K = 180
+    poses, edges = _random_pose_graph(rng, K=K, n_loops=6)
+    index_list = sorted(rng.choice(np.arange(3 * K), K, replace=False).tolist())       # keyframe frame numbers
+    symbol = lambda ch, i: (ch, int(i))
+
+    def spd():
+        a = rng.normal(0, 1, (6, 6))
+        return (a @ a.T + 6 * np.eye(6)) * 10.0 ** rng.uniform(-4, -2)
+
+    ref_graph, cov_dict = _FakeGraph(), {}
+    for a, b, c in edges:
+        fa, fb = index_list[a], index_list[b]
+        ref_graph.add_edge(fa, fb, c)                          # graph weights: det of the stored covariance
+        if b == a + 1:                                         # consecutive keyframes: loop_closure.py:264-282
+            cov_dict[str((fa, fb))] = c
+            cov_dict[str((fb, fa))] = spd()                    # c1 given c2: a different matrix
+            cov_dict[fb] = c
+    cov_dict[index_list[0]] = spd()                            # :286
+    values = _FakeValues({index_list[i]: poses[i] for i in range(K)})
+    checked = used_loop = 0
+    for n in [11, 60, 61, 140, K - 1]:
+        want = oracle.gate_distances_typed(poses, ref_graph.graph, cov_dict, index_list, n)
+        graph = loop.covariance_graph_from_reference(ref_graph, index_list, cov_dict, None, symbol)
+        dist, hops = loop.gate_distances(poses, graph, [n])
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isfinite(dist[0]), fin)
+        assert np.allclose(dist[0][fin], want[fin], rtol=1e-9, atol=0)
+        used_loop += int((hops[0][fin] < n - np.nonzero(fin)[0]).sum())
+        got = loop.get_good_candidates_typed(n, None, values, index_list, ref_graph, cov_dict, symbol=symbol)
+        ref = sorted([(want[i], i) for i in np.nonzero(want < loop.MAHALANOBIS_THRESHOLD)[0]])[:loop.MAX_CANDIDATES]
+        assert got == [index_list[i] for _, i in ref]
+        checked += len(got)
+    assert used_loop > 0 and checked > 0   # loop edges are used by some shortest paths; some candidates pass the gate
+    # an edge no dictionary covers falls back to the joint marginal information, as loop_closure.py:99-106
+
+    class _Info:
+        def __init__(self, m):
+            self.m = m
+
+        def at(self, a, b):
+            return self.m
+
+    class _Marg:
+        def jointMarginalInformation(self, keys):
+            return _Info(np.diag([4.0] * 6))
+
+    c = loop.traversal_covariance(7, 9, {}, _Marg(), symbol)
+    assert np.allclose(c, np.eye(6) / 4)

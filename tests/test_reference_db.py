@@ -311,3 +311,89 @@ def test_patch_rebinds_a_non_binary_feature_and_pack_frames_validates(monkeypatc
         sdb.pack_frames([(pts, pts, np.zeros((5, 128), np.float32), np.zeros((5, 128), np.float32))], pin=False)
     with pytest.raises(TypeError, match="uint8"):
         sdb.pack_frames([(pts, pts, np.zeros((5, 32), np.uint8), np.zeros((5, 32), np.uint8))], pin=False)
+
+
+def test_patch_batched_gating_reads_the_reference_module_globals(monkeypatch):
+    """patch(batched_gating=True) on the real reference module tree: `loop_closure.get_good_candidates`
+    (loop_closure.py:199-228) is rebound to slamfe.loop.get_good_candidates_typed, which reads the module's own
+    `cov_dijkstra_graph` (the unmodified Graph class, graph.py) and `relative_covariance_dict` at call time.
+    The device launch is replaced by a NumPy walk over the very arrays the kernel would get
+    (CovarianceGraph.arrays(): directed rows), so this checks the translation of the reference's structures;
+    expected values: the oracle's restatement of check_candidate over the reference's own adjacency dict."""
+    import sys
+    from oracle import ref_oracle as oracle
+    from test_oracle import _random_pose_graph
+    ref = refshim.load_loop_closure()
+    from slamfe import loop as sloop, patch
+    lc = ref.loop_closure
+    rng = np.random.default_rng(11)
+    K = 60
+    poses, edges = _random_pose_graph(rng, K=K, n_loops=4)
+    index_list = sorted(rng.choice(np.arange(4 * K), K, replace=False).tolist())
+
+    def spd():
+        a = rng.normal(0, 1, (6, 6))
+        return (a @ a.T + 6 * np.eye(6)) * 1e-3
+
+    graph, cov_dict = type(lc.cov_dijkstra_graph)(), {}
+    for a, b, c in edges:
+        graph.add_edge(index_list[a], index_list[b], np.array(c))
+        if b == a + 1:
+            cov_dict[str((index_list[a], index_list[b]))] = c
+            cov_dict[str((index_list[b], index_list[a]))] = spd()
+            cov_dict[index_list[b]] = c
+    cov_dict[index_list[0]] = spd()
+    monkeypatch.setattr(lc, "cov_dijkstra_graph", graph)
+    monkeypatch.setattr(lc, "relative_covariance_dict", cov_dict)
+    monkeypatch.setattr(sys.modules["gtsam"], "symbol", lambda ch, i: (ch, int(i)), raising=False)
+
+    class Values:
+        def atPose3(self, key):
+            T = np.vstack([poses[index_list.index(key[1])], [0, 0, 0, 1.0]])
+            return type("P", (), {"matrix": lambda self: T})()
+
+    def gate_on_host(poses_, g, queries, gap=sloop.KEY_FRAME_GAP):
+        off, node, edge, w, cov = g.arrays()
+        out = np.full((len(queries), len(poses_)), np.inf)
+        for qi, n in enumerate(queries):                     # Dijkstra from the query, as the kernel runs it
+            import heapq
+            dist, pred, pe = {n: 0.0}, {}, {}
+            pq = [(0.0, n)]
+            while pq:
+                d, u = heapq.heappop(pq)
+                if d > dist.get(u, np.inf):
+                    continue
+                for e in range(off[u], off[u + 1]):
+                    v, nd = int(node[e]), d + w[edge[e]]
+                    if nd < dist.get(v, np.inf):
+                        dist[v], pred[v], pe[v] = nd, u, int(edge[e])
+                        heapq.heappush(pq, (nd, v))
+            Rn, tn = poses_[n][:3, :3], poses_[n][:3, 3]
+            for i in range(0, n - gap):
+                c, v = None, i
+                while v != n:
+                    c = cov[pe[v]].reshape(6, 6).copy() if c is None else c + cov[pe[v]].reshape(6, 6)
+                    v = pred[v]
+                xi = oracle.pose3_logmap(Rn.T @ poses_[i][:3, :3], Rn.T @ (poses_[i][:3, 3] - tn))
+                out[qi, i] = np.sqrt(xi @ np.linalg.solve(c, xi))
+        return out, None
+
+    monkeypatch.setattr(sloop, "gate_distances", gate_on_host)
+    monkeypatch.setattr(patch, "replacements", lambda: {})
+    monkeypatch.setattr(patch, "_REBINDS", {})
+    original = lc.get_good_candidates
+    mods = {k: v for k, v in sys.modules.items() if k.startswith("final_project")}
+    tok = patch.patch(mods, batched_gating=True)
+    try:
+        assert lc.get_good_candidates is not original
+        some = 0
+        for n in (K - 1, 40, 12):
+            got = lc.get_good_candidates(n, None, Values(), index_list)
+            want = oracle.gate_distances_typed(poses, graph.graph, cov_dict, index_list, n)
+            ref_sel = sorted([(want[i], i) for i in np.nonzero(want < lc.MAHALANOBIS_THRESHOLD)[0]])[:lc.MAX_CANDIDATES]
+            assert got == [index_list[i] for _, i in ref_sel]
+            some += len(got)
+        assert some > 0
+    finally:
+        patch.unpatch(tok)
+    assert lc.get_good_candidates is original

@@ -481,6 +481,33 @@ class FrontEnd:
         n_l_dev, n_r_dev = small_dev[pos:pos + F], small_dev[pos + F:pos + 2 * F]
         ev_done = []
         ev_links_prev = None
+        tr = self.trace
+
+        def mark(stream):
+            if tr is None:
+                return None
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            return e
+
+        # The copy-in stream is the critical resource (the step is PCIe-bound): all of its copies are enqueued
+        # before any kernel, so it never waits for the host to finish launching a chunk's kernels.
+        ev_in_all = []
+        with torch.cuda.stream(s_in):
+            for c in range(len(bounds) - 1):
+                f0, f1 = bounds[c], bounds[c + 1]
+                a, b = int(l_off[f0]), int(l_off[f1])
+                ra, rb = int(r_off[f0]), int(r_off[f1])
+                e0 = mark(s_in)
+                for k, lo, hi in (("desc_l", a, b), ("pts_l", a, b), ("desc_r", ra, rb), ("pts_r", ra, rb)):
+                    src = seq.tensors[k][lo:hi]
+                    din[k][lo:hi].copy_(src, non_blocking=True)
+                    h2d += src.numel() * src.element_size()
+                ev_in = torch.cuda.Event(enable_timing=tr is not None)
+                ev_in.record(s_in)
+                ev_in_all.append(ev_in)
+                if tr is not None:
+                    tr.append(("h2d", c, e0, ev_in))
         for c in range(len(bounds) - 1):
             # chunks alternate between two compute streams, so the tail of one chunk's matcher
             # launch (few long CTAs left) overlaps the head of the next chunk's
@@ -489,25 +516,7 @@ class FrontEnd:
             n = f1 - f0
             a, b = int(l_off[f0]), int(l_off[f1])
             ra, rb = int(r_off[f0]), int(r_off[f1])
-            tr = self.trace
-
-            def mark(stream):
-                if tr is None:
-                    return None
-                e = torch.cuda.Event(enable_timing=True)
-                e.record(stream)
-                return e
-
-            with torch.cuda.stream(s_in):
-                e0 = mark(s_in)
-                for k, lo, hi in (("desc_l", a, b), ("pts_l", a, b), ("desc_r", ra, rb), ("pts_r", ra, rb)):
-                    src = seq.tensors[k][lo:hi]
-                    din[k][lo:hi].copy_(src, non_blocking=True)
-                    h2d += src.numel() * src.element_size()
-                ev_in = torch.cuda.Event(enable_timing=tr is not None)
-                ev_in.record(s_in)
-                if tr is not None:
-                    tr.append(("h2d", c, e0, ev_in))
+            ev_in = ev_in_all[c]
             (l0, l1), (r0, r1), (q0, q1), (t0, t1), (lp0, lp1), (rp0, rp1) = index[c]
             with torch.cuda.stream(s_cmp):
                 s_cmp.wait_event(ev_in)

@@ -180,8 +180,10 @@ __global__ void __launch_bounds__(RS_THREADS, 4) ransac_score_kernel(const Ransa
 #pragma unroll
                 for (int k = 0; k < RS_PP; ++k) {
                     bool in = false;
-                    if (maybe[k]) {  // implies the slot holds a correspondence
-                        const size_t g = static_cast<size_t>(p0 + blockIdx.x * RS_TILE + k * RS_THREADS + tid);
+                    const int i = blockIdx.x * RS_TILE + k * RS_THREADS + tid;
+                    // (an empty slot is dropped by its -inf slack unless the hypothesis holds a NaN: checked here)
+                    if (maybe[k] && i < np) {
+                        const size_t g = static_cast<size_t>(p0 + i);
                         in = agrees_rows(M, shared, __ldg(p.pts + 3 * g), __ldg(p.pts + 3 * g + 1), __ldg(p.pts + 3 * g + 2),
                                          __ldg(p.l_pix + 2 * g), __ldg(p.l_pix + 2 * g + 1), __ldg(p.r_pix + 2 * g),
                                          __ldg(p.r_pix + 2 * g + 1));

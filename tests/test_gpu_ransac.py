@@ -155,6 +155,39 @@ def test_borderline_reprojection_errors_take_the_exact_path(slamfe, oracle):
     assert 0 < counts[0] < n                   # the thresholded hypothesis is genuinely split
 
 
+def test_prefilter_edge_hypotheses_and_partial_tiles(slamfe, oracle):
+    """The scorer's fp32 pre-filter at its range guards, through the kernel: hypotheses with NaN / inf entries,
+    a translation of 1e12 (beyond the 1e9 guard: never filtered), a 1e-30 one, the identity, next to ordinary
+    good and bad ones; point counts that leave the last 512-point tile partly empty (1, 511, 513, 1300), where
+    an empty slot must never be counted even when a NaN hypothesis defeats its -inf slack; points and pixels
+    beyond 1e9.  Counts, winner and mask equal the reference formula in numpy."""
+    from slamfe import ransac, synth
+    rng = np.random.default_rng(78)
+    K, M1, M2 = synth.cameras()
+    ransac.set_cameras(K, M1, M2)
+    for n in (1, 511, 513, 1300):
+        Ts, pts, lp, rp = synth.pnp_problem(rng, n, 70)
+        Ts = Ts.copy()
+        Ts[3][1, 3] = np.nan
+        Ts[4][0, 0] = np.inf
+        Ts[5][:, 3] = [1e12, -3e11, 2e12]
+        Ts[6][:, 3] *= 1e-30
+        Ts[7] = np.hstack([np.eye(3), np.zeros((3, 1))])
+        Ts[8][:] = np.nan
+        for h in range(9, 40):                      # bad hypotheses: far-off poses
+            Ts[h] = np.hstack([synth._rodrigues(rng.normal(0, 0.6, 3)), rng.normal(0, 4, (3, 1))])
+        if n > 10:
+            pts[5] = [3e9, 1.0, 8.0]                # beyond the point guard
+            lp[6, 0] = 2e9                          # beyond the pixel guard
+            pts[7] = [np.nan, 1.0, 5.0]
+            lp[8, 1] = np.inf
+        with np.errstate(all="ignore"):
+            counts, best, cnt, mask = ransac.score_hypotheses(Ts, pts, lp, rp)
+            oc, ob, om = oracle.score_hypotheses(Ts, pts, lp, rp, K, M1, M2)
+        assert np.array_equal(counts, oc) and best == ob and np.array_equal(mask, om), n
+        assert counts[0] > 0.5 * n or n == 1
+
+
 def test_hypothesis_kernel_equals_host_build_of_the_same_solver(slamfe, oracle):
     """slamfe_ransac_hypotheses with given samples against the HOST build of csrc/p3p.cuh (pinned on
     the CPU against ground truth and cv2.SOLVEPNP_P3P by tests/test_oracle.py)."""

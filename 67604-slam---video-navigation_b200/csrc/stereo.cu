@@ -29,7 +29,11 @@ __global__ void stereo_filter_kernel(const float2 *__restrict__ pl, const float2
     mask[i] = stereo_inlier(a.x, a.y, b.x, b.y) ? 1 : 0;
 }
 
-constexpr int SL_THREADS = 512;   // one CTA per frame: the tile loop is latency-bound (4 barriers per tile), so fewer, wider tiles
+constexpr int SL_THREADS = 512;
+constexpr int SL_TILES = 16;                          // tiles of SL_THREADS rows per pass
+constexpr int SL_PASS = SL_TILES * SL_THREADS;        // 8192 rows: one pass covers any frame of the workload
+constexpr int SL_WARPS = SL_THREADS / 32;
+static_assert(SL_TILES * SL_WARPS <= SL_THREADS, "one scan element per thread");
 
 struct StereoLinksParams {
     const uint2 *row_keys;
@@ -43,109 +47,170 @@ struct StereoLinksParams {
     uint8_t *feat;
 };
 
+// One CTA per frame, three phases per pass of up to 8192 left rows, five barriers per pass (the first
+// version walked 512-row tiles with four barriers each and was bound by their latency):
+//   1. every thread classifies its rows of all tiles (crossCheck: row key -> column key -> mutual; row filter on
+//      the two keypoints) — 16 independent dependent-load chains per thread in flight — writes match_t and
+//      leaves one ballot count per (tile, warp) in shared memory;
+//   2. after an exclusive scan of the 256 counts, the good rows write link_src / links at their rank (ascending
+//      left keypoint index: the order cv2's crossCheck list + the reference's loops produce) and their row
+//      number into a shared list;
+//   3. 16 threads per link copy the descriptors of the listed rows into zero-padded 64-byte rows.
 __global__ void __launch_bounds__(SL_THREADS) stereo_links_kernel(const StereoLinksParams p)
 {
-    __shared__ int warp_cnt[SL_THREADS / 32];
-    __shared__ int warp_mut[SL_THREADS / 32];
-    __shared__ int chunk_src[SL_THREADS];  // left rows of this chunk's links, in order
-    __shared__ int s_base, s_mut;
+    __shared__ int s_cnt[SL_TILES * SL_WARPS];    // good rows per (tile, warp), then their exclusive prefix
+    __shared__ int s_wsum[SL_WARPS];
+    __shared__ int s_mut[SL_WARPS];
+    __shared__ uint16_t s_src[SL_PASS];            // left row (relative to the pass) of the pass' links, in order
+    __shared__ int s_total;
 
     const int f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int l0 = p.l_off[f], nl = p.l_cnt ? p.l_cnt[f] : p.l_off[f + 1] - l0;
     const int r0 = p.r_off[f], nr = p.r_cnt ? p.r_cnt[f] : p.r_off[f + 1] - r0;
-    if (tid == 0) { s_base = 0; s_mut = 0; }
-    __syncthreads();
+    int base = 0, n_mut = 0;   // links written so far; mutual matches seen by this warp (lane 0)
 
-    for (int c0 = 0; c0 < nl; c0 += SL_THREADS) {
-        const int i = c0 + tid;
-        bool mutual = false, good = false;
-        int j = -1;
-        float xl = 0.f, xr = 0.f, y = 0.f;
-        if (i < nl) {
-            const uint32_t k = p.row_keys[l0 + i].x;
-            if (k != KEY_NONE) {
-                const uint32_t jj = k & KEY_IDX_MASK;
-                if (jj < static_cast<uint32_t>(nr)) {
-                    const uint32_t c = p.col_keys[r0 + jj];
-                    mutual = (c != KEY_NONE) && ((c & KEY_IDX_MASK) == static_cast<uint32_t>(i));
-                    if (mutual) j = static_cast<int>(jj);
+    for (int pass0 = 0; pass0 < nl; pass0 += SL_PASS) {
+        const int n_tiles = min(SL_TILES, (nl - pass0 + SL_THREADS - 1) / SL_THREADS);
+        // ---- 1. classify ----
+        uint32_t good_bits = 0;
+#pragma unroll 4
+        for (int t = 0; t < n_tiles; ++t) {
+            const int i = pass0 + t * SL_THREADS + tid;
+            bool mutual = false, good = false;
+            if (i < nl) {
+                int j = -1;
+                const uint32_t k = p.row_keys[l0 + i].x;
+                if (k != KEY_NONE) {
+                    const uint32_t jj = k & KEY_IDX_MASK;
+                    if (jj < static_cast<uint32_t>(nr)) {
+                        const uint32_t c = p.col_keys[r0 + jj];
+                        mutual = (c != KEY_NONE) && ((c & KEY_IDX_MASK) == static_cast<uint32_t>(i));
+                        if (mutual) j = static_cast<int>(jj);
+                    }
+                }
+                p.match_t[l0 + i] = j;
+                if (mutual) {
+                    const float2 a = p.pl[l0 + i], b = p.pr[r0 + j];
+                    good = stereo_inlier(a.x, a.y, b.x, b.y);
                 }
             }
-            p.match_t[l0 + i] = j;
-            if (mutual) {
-                const float2 a = p.pl[l0 + i], b = p.pr[r0 + j];
-                good = stereo_inlier(a.x, a.y, b.x, b.y);
-                xl = a.x;
-                xr = b.x;
-                // tracking_database.py:243: (yl + yr) / 2 in double, stored as float
-                y = static_cast<float>((static_cast<double>(a.y) + static_cast<double>(b.y)) / 2.0);
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, good);
+            const uint32_t balm = __ballot_sync(0xFFFFFFFFu, mutual);
+            if (good) good_bits |= 1u << t;
+            if (lane == 0) {
+                s_cnt[t * SL_WARPS + warp] = __popc(bal);
+                n_mut += __popc(balm);
             }
         }
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, good);
-        const uint32_t balm = __ballot_sync(0xFFFFFFFFu, mutual);
-        if (lane == 0) {
-            warp_cnt[warp] = __popc(bal);
-            warp_mut[warp] = __popc(balm);
-        }
         __syncthreads();
-        int woff = 0, total = 0, mtotal = 0;
+        // ---- exclusive scan of the n_tiles * SL_WARPS counts (tile-major: ascending row order) ----
+        {
+            const int n_el = n_tiles * SL_WARPS;
+            const int v = tid < n_el ? s_cnt[tid] : 0;
+            int inc = v;
 #pragma unroll
-        for (int w = 0; w < SL_THREADS / 32; ++w) {
-            if (w < warp) woff += warp_cnt[w];
-            total += warp_cnt[w];
-            mtotal += warp_mut[w];
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= o) inc += u;
+            }
+            if (lane == 31) s_wsum[warp] = inc;
+            __syncthreads();
+            int woff = 0;
+#pragma unroll
+            for (int w = 0; w < SL_WARPS; ++w)
+                if (w < warp) woff += s_wsum[w];
+            if (tid < n_el) s_cnt[tid] = woff + inc - v;
+            if (tid == 0) {
+                int tot = 0;
+                for (int w = 0; w < SL_WARPS; ++w) tot += s_wsum[w];
+                s_total = tot;
+            }
+            __syncthreads();
         }
-        const int base = s_base;
-        if (good) {
-            const int pos = woff + __popc(bal & ((1u << lane) - 1u));
-            const size_t o = static_cast<size_t>(l0 + base + pos);
-            p.link_src[o] = i;
-            p.links[3 * o + 0] = xl;
-            p.links[3 * o + 1] = xr;
-            p.links[3 * o + 2] = y;
-            chunk_src[pos] = i;
-        }
-        __syncthreads();
-        if (p.feat) {
-            // 16 threads per link copy one descriptor into a zero-padded 64-byte row
-            for (int e = tid; e < total * 16; e += SL_THREADS) {
-                const int k = e >> 4, w = e & 15;
-                const uint8_t *src = p.desc + static_cast<size_t>(l0 + chunk_src[k]) * p.l_stride + 4 * w;
-                // bytes [4w, 4w + 4) of a row at any alignment: the one or two aligned words that hold them
-                // (a word is only read when it contains a valid descriptor byte), funnel shift, tail mask
-                const int valid = min(4, p.desc_bytes - 4 * w);
-                uint32_t v = 0;
-                if (valid > 0) {
-                    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
-                    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(a & ~static_cast<uintptr_t>(3));
-                    const int mis = static_cast<int>(a & 3);
-                    const uint32_t lo = __ldg(s32);
-                    const uint32_t hi = (mis + valid > 4) ? __ldg(s32 + 1) : 0u;
-                    v = __funnelshift_r(lo, hi, mis * 8);
-                    if (valid < 4) v &= (1u << (8 * valid)) - 1u;
-                }
-                reinterpret_cast<uint32_t *>(p.feat)[static_cast<size_t>(l0 + base + k) * 16 + w] = v;
+        const int total = s_total;
+        // ---- 2. links of the good rows, at their rank ----
+#pragma unroll 4
+        for (int t = 0; t < n_tiles; ++t) {
+            const bool good = (good_bits >> t) & 1u;
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, good);
+            if (good) {
+                const int i = pass0 + t * SL_THREADS + tid;
+                const int pos = s_cnt[t * SL_WARPS + warp] + __popc(bal & ((1u << lane) - 1u));
+                const int j = p.match_t[l0 + i];   // this thread's own store of phase 1
+                const float2 a = p.pl[l0 + i], b = p.pr[r0 + j];
+                const size_t o = static_cast<size_t>(l0 + base + pos);
+                p.link_src[o] = i;
+                p.links[3 * o + 0] = a.x;
+                p.links[3 * o + 1] = b.x;
+                // tracking_database.py:243: (yl + yr) / 2 in double, stored as float
+                p.links[3 * o + 2] = static_cast<float>((static_cast<double>(a.y) + static_cast<double>(b.y)) / 2.0);
+                s_src[pos] = static_cast<uint16_t>(i - pass0);
             }
         }
         __syncthreads();
-        if (tid == 0) {
-            s_base = base + total;
-            s_mut += mtotal;
+        // ---- 3. features[is_valid] ----
+        if (p.feat) {
+            // 16 threads per link copy one descriptor into a zero-padded 64-byte row; SL_BATCH items per thread
+            // are loaded before any is stored, so their global loads (L2 / HBM latency) overlap
+            constexpr int SL_BATCH = 8;
+            uint32_t *feat32 = reinterpret_cast<uint32_t *>(p.feat) + static_cast<size_t>(l0 + base) * 16;
+            for (int e0 = tid; e0 < total * 16; e0 += SL_THREADS * SL_BATCH) {
+                uint32_t lo[SL_BATCH], hi[SL_BATCH];
+#pragma unroll
+                for (int u = 0; u < SL_BATCH; ++u) {
+                    const int e = e0 + u * SL_THREADS;
+                    lo[u] = hi[u] = 0u;
+                    if (e < total * 16) {
+                        const int k = e >> 4, w = e & 15;
+                        // bytes [4w, 4w + 4) of a row at any alignment: the one or two aligned words that hold
+                        // them (a word is only read when it contains a valid descriptor byte)
+                        const int valid = min(4, p.desc_bytes - 4 * w);
+                        if (valid > 0) {
+                            const uintptr_t a = reinterpret_cast<uintptr_t>(
+                                p.desc + static_cast<size_t>(l0 + pass0 + s_src[k]) * p.l_stride + 4 * w);
+                            const uint32_t *s32 = reinterpret_cast<const uint32_t *>(a & ~static_cast<uintptr_t>(3));
+                            lo[u] = __ldg(s32);
+                            if (static_cast<int>(a & 3) + valid > 4) hi[u] = __ldg(s32 + 1);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < SL_BATCH; ++u) {
+                    const int e = e0 + u * SL_THREADS;
+                    if (e < total * 16) {
+                        const int k = e >> 4, w = e & 15;
+                        const int valid = min(4, p.desc_bytes - 4 * w);
+                        uint32_t v = 0;
+                        if (valid > 0) {   // funnel shift by the row's misalignment, tail mask
+                            const int mis = static_cast<int>(
+                                (reinterpret_cast<uintptr_t>(p.desc) + static_cast<size_t>(l0 + pass0 + s_src[k]) * p.l_stride) & 3);
+                            v = __funnelshift_r(lo[u], hi[u], mis * 8);
+                            if (valid < 4) v &= (1u << (8 * valid)) - 1u;
+                        }
+                        feat32[static_cast<size_t>(k) * 16 + w] = v;
+                    }
+                }
+            }
         }
-        __syncthreads();
+        base += total;
+        __syncthreads();   // s_cnt / s_src / s_total are rewritten by the next pass
     }
     // rows of this frame's capacity that hold no link: deterministic filler
-    for (int k = s_base + tid; k < nl; k += SL_THREADS) {
+    for (int k = base + tid; k < nl; k += SL_THREADS) {
         const size_t o = static_cast<size_t>(l0 + k);
         p.link_src[o] = -1;
         p.links[3 * o + 0] = 0.f;
         p.links[3 * o + 1] = 0.f;
         p.links[3 * o + 2] = 0.f;
     }
+    if (lane == 0) s_mut[warp] = n_mut;
+    __syncthreads();
     if (tid == 0) {
-        p.n_links[f] = s_base;
-        p.n_matches[f] = s_mut;
+        int m = 0;
+        for (int w = 0; w < SL_WARPS; ++w) m += s_mut[w];
+        p.n_links[f] = base;
+        p.n_matches[f] = m;
     }
 }
 

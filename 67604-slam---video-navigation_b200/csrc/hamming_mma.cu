@@ -499,6 +499,36 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
             if (trows > 0) mbar_wait(&sm.raw_full[b], ph);
             mbar_wait(&sm.b_empty[b], ph ^ 1);
             uint32_t w[WPT];
+            // 64-byte rows (the compacted features of the sequence pipeline): word k of 32 consecutive rows lives
+            // in TWO banks, so the word-by-word read below is a 16-way conflict (this launch ran at 0.45 of the
+            // MMA issue floor where 61-byte rows of the same size ran at 0.65).  Read 16-byte chunks instead,
+            // each thread starting at chunk (r / 2) mod 4: the four rows of equal parity in a quarter-warp then
+            // hit four different bank groups, and the chunk's words go straight to their K positions.
+            const bool rows64 = G::EXP_SPLIT == 1 && n_k == W && p.t_stride == 64 && r < trows && r < rows;
+            if (rows64) {
+                uint8_t *dst64 = sm.b[b] + r * 16;
+                const uint4 *raw128 = reinterpret_cast<const uint4 *>(sm.raw[b] + r * 64);
+                const uint32_t slo = 0x80000000u;   // a valid row: 0x80 on the four popc positions of the tail word
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int cc = (c + (r >> 1)) & 3;
+                    const uint4 v = raw128[cc];
+                    const bool tail = cc == 3;
+                    const uint32_t ww[4] = {v.x, v.y, v.z, tail ? (v.w & last_mask) : v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t sl = (tail && j == 3) ? slo : 0u;
+                        uint8_t *d = dst64 + 2 * (4 * cc + j) * LBO;
+                        *reinterpret_cast<uint4 *>(d) = make_uint4(spread80(ww[j], mul[0]) | sl, spread80(ww[j], mul[1]) | sl,
+                                                                   spread80(ww[j], mul[2]) | sl, spread80(ww[j], mul[3]) | sl);
+                        *reinterpret_cast<uint4 *>(d + LBO) = make_uint4(spread80(ww[j], mul[4]), spread80(ww[j], mul[5]),
+                                                                         spread80(ww[j], mul[6]), spread80(ww[j], mul[7]));
+                    }
+                }
+                fence_async_smem();
+                mbar_arrive(&sm.b_full[b]);
+                continue;
+            }
             if (r >= rows) {
 #pragma unroll
                 for (int k = 0; k < WPT; ++k) w[k] = 0;

@@ -49,6 +49,8 @@
 // exactness, MMA cycles at the issue floor, TMEM read bandwidth.
 #include <cstdlib>
 #include "common.cuh"
+#include <type_traits>
+
 #include "hamming_params.cuh"
 
 namespace slamfe {
@@ -492,97 +494,105 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
 #pragma unroll
         for (int s = 0; s < 8; ++s) mul[s] = (1u << (7 - s)) * static_cast<uint32_t>(p.desc_bytes > 0);
         const uint32_t last_mask = word_mask(p.desc_bytes, ws);   // the word that holds the descriptor's tail + the spare byte
-        for (int s = 0; s < n_stage; ++s) {
-            const int b = s % NB;
-            const uint32_t ph = (s / NB) & 1;
-            const int rows = stage_rows(s), trows = stage_tma_rows(s);
-            if (trows > 0) mbar_wait(&sm.raw_full[b], ph);
-            mbar_wait(&sm.b_empty[b], ph ^ 1);
-            uint32_t w[WPT];
-            // 64-byte rows (the compacted features of the sequence pipeline): word k of 32 consecutive rows lives
-            // in TWO banks, so the word-by-word read below is a 16-way conflict (this launch ran at 0.45 of the
-            // MMA issue floor where 61-byte rows of the same size ran at 0.65).  Read 16-byte chunks instead,
-            // each thread starting at chunk (r / 2) mod 4: the four rows of equal parity in a quarter-warp then
-            // hit four different bank groups, and the chunk's words go straight to their K positions.
-            const bool rows64 = G::EXP_SPLIT == 1 && n_k == W && p.t_stride == 64 && r < trows && r < rows;
-            if (rows64) {
-                uint8_t *dst64 = sm.b[b] + r * 16;
-                const uint4 *raw128 = reinterpret_cast<const uint4 *>(sm.raw[b] + r * 64);
-                const uint32_t slo = 0x80000000u;   // a valid row: 0x80 on the four popc positions of the tail word
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int cc = (c + (r >> 1)) & 3;
-                    const uint4 v = raw128[cc];
-                    const bool tail = cc == 3;
-                    const uint32_t ww[4] = {v.x, v.y, v.z, tail ? (v.w & last_mask) : v.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t sl = (tail && j == 3) ? slo : 0u;
-                        uint8_t *d = dst64 + 2 * (4 * cc + j) * LBO;
-                        *reinterpret_cast<uint4 *>(d) = make_uint4(spread80(ww[j], mul[0]) | sl, spread80(ww[j], mul[1]) | sl,
-                                                                   spread80(ww[j], mul[2]) | sl, spread80(ww[j], mul[3]) | sl);
-                        *reinterpret_cast<uint4 *>(d + LBO) = make_uint4(spread80(ww[j], mul[4]), spread80(ww[j], mul[5]),
-                                                                         spread80(ww[j], mul[6]), spread80(ww[j], mul[7]));
+        // Two copies of the stage loop, chosen once per kernel: the 64-byte-row path costs the general one
+        // registers and scheduling freedom when both live in the same loop (-3.7 % on the dense sweep).
+        auto sweep = [&](auto rows64_c) {
+            constexpr bool ROWS64 = decltype(rows64_c)::value;
+            for (int s = 0; s < n_stage; ++s) {
+                const int b = s % NB;
+                const uint32_t ph = (s / NB) & 1;
+                const int rows = stage_rows(s), trows = stage_tma_rows(s);
+                if (trows > 0) mbar_wait(&sm.raw_full[b], ph);
+                mbar_wait(&sm.b_empty[b], ph ^ 1);
+                uint32_t w[WPT];
+                // 64-byte rows (the compacted features of the sequence pipeline): word k of 32 consecutive rows lives
+                // in TWO banks, so the word-by-word read below is a 16-way conflict (this launch ran at 0.45 of the
+                // MMA issue floor where 61-byte rows of the same size ran at 0.65).  Read 16-byte chunks instead,
+                // each thread starting at chunk (r / 2) mod 4: the four rows of equal parity in a quarter-warp then
+                // hit four different bank groups, and the chunk's words go straight to their K positions.
+                if (ROWS64 && r < trows && r < rows) {
+                    uint8_t *dst64 = sm.b[b] + r * 16;
+                    const uint4 *raw128 = reinterpret_cast<const uint4 *>(sm.raw[b] + r * 64);
+                    const uint32_t slo = 0x80000000u;   // a valid row: 0x80 on the four popc positions of the tail word
+    #pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int cc = (c + (r >> 1)) & 3;
+                        const uint4 v = raw128[cc];
+                        const bool tail = cc == 3;
+                        const uint32_t ww[4] = {v.x, v.y, v.z, tail ? (v.w & last_mask) : v.w};
+    #pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t sl = (tail && j == 3) ? slo : 0u;
+                            uint8_t *d = dst64 + 2 * (4 * cc + j) * LBO;
+                            *reinterpret_cast<uint4 *>(d) = make_uint4(spread80(ww[j], mul[0]) | sl, spread80(ww[j], mul[1]) | sl,
+                                                                       spread80(ww[j], mul[2]) | sl, spread80(ww[j], mul[3]) | sl);
+                            *reinterpret_cast<uint4 *>(d + LBO) = make_uint4(spread80(ww[j], mul[4]), spread80(ww[j], mul[5]),
+                                                                             spread80(ww[j], mul[6]), spread80(ww[j], mul[7]));
+                        }
+                    }
+                    fence_async_smem();
+                    mbar_arrive(&sm.b_full[b]);
+                    continue;
+                }
+                if (r >= rows) {
+    #pragma unroll
+                    for (int k = 0; k < WPT; ++k) w[k] = 0;
+                } else if (r < trows) {
+                    const int o = r * p.t_stride + 4 * k_lo;  // any alignment: LDS.32 + funnel shift
+                    const uint32_t *raw32 = reinterpret_cast<const uint32_t *>(sm.raw[b]) + (o >> 2);
+                    const int sh = (o & 3) * 8;
+                    uint32_t lo = raw32[0];
+    #pragma unroll
+                    for (int k = 0; k < WPT; ++k) {
+                        // words past the descriptor hold stale bytes of the staging buffer (never past its end:
+                        // RAW_STAGE has 16 bytes of slack); they are masked / skipped below
+                        const uint32_t hi = raw32[k + 1];
+                        w[k] = __funnelshift_r(lo, hi, sh);
+                        lo = hi;
+                    }
+                } else {  // rows the bulk copy could not take (misaligned source / tail): read global memory
+                    uint32_t wf[W];
+                    load_desc_global(stage_src(s) + static_cast<size_t>(r) * p.t_stride, p.desc_bytes, wf);
+    #pragma unroll
+                    for (int k = 0; k < WPT; ++k) w[k] = wf[(G::EXP_SPLIT == 1 ? 0 : k_lo) + k];
+                }
+                uint8_t *dst = sm.b[b] + r * 16;
+                // valid rows carry 0x80 on the four popc positions, invalid rows on the four marker positions
+                const uint32_t spare_lo = (r < rows) ? 0x80000000u : 0u, spare_hi = (r < rows) ? 0u : 0x80000000u;
+                auto put = [&](int kk, uint32_t wk, uint32_t slo, uint32_t shi) {
+                    uint8_t *d = dst + 2 * kk * LBO;
+                    *reinterpret_cast<uint4 *>(d) = make_uint4(spread80(wk, mul[0]) | slo, spread80(wk, mul[1]) | slo,
+                                                               spread80(wk, mul[2]) | slo, spread80(wk, mul[3]) | slo);
+                    *reinterpret_cast<uint4 *>(d + LBO) = make_uint4(spread80(wk, mul[4]) | shi, spread80(wk, mul[5]) | shi,
+                                                                     spread80(wk, mul[6]) | shi, spread80(wk, mul[7]) | shi);
+                };
+                if (n_k == W) {   // descriptors of 60..63 bytes (AKAZE: 61): word 15 is the tail word, no per-word tests
+    #pragma unroll
+                    for (int k = 0; k < WPT; ++k) {
+                        const bool tail = (G::EXP_SPLIT == 1) ? (k == W - 1) : (k == WPT - 1 && k_lo + WPT == W);
+                        if (tail)
+                            put(k_lo + k, w[k] & last_mask, spare_lo, spare_hi);
+                        else
+                            put(k_lo + k, w[k], 0u, 0u);
+                    }
+                } else {
+    #pragma unroll
+                    for (int k = 0; k < WPT; ++k) {
+                        const int kk = k_lo + k;
+                        if (kk < ws)
+                            put(kk, w[k], 0u, 0u);
+                        else if (kk == ws)
+                            put(kk, w[k] & last_mask, spare_lo, spare_hi);
                     }
                 }
-                fence_async_smem();
+                fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
                 mbar_arrive(&sm.b_full[b]);
-                continue;
             }
-            if (r >= rows) {
-#pragma unroll
-                for (int k = 0; k < WPT; ++k) w[k] = 0;
-            } else if (r < trows) {
-                const int o = r * p.t_stride + 4 * k_lo;  // any alignment: LDS.32 + funnel shift
-                const uint32_t *raw32 = reinterpret_cast<const uint32_t *>(sm.raw[b]) + (o >> 2);
-                const int sh = (o & 3) * 8;
-                uint32_t lo = raw32[0];
-#pragma unroll
-                for (int k = 0; k < WPT; ++k) {
-                    // words past the descriptor hold stale bytes of the staging buffer (never past its end:
-                    // RAW_STAGE has 16 bytes of slack); they are masked / skipped below
-                    const uint32_t hi = raw32[k + 1];
-                    w[k] = __funnelshift_r(lo, hi, sh);
-                    lo = hi;
-                }
-            } else {  // rows the bulk copy could not take (misaligned source / tail): read global memory
-                uint32_t wf[W];
-                load_desc_global(stage_src(s) + static_cast<size_t>(r) * p.t_stride, p.desc_bytes, wf);
-#pragma unroll
-                for (int k = 0; k < WPT; ++k) w[k] = wf[(G::EXP_SPLIT == 1 ? 0 : k_lo) + k];
-            }
-            uint8_t *dst = sm.b[b] + r * 16;
-            // valid rows carry 0x80 on the four popc positions, invalid rows on the four marker positions
-            const uint32_t spare_lo = (r < rows) ? 0x80000000u : 0u, spare_hi = (r < rows) ? 0u : 0x80000000u;
-            auto put = [&](int kk, uint32_t wk, uint32_t slo, uint32_t shi) {
-                uint8_t *d = dst + 2 * kk * LBO;
-                *reinterpret_cast<uint4 *>(d) = make_uint4(spread80(wk, mul[0]) | slo, spread80(wk, mul[1]) | slo,
-                                                           spread80(wk, mul[2]) | slo, spread80(wk, mul[3]) | slo);
-                *reinterpret_cast<uint4 *>(d + LBO) = make_uint4(spread80(wk, mul[4]) | shi, spread80(wk, mul[5]) | shi,
-                                                                 spread80(wk, mul[6]) | shi, spread80(wk, mul[7]) | shi);
-            };
-            if (n_k == W) {   // descriptors of 60..63 bytes (AKAZE: 61): word 15 is the tail word, no per-word tests
-#pragma unroll
-                for (int k = 0; k < WPT; ++k) {
-                    const bool tail = (G::EXP_SPLIT == 1) ? (k == W - 1) : (k == WPT - 1 && k_lo + WPT == W);
-                    if (tail)
-                        put(k_lo + k, w[k] & last_mask, spare_lo, spare_hi);
-                    else
-                        put(k_lo + k, w[k], 0u, 0u);
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < WPT; ++k) {
-                    const int kk = k_lo + k;
-                    if (kk < ws)
-                        put(kk, w[k], 0u, 0u);
-                    else if (kk == ws)
-                        put(kk, w[k] & last_mask, spare_lo, spare_hi);
-                }
-            }
-            fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
-            mbar_arrive(&sm.b_full[b]);
-        }
+        };
+        if (G::EXP_SPLIT == 1 && n_k == W && p.t_stride == 64)
+            sweep(std::true_type{});
+        else
+            sweep(std::false_type{});
     } else if (warp == MMA_WARP) {
         // ============================== MMA issue (whole warp, one elected lane issues) ===========
         // This thread does nothing but wait and issue: tcgen05.mma blocks when the tensor pipe's queue is

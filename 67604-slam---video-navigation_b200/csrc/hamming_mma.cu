@@ -47,9 +47,12 @@
 // Facts pinned on a B200 by scripts/probe_tcgen05.cu (profiles/r02_probe_tcgen05.log): descriptor
 // field meaning (LBO = K-chunk stride, SBO = 8-row stride), TMEM A layout (4 K-bytes per column),
 // exactness, MMA cycles at the issue floor, TMEM read bandwidth.
+#include <algorithm>
 #include <cstdlib>
-#include "common.cuh"
+#include <mutex>
 #include <type_traits>
+
+#include "common.cuh"
 
 #include "hamming_params.cuh"
 
@@ -674,8 +677,13 @@ int launch_mma(const HammingParams &p, dim3 grid, cudaStream_t stream)
     return launch_status();
 }
 
+#ifdef SLAMFE_MMA_DEV
+#include "hamming_mma_persistent.cuh"   // measured and not shipped; see the header
+#endif
+
 template <class G>
-int run_geometry(HammingParams p, int n_problems, int max_nq, int max_nt, bool top2, cudaStream_t stream)
+int run_geometry(HammingParams p, int n_problems, int max_nq, int max_nt, bool top2, cudaStream_t stream,
+                 bool persistent = false)
 {
     // One CTA per SM (all 512 TMEM columns).  When the query tiles alone do not fill the machine the train
     // set is cut into slices (grid.y); their results merge exactly through atomicMin / the CAS pair merge,
@@ -693,6 +701,25 @@ int run_geometry(HammingParams p, int n_problems, int max_nq, int max_nt, bool t
     const int n_slices = (stages_total + stages_per_slice - 1) / stages_per_slice;
     const dim3 grid((max_nq + G::CQ - 1) / G::CQ, n_slices, n_problems);
     if (grid.y > 65535u || grid.z > 65535u) return SLAMFE_ERANGE;
+#ifdef SLAMFE_MMA_DEV
+    if constexpr (G::QT == 2 && !G::REDUX && G::EXP_SPLIT == 1) if (persistent) {
+        const long long total = static_cast<long long>(grid.x) * grid.y * grid.z;
+        if (total > 0x7FFF0000LL) return SLAMFE_ERANGE;
+        p.jobs_x = static_cast<int>(grid.x);
+        p.jobs_y = static_cast<int>(grid.y);
+        p.jobs_total = static_cast<int>(total);
+        p.job_counter = next_job_counter();
+        if (!p.job_counter) return SLAMFE_EINVAL;
+        const int ctas = static_cast<int>(std::min<long long>(sms, total));
+        if (p.col_keys)
+            return top2 ? launch_mma_persistent<G, true, true>(p, ctas, stream)
+                        : launch_mma_persistent<G, true, false>(p, ctas, stream);
+        return top2 ? launch_mma_persistent<G, false, true>(p, ctas, stream)
+                    : launch_mma_persistent<G, false, false>(p, ctas, stream);
+    }
+#else
+    (void)persistent;
+#endif
     if (p.col_keys) return top2 ? launch_mma<G, true, true>(p, grid, stream) : launch_mma<G, true, false>(p, grid, stream);
     return top2 ? launch_mma<G, false, true>(p, grid, stream) : launch_mma<G, false, false>(p, grid, stream);
 }
@@ -718,7 +745,27 @@ int run_hamming_mma(HammingParams p, int n_problems, int max_nq, int max_nt, boo
         default: break;
     }
 #endif
+#ifdef SLAMFE_MMA_DEV
+    static const bool persistent = [] {   // the persistent form of the kernel (hamming_mma_persistent.cuh), A/B runs only
+        const char *v = getenv("SLAMFE_MMA_PERSISTENT");
+        return v && *v && atoi(v) != 0;
+    }();
+    return run_geometry<Geo<2, 128, false, 1>>(p, n_problems, max_nq, max_nt, top2, stream, persistent);
+#else
     return run_geometry<Geo<2, 128, false, 1>>(p, n_problems, max_nq, max_nt, top2, stream);
+#endif
 }
 
 }  // namespace slamfe
+
+#if defined(SLAMFE_MMA_DEV) && defined(SLAMFE_MMA_PROF)
+extern "C" int slamfe_dev_mma_prof(unsigned long long *out, int clear)
+{
+    if (out && cudaMemcpyFromSymbol(out, slamfe::g_mma_prof, sizeof(slamfe::g_mma_prof)) != cudaSuccess) return -1;
+    if (clear) {
+        static unsigned long long zero[256][16];
+        if (cudaMemcpyToSymbol(slamfe::g_mma_prof, zero, sizeof(zero)) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif

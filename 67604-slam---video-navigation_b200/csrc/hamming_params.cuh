@@ -19,6 +19,9 @@ struct HammingParams {
     uint2 *row_keys;
     uint32_t *col_keys;
     int compact;      // best-only results as one u32 per query row instead of (best, second)
+    // persistent tcgen05 kernel only: the (query tile, train slice, problem) job space and the launch's job counter
+    int jobs_x, jobs_y, jobs_total;
+    uint32_t *job_counter;
 };
 
 // Load one descriptor (desc_bytes useful bytes) from global memory into 16 zero-padded words.

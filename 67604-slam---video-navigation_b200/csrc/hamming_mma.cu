@@ -72,8 +72,9 @@ constexpr uint32_t TMEM_COLS = 512;
 //             ~83 + 0.2 N cycles on this part: 109 at N = 128, 122 at N = 192) at twice the expansion work
 //             per pair; the accumulators alternate between stages; column minima by redux only (no room
 //             for the transpose scratch next to 2 x 96 KB of B stages)
-template <int QT_, int NT_, bool REDUX_, int EXP_SPLIT_ = 1>
+template <int QT_, int NT_, bool REDUX_, int EXP_SPLIT_ = 1, bool SCR2_ = false>
 struct Geo {
+    static constexpr bool SCR2 = SCR2_;              // one transpose scratch per 64-column chunk: both chunks of a stage in flight
     static constexpr int QT = QT_, NT = NT_;
     static constexpr bool REDUX = REDUX_;
     static constexpr int CQ = MQ * QT;               // query rows per CTA
@@ -99,7 +100,7 @@ struct Geo {
     struct __align__(16) Smem {
         uint8_t b[NB][B_STAGE];
         uint8_t raw[NB][RAW_STAGE];
-        uint32_t scratch[REDUX ? 1 : N_EPI_WARPS][REDUX ? 4 : 32 * 32];  // per-warp 32 x 64 packed distances, swizzled
+        uint32_t scratch[REDUX ? 1 : N_EPI_WARPS][REDUX ? 4 : (SCR2 ? 2 : 1) * 32 * 32];  // per-warp 32 x 64 packed distances, swizzled
         uint32_t colmin[QT][2][NT];                                      // per query tile, double buffered over stages
         uint64_t raw_full[NB], b_full[NB], b_empty[NB], d_full[2], d_empty[2], a_ready;
         uint32_t tmem_base;
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                 for (int h = 0; h < G::NCH; ++h) {
                     if (h > 0 && 64 * h >= rows) break;  // warp-uniform
                     uint32_t (&v)[32] = vv[h];
-                    if (COL && !G::REDUX) {
+                    if (COL && !G::REDUX && !G::SCR2) {
                         // scratch[row = lane][32 words], 16-byte chunk i stored at chunk i ^ (lane & 7):
                         // conflict-free both for these row-wise STS.128 and for the column-wise LDS.32 below
 #pragma unroll
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                             top2_insert(c[i] >= (505u << 7) ? KEY_NONE : ((c[i] >> 7) << KEY_IDX_BITS) + jh + (c[i] & 127u),
                                         b1, b2);
                     }
-                    if (COL) {
+                    if (COL && !G::SCR2) {
                         // ---- column minima over this warp's 32 query rows; lane l ends up with the packed
                         //      minima of train columns 2l, 2l+1 of the chunk: key16 = (d << 5) | row-in-warp ----
                         uint32_t m = 0xFFFFFFFFu;
@@ -453,6 +454,58 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                             const int c = 64 * h + 2 * lane + hh;
                             if (c < rows)
                                 atomicMin(&sm.colmin[tile][s & 1][c], ((k16 >> 5) << KEY_IDX_BITS) + rbase + (k16 & 31u));
+                        }
+                    }
+                }
+                if (COL && G::SCR2) {
+                    // both chunks of the stage through their own scratch: 16 STS.128, one __syncwarp, 64 LDS.32 feeding
+                    // two independent minimum chains, one __syncwarp
+                    const int nh = rows > 64 ? 2 : 1;   // warp-uniform
+#pragma unroll
+                    for (int h = 0; h < G::NCH; ++h) {
+                        if (h < nh) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const uint32_t a = scr_addr + h * 4096 + lane * 128 + ((i ^ (lane & 7)) << 4);
+                                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(vv[h][4 * i]),
+                                             "r"(vv[h][4 * i + 1]), "r"(vv[h][4 * i + 2]), "r"(vv[h][4 * i + 3])
+                                             : "memory");
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    uint32_t mc[G::NCH];
+#pragma unroll
+                    for (int h = 0; h < G::NCH; ++h) mc[h] = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int r = 0; r < 32; r += 2) {
+#pragma unroll
+                        for (int h = 0; h < G::NCH; ++h) {
+                            if (h < nh) {
+                                uint32_t x0, x1;
+                                const uint32_t a0 =
+                                    scr_addr + h * 4096 + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2));
+                                const uint32_t a1 = scr_addr + h * 4096 + (r + 1) * 128 +
+                                                    ((((lane >> 2) ^ ((r + 1) & 7)) << 4) | ((lane & 3) << 2));
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x0) : "r"(a0) : "memory");
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x1) : "r"(a1) : "memory");
+                                const uint32_t k0 = add_imad(x0 >> 2, one, (static_cast<uint32_t>(r) << 16) | r);
+                                const uint32_t k1 = add_imad(x1 >> 2, one, (static_cast<uint32_t>(r + 1) << 16) | (r + 1));
+                                mc[h] = __vimin3_u16x2(mc[h], k0, k1);
+                            }
+                        }
+                    }
+                    __syncwarp();  // the scratch is rewritten by the next stage
+#pragma unroll
+                    for (int h = 0; h < G::NCH; ++h) {
+                        if (h < nh) {
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const uint32_t k16 = hh ? (mc[h] >> 16) : (mc[h] & 0xFFFFu);
+                                const int c = 64 * h + 2 * lane + hh;
+                                if (c < rows)
+                                    atomicMin(&sm.colmin[tile][s & 1][c], ((k16 >> 5) << KEY_IDX_BITS) + rbase + (k16 & 31u));
+                            }
                         }
                     }
                 }
@@ -678,7 +731,8 @@ int launch_mma(const HammingParams &p, dim3 grid, cudaStream_t stream)
 }
 
 #ifdef SLAMFE_MMA_DEV
-#include "hamming_mma_persistent.cuh"   // measured and not shipped; see the header
+#include "hamming_mma_persistent.cuh"   // measured and not shipped; see the headers
+#include "hamming_mma_pair.cuh"
 #endif
 
 template <class G>
@@ -702,7 +756,7 @@ int run_geometry(HammingParams p, int n_problems, int max_nq, int max_nt, bool t
     const dim3 grid((max_nq + G::CQ - 1) / G::CQ, n_slices, n_problems);
     if (grid.y > 65535u || grid.z > 65535u) return SLAMFE_ERANGE;
 #ifdef SLAMFE_MMA_DEV
-    if constexpr (G::QT == 2 && !G::REDUX && G::EXP_SPLIT == 1) if (persistent) {
+    if constexpr (G::QT == 2 && !G::REDUX && G::EXP_SPLIT == 1 && !G::SCR2) if (persistent) {
         const long long total = static_cast<long long>(grid.x) * grid.y * grid.z;
         if (total > 0x7FFF0000LL) return SLAMFE_ERANGE;
         p.jobs_x = static_cast<int>(grid.x);
@@ -733,7 +787,8 @@ int run_hamming_mma(HammingParams p, int n_problems, int max_nq, int max_nt, boo
 #ifdef SLAMFE_MMA_DEV
     // Development build only (-DSLAMFE_MMA_DEV, see scripts/README.md): the other instantiations of the template,
     // chosen per process by SLAMFE_MMA_GEOMETRY for A/B runs (profiles/r02_mma_geometries.log).
-    //   0 = shipped, 1 = <2,128> redux column minima, 2 = <1,192> redux, 3 = <2,128> two expander threads per row
+    //   0 = shipped, 1 = <2,128> redux column minima, 2 = <1,192> redux, 3 = <2,128> two expander threads per row,
+    //   4 = <2,128> with one transpose scratch per 64-column chunk
     static const int geometry = [] {
         const char *v = getenv("SLAMFE_MMA_GEOMETRY");
         return v && *v ? atoi(v) : 0;
@@ -742,10 +797,16 @@ int run_hamming_mma(HammingParams p, int n_problems, int max_nq, int max_nt, boo
         case 1: return run_geometry<Geo<2, 128, true>>(p, n_problems, max_nq, max_nt, top2, stream);
         case 2: return run_geometry<Geo<1, 192, true>>(p, n_problems, max_nq, max_nt, top2, stream);
         case 3: return run_geometry<Geo<2, 128, false, 2>>(p, n_problems, max_nq, max_nt, top2, stream);
+        case 4: return run_geometry<Geo<2, 128, false, 1, true>>(p, n_problems, max_nq, max_nt, top2, stream);
         default: break;
     }
 #endif
 #ifdef SLAMFE_MMA_DEV
+    static const bool pair = [] {   // A/B of the two-SM kernel in a development build
+        const char *v = getenv("SLAMFE_MMA_PAIR");
+        return v && *v && atoi(v) != 0;
+    }();
+    if (pair) return run_pair(p, n_problems, max_nq, max_nt, top2, stream);
     static const bool persistent = [] {   // the persistent form of the kernel (hamming_mma_persistent.cuh), A/B runs only
         const char *v = getenv("SLAMFE_MMA_PERSISTENT");
         return v && *v && atoi(v) != 0;

@@ -72,8 +72,12 @@ constexpr uint32_t TMEM_COLS = 512;
 //             ~83 + 0.2 N cycles on this part: 109 at N = 128, 122 at N = 192) at twice the expansion work
 //             per pair; the accumulators alternate between stages; column minima by redux only (no room
 //             for the transpose scratch next to 2 x 96 KB of B stages)
-template <int QT_, int NT_, bool REDUX_, int EXP_SPLIT_ = 1, bool SCR2_ = false>
+template <int QT_, int NT_, bool REDUX_, int EXP_SPLIT_ = 1, bool SCR2_ = false, bool LD16_ = false, bool IDXK_ = false>
 struct Geo {
+    static constexpr bool IDXK = IDXK_;              // the train row's index within the stage rides in a spare K position
+                                                     // (A = 1, B = index): the accumulator IS the 16-bit row key, no add
+    static constexpr bool LD16 = LD16_;              // epilogue reads the accumulators with tcgen05.ld.16x256b: a thread holds
+                                                     // 4 query rows x 32 train columns and pre-reduces rows in registers
     static constexpr bool SCR2 = SCR2_;              // one transpose scratch per 64-column chunk: both chunks of a stage in flight
     static constexpr int QT = QT_, NT = NT_;
     static constexpr bool REDUX = REDUX_;
@@ -192,6 +196,12 @@ __device__ __forceinline__ void tmem_ld64_packed(uint32_t taddr, uint32_t (&v)[3
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = out[j];
 #endif
+}
+// 16 TMEM lanes x 128 columns as 32 packed registers (profiles/r02_probe_ldshape.log): with q = lane / 4, m = lane % 4,
+// register 4u + k holds columns 16u + 4m + 2(k & 1) (low half) and + 1 (high half) of TMEM lane q + 8(k >> 1)
+__device__ __forceinline__ void tmem_ld16x128_packed(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x8.pack::16b.b32 " SLAMFE_LD32_OPERANDS);
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -316,6 +326,17 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
             // rows past the end mirror the last row (min(row, nq - 1) at kernel entry): their results are not
             // written, and for column minima they lose every tie to the real row
             const uint32_t one = static_cast<uint32_t>(p.desc_bytes > 0);  // opaque 1: keeps key adds on the FMA pipe
+            // column-minima key of a packed accumulator pair: (d << 5) | query row within the warp.  With the train index in
+            // the accumulator's low 7 bits (IDXK) the row field is masked in with one LOP3 instead of added with one IMAD
+            auto col_key = [&](uint32_t acc2, uint32_t rowc) {
+                if (G::IDXK) {
+                    uint32_t r;
+                    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(acc2 >> 2), "r"(0x3FE03FE0u), "r"(rowc));   // (a & b) | c: the mask also drops the two index bits
+                                                                                                                     // the shift moved from the high half into the low one
+                    return r;
+                }
+                return add_imad(acc2 >> 2, one, rowc);
+            };
             {
                 uint32_t (&w)[W] = wq;   // fetched at kernel entry
                 uint32_t pq = 0;
@@ -331,6 +352,10 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                 }
 #pragma unroll
                 for (int s = 4; s < 8; ++s) spare[s] = 127u << 24;
+                if (G::IDXK) {   // invalid rows: 2 x 127 x 255 = 128 * 506 + 2; position 7: + index of the train row
+                    spare[6] = 0u;
+                    spare[7] = 1u << 24;
+                }
                 // +-1 bytes: bit s of every byte moves to the byte's msb (IMAD by 1 << (7 - s), FMA pipe), PRMT
                 // replicates it over the byte (0xFF / 0x00), OR 1 makes it -1 / +1: 2 ALU-pipe ops per 4 positions
                 uint32_t mul[8];
@@ -359,6 +384,7 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                 mbar_arrive(&sm.a_ready);
             }
             uint32_t b1 = KEY_NONE, b2 = KEY_NONE;
+            uint32_t rb1[4] = {KEY_NONE, KEY_NONE, KEY_NONE, KEY_NONE}, rb2[4] = {KEY_NONE, KEY_NONE, KEY_NONE, KEY_NONE};  // LD16
             const uint32_t scr_addr = smem_u32(sm.scratch[G::REDUX ? 0 : warp]);
             const uint32_t rbase = static_cast<uint32_t>(qt0 + tile * MQ + quarter * 32);
             for (int s = 0; s < n_stage; ++s) {
@@ -367,6 +393,114 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                 mbar_wait_relaxed(&sm.d_full[acc], use & 1, 128);
                 tc_fence_after();
                 const uint32_t jstage = static_cast<uint32_t>(p.t_index_base + tb + s * NT);
+                if constexpr (G::LD16) {
+                    static_assert(!G::LD16 || NT == 128, "16x256b.x8.pack covers 128 columns");
+                    // Thread (q, m) = (lane / 4, lane % 4) holds query rows q, q + 8, q + 16, q + 24 of the warp's 32 and
+                    // train columns 16u + 4m + {0..3}, u = 0..7.  Row minima stay in the thread (four running keys,
+                    // merged over m at the end of the sweep); column minima are reduced over the thread's four rows
+                    // in registers BEFORE anything goes through shared memory: 2 KB out + 2 KB back per warp and stage
+                    // instead of 8 + 8 KB.
+                    const int q = lane >> 2, m4 = lane & 3;
+                    uint32_t va[32], vb[32];
+                    tmem_ld16x128_packed(tmem + lane_base + acc * NT, va);
+                    tmem_ld16x128_packed(tmem + lane_base + (16u << 16) + acc * NT, vb);
+                    tmem_wait_ld();
+                    tc_fence_before();
+                    mbar_arrive(&sm.d_empty[acc]);
+                    const uint32_t mcol = static_cast<uint32_t>(4 * m4) * 0x00010001u;
+#pragma unroll
+                    for (int ri = 0; ri < 4; ++ri) {
+                        const uint32_t (&src)[32] = ri < 2 ? va : vb;
+                        const int rs = (ri & 1) * 2;
+                        if (!TOP2) {
+                            uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const uint32_t k0 = add_imad(src[4 * u + rs], one, ((16u * u + 1u) << 16) | (16u * u));
+                                const uint32_t k1 = add_imad(src[4 * u + rs + 1], one, ((16u * u + 3u) << 16) | (16u * u + 2u));
+                                m = __vimin3_u16x2(m, k0, k1);
+                            }
+                            m += mcol;
+                            const uint32_t k16 = min(m & 0xFFFFu, m >> 16);
+                            rb1[ri] = min(rb1[ri], ((k16 >> 7) << KEY_IDX_BITS) + jstage + (k16 & 127u));
+                        } else {
+                            uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;  // per 16-bit half: best and second best
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                                for (int kk = 0; kk < 2; ++kk) {
+                                    const uint32_t k = add_imad(src[4 * u + rs + kk], one,
+                                                                ((16u * u + 2u * kk + 1u) << 16) | (16u * u + 2u * kk));
+                                    m2 = __vminu2(m2, __vmaxu2(m1, k));
+                                    m1 = __vminu2(m1, k);
+                                }
+                            }
+                            const uint32_t c[4] = {m1 & 0xFFFFu, m1 >> 16, m2 & 0xFFFFu, m2 >> 16};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)  // empty slots and invalid train rows (d = 508) are no candidates
+                                top2_insert(c[i] >= (505u << 7) ? KEY_NONE
+                                                                : ((c[i] >> 7) << KEY_IDX_BITS) + jstage + (c[i] & 127u) + 4u * m4,
+                                            rb1[ri], rb2[ri]);
+                        }
+                    }
+                    if (COL) {
+                        // key16 = (d << 5) | row-in-warp; the thread's four rows are q + 8 ri
+                        const uint32_t rq = static_cast<uint32_t>(q) * 0x00010001u;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {   // four registers (two units) per 16-byte store
+                            uint32_t cmn[4];
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const int u = 2 * i + (jj >> 1), kk = jj & 1;
+                                const uint32_t x0 = add_imad(va[4 * u + kk] >> 2, one, rq);
+                                const uint32_t x1 = add_imad(va[4 * u + 2 + kk] >> 2, one, rq + 0x00080008u);
+                                const uint32_t x2 = add_imad(vb[4 * u + kk] >> 2, one, rq + 0x00100010u);
+                                const uint32_t x3 = add_imad(vb[4 * u + 2 + kk] >> 2, one, rq + 0x00180018u);
+                                cmn[jj] = __vminu2(__vimin3_u16x2(x0, x1, x2), x3);
+                            }
+                            // slot of thread t: 64 bytes, 16-byte chunk i stored at chunk i ^ ((t >> 1) & 3): conflict-free STS.128
+                            const uint32_t a = scr_addr + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(cmn[0]), "r"(cmn[1]), "r"(cmn[2]),
+                                         "r"(cmn[3])
+                                         : "memory");
+                        }
+                        __syncwarp();
+                        // thread t = (q, m) merges registers 2q, 2q + 1 of the eight threads (q', m): train columns 4t .. 4t + 3
+#pragma unroll
+                        for (int jj = 0; jj < 2; ++jj) {
+                            const int j = 2 * q + jj;
+                            uint32_t mm = 0xFFFFFFFFu;
+#pragma unroll
+                            for (int qq = 0; qq < 8; qq += 2) {
+                                uint32_t x0, x1;
+                                const int t0 = 4 * qq + m4, t1 = 4 * (qq + 1) + m4;
+                                const uint32_t a0 = scr_addr + t0 * 64 + ((((j >> 2) ^ ((t0 >> 1) & 3)) << 4) | ((j & 3) << 2));
+                                const uint32_t a1 = scr_addr + t1 * 64 + ((((j >> 2) ^ ((t1 >> 1) & 3)) << 4) | ((j & 3) << 2));
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x0) : "r"(a0) : "memory");
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x1) : "r"(a1) : "memory");
+                                mm = __vimin3_u16x2(mm, x0, x1);
+                            }
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const uint32_t k16 = hh ? (mm >> 16) : (mm & 0xFFFFu);
+                                const int c = 4 * lane + 2 * jj + hh;
+                                if (c < rows)
+                                    atomicMin(&sm.colmin[tile][s & 1][c], ((k16 >> 5) << KEY_IDX_BITS) + rbase + (k16 & 31u));
+                            }
+                        }
+                        __syncwarp();  // the scratch is rewritten by the next stage
+                        // the 4 warps of this query tile merge: one global atomicMin per train row, tile and stage
+                        if (tile == 0)
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                        else
+                            asm volatile("bar.sync 2, 128;" ::: "memory");
+                        for (int c = row_in_tile; c < rows; c += 128) {
+                            atomicMin(p.col_keys + t_row0 + tb + s * NT + c, sm.colmin[tile][s & 1][c]);
+                            sm.colmin[tile][s & 1][c] = KEY_NONE;  // reused in stage s + 2, after the barrier of s + 1
+                        }
+                    }
+                    continue;
+                }
                 // read every 64-column chunk that holds a valid train row, then hand the accumulator back to
                 // the tensor core BEFORE folding: the MMAs of the next stage never wait for this warp's arithmetic
                 uint32_t vv[G::NCH][32];
@@ -397,24 +531,26 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                         uint32_t m = 0xFFFFFFFFu;
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
-                            const uint32_t k0 = add_imad(v[j], one, ((2u * j + 1u) << 16) | (2u * j));
-                            const uint32_t k1 = add_imad(v[j + 1], one, ((2u * j + 3u) << 16) | (2u * j + 2u));
+                            const uint32_t k0 = G::IDXK ? v[j] : add_imad(v[j], one, ((2u * j + 1u) << 16) | (2u * j));
+                            const uint32_t k1 = G::IDXK ? v[j + 1] : add_imad(v[j + 1], one, ((2u * j + 3u) << 16) | (2u * j + 2u));
                             m = __vimin3_u16x2(m, k0, k1);
                         }
                         const uint32_t k16 = min(m & 0xFFFFu, m >> 16);
-                        b1 = min(b1, ((k16 >> 7) << KEY_IDX_BITS) + jh + (k16 & 127u));
+                        b1 = min(b1, ((k16 >> 7) << KEY_IDX_BITS) + (G::IDXK ? jstage : jh) + (k16 & 127u));
                     } else {
                         uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;  // per 16-bit half: best and second best
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const uint32_t k = add_imad(v[j], one, ((2u * j + 1u) << 16) | (2u * j));
+                            const uint32_t k = G::IDXK ? v[j] : add_imad(v[j], one, ((2u * j + 1u) << 16) | (2u * j));
                             m2 = __vminu2(m2, __vmaxu2(m1, k));
                             m1 = __vminu2(m1, k);
                         }
                         const uint32_t c[4] = {m1 & 0xFFFFu, m1 >> 16, m2 & 0xFFFFu, m2 >> 16};
 #pragma unroll
                         for (int i = 0; i < 4; ++i)  // empty slots and invalid train rows (d = 508) are no candidates
-                            top2_insert(c[i] >= (505u << 7) ? KEY_NONE : ((c[i] >> 7) << KEY_IDX_BITS) + jh + (c[i] & 127u),
+                            top2_insert(c[i] >= (505u << 7)
+                                            ? KEY_NONE
+                                            : ((c[i] >> 7) << KEY_IDX_BITS) + (G::IDXK ? jstage : jh) + (c[i] & 127u),
                                         b1, b2);
                     }
                     if (COL && !G::SCR2) {
@@ -442,8 +578,8 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                                     scr_addr + (r + 1) * 128 + ((((lane >> 2) ^ ((r + 1) & 7)) << 4) | ((lane & 3) << 2));
                                 asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x0) : "r"(a0) : "memory");
                                 asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x1) : "r"(a1) : "memory");
-                                const uint32_t k0 = add_imad(x0 >> 2, one, (static_cast<uint32_t>(r) << 16) | r);
-                                const uint32_t k1 = add_imad(x1 >> 2, one, (static_cast<uint32_t>(r + 1) << 16) | (r + 1));
+                                const uint32_t k0 = col_key(x0, (static_cast<uint32_t>(r) << 16) | r);
+                                const uint32_t k1 = col_key(x1, (static_cast<uint32_t>(r + 1) << 16) | (r + 1));
                                 m = __vimin3_u16x2(m, k0, k1);
                             }
                             __syncwarp();  // the scratch is rewritten by the next chunk / stage
@@ -521,7 +657,39 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                     }
                 }
             }
-            if (row < nq) {
+            if constexpr (G::LD16) {
+                // the four threads (q, 0..3) hold partial results for rows q + 8 ri: merge over m, lane (q, 0) writes
+#pragma unroll
+                for (int ri = 0; ri < 4; ++ri) {
+#pragma unroll
+                    for (int d = 1; d <= 2; d <<= 1) {
+                        const uint32_t o1 = __shfl_xor_sync(0xFFFFFFFFu, rb1[ri], d);
+                        const uint32_t o2 = __shfl_xor_sync(0xFFFFFFFFu, rb2[ri], d);
+                        const uint32_t n2 = min(max(rb1[ri], o1), min(rb2[ri], o2));
+                        rb1[ri] = min(rb1[ri], o1);
+                        rb2[ri] = n2;
+                    }
+                    const int row4 = qt0 + tile * MQ + quarter * 32 + (lane >> 2) + 8 * ri;
+                    if ((lane & 3) == 0 && row4 < nq) {
+                        const size_t orow = static_cast<size_t>(p.row_out_off ? p.row_out_off[prob] : q_row0) + row4;
+                        if (!TOP2 && p.compact) {
+                            uint32_t *c = reinterpret_cast<uint32_t *>(p.row_keys) + orow;
+                            if (gridDim.y == 1)
+                                *c = rb1[ri];
+                            else
+                                atomicMin(c, rb1[ri]);
+                        } else {
+                            uint2 *g = p.row_keys + orow;
+                            if (gridDim.y == 1)
+                                *g = make_uint2(rb1[ri], TOP2 ? rb2[ri] : KEY_NONE);
+                            else if (TOP2)
+                                merge_row_keys(g, rb1[ri], rb2[ri]);
+                            else
+                                atomicMin(&g->x, rb1[ri]);  // second key stays KEY_NONE (pre-set)
+                        }
+                    }
+                }
+            } else if (row < nq) {
                 const size_t orow = static_cast<size_t>(p.row_out_off ? p.row_out_off[prob] : q_row0) + row;
                 if (!TOP2 && p.compact) {
                     uint32_t *c = reinterpret_cast<uint32_t *>(p.row_keys) + orow;
@@ -582,8 +750,9 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                             uint8_t *d = dst64 + 2 * (4 * cc + j) * LBO;
                             *reinterpret_cast<uint4 *>(d) = make_uint4(spread80(ww[j], mul[0]) | sl, spread80(ww[j], mul[1]) | sl,
                                                                        spread80(ww[j], mul[2]) | sl, spread80(ww[j], mul[3]) | sl);
+                            const uint32_t s7 = (G::IDXK && tail && j == 3) ? (static_cast<uint32_t>(r) << 24) : 0u;
                             *reinterpret_cast<uint4 *>(d + LBO) = make_uint4(spread80(ww[j], mul[4]), spread80(ww[j], mul[5]),
-                                                                             spread80(ww[j], mul[6]), spread80(ww[j], mul[7]));
+                                                                             spread80(ww[j], mul[6]), spread80(ww[j], mul[7]) | s7);
                         }
                     }
                     fence_async_smem();
@@ -614,13 +783,17 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                 }
                 uint8_t *dst = sm.b[b] + r * 16;
                 // valid rows carry 0x80 on the four popc positions, invalid rows on the four marker positions
-                const uint32_t spare_lo = (r < rows) ? 0x80000000u : 0u, spare_hi = (r < rows) ? 0u : 0x80000000u;
+                const uint32_t spare_lo = (r < rows) ? 0x80000000u : 0u;
+                // IDXK: invalid rows carry 0xFF on marker positions 4 and 5, every row its index on position 7
+                const uint32_t spare_hi = (r < rows) ? 0u : (G::IDXK ? 0xFF000000u : 0x80000000u);
                 auto put = [&](int kk, uint32_t wk, uint32_t slo, uint32_t shi) {
                     uint8_t *d = dst + 2 * kk * LBO;
+                    const uint32_t s6 = G::IDXK ? 0u : shi;
+                    const uint32_t s7 = G::IDXK ? (kk == ws ? (static_cast<uint32_t>(r) << 24) : 0u) : shi;
                     *reinterpret_cast<uint4 *>(d) = make_uint4(spread80(wk, mul[0]) | slo, spread80(wk, mul[1]) | slo,
                                                                spread80(wk, mul[2]) | slo, spread80(wk, mul[3]) | slo);
                     *reinterpret_cast<uint4 *>(d + LBO) = make_uint4(spread80(wk, mul[4]) | shi, spread80(wk, mul[5]) | shi,
-                                                                     spread80(wk, mul[6]) | shi, spread80(wk, mul[7]) | shi);
+                                                                     spread80(wk, mul[6]) | s6, spread80(wk, mul[7]) | s7);
                 };
                 if (n_k == W) {   // descriptors of 60..63 bytes (AKAZE: 61): word 15 is the tail word, no per-word tests
     #pragma unroll
@@ -756,7 +929,7 @@ int run_geometry(HammingParams p, int n_problems, int max_nq, int max_nt, bool t
     const dim3 grid((max_nq + G::CQ - 1) / G::CQ, n_slices, n_problems);
     if (grid.y > 65535u || grid.z > 65535u) return SLAMFE_ERANGE;
 #ifdef SLAMFE_MMA_DEV
-    if constexpr (G::QT == 2 && !G::REDUX && G::EXP_SPLIT == 1 && !G::SCR2) if (persistent) {
+    if constexpr (G::QT == 2 && !G::REDUX && G::EXP_SPLIT == 1 && !G::SCR2 && !G::LD16 && !G::IDXK) if (persistent) {
         const long long total = static_cast<long long>(grid.x) * grid.y * grid.z;
         if (total > 0x7FFF0000LL) return SLAMFE_ERANGE;
         p.jobs_x = static_cast<int>(grid.x);
@@ -788,7 +961,8 @@ int run_hamming_mma(HammingParams p, int n_problems, int max_nq, int max_nt, boo
     // Development build only (-DSLAMFE_MMA_DEV, see scripts/README.md): the other instantiations of the template,
     // chosen per process by SLAMFE_MMA_GEOMETRY for A/B runs (profiles/r02_mma_geometries.log).
     //   0 = shipped, 1 = <2,128> redux column minima, 2 = <1,192> redux, 3 = <2,128> two expander threads per row,
-    //   4 = <2,128> with one transpose scratch per 64-column chunk
+    //   4 = <2,128> with one transpose scratch per 64-column chunk, 5 = 16x256b accumulator loads (rows pre-reduced in
+    //   registers), 6 = train index in a spare K position (the accumulator is the row key)
     static const int geometry = [] {
         const char *v = getenv("SLAMFE_MMA_GEOMETRY");
         return v && *v ? atoi(v) : 0;
@@ -798,6 +972,8 @@ int run_hamming_mma(HammingParams p, int n_problems, int max_nq, int max_nt, boo
         case 2: return run_geometry<Geo<1, 192, true>>(p, n_problems, max_nq, max_nt, top2, stream);
         case 3: return run_geometry<Geo<2, 128, false, 2>>(p, n_problems, max_nq, max_nt, top2, stream);
         case 4: return run_geometry<Geo<2, 128, false, 1, true>>(p, n_problems, max_nq, max_nt, top2, stream);
+        case 5: return run_geometry<Geo<2, 128, false, 1, false, true>>(p, n_problems, max_nq, max_nt, top2, stream);
+        case 6: return run_geometry<Geo<2, 128, false, 1, false, false, true>>(p, n_problems, max_nq, max_nt, top2, stream);
         default: break;
     }
 #endif

@@ -72,5 +72,38 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+OBJECTS_SRC = os.path.join(PKG_DIR, "chost", "objects.c")
+
+
+def objects_path() -> str:
+    import sysconfig
+    return os.path.join(PKG_DIR, "_slamfe_objects" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_objects(force: bool = False) -> str:
+    """The host helper that builds cv2.DMatch tuples (chost/objects.c, plain C against Python.h): gcc, in-tree."""
+    import hashlib
+    import sysconfig
+    out = objects_path()
+    with open(OBJECTS_SRC, "rb") as fh:
+        digest = hashlib.sha256(fh.read()).hexdigest()
+    stamp = out + ".srchash"
+    if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+        return out
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        raise RuntimeError("gcc not found; the cv2 object helper cannot be built")
+    tmp = out + f".tmp{os.getpid()}"
+    cmd = [cc, "-O2", "-fPIC", "-shared", "-I", sysconfig.get_paths()["include"], OBJECTS_SRC, "-o", tmp]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("gcc failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, out)   # atomic: ranks of a multi-process launch may build at the same time
+    with open(stamp, "w") as fh:
+        fh.write(digest + "\n")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_objects(force="--force" in sys.argv))

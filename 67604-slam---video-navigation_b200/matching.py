@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import _cabi, ops
+from . import _cabi, _objects, ops
 
 try:  # cv2 provides the DMatch / KeyPoint container types the reference's callers consume
     import cv2
@@ -116,6 +116,9 @@ def _dmatches(qidx, tidx, dist):
     """Arrays -> tuple of cv2.DMatch(queryIdx, trainIdx, imgIdx=0, distance) (the 4-argument form:
     matcher output has imgIdx 0).  .tolist() first: building the objects from
     Python ints/floats is ~3x faster than from numpy scalars."""
+    fast = _objects.dmatch_tuple(qidx, tidx, dist)   # C helper: 0.15 us per object instead of 1 us
+    if fast is not None:
+        return fast
     n = len(qidx)
     return tuple(map(cv2.DMatch, np.asarray(qidx).tolist(), np.asarray(tidx).tolist(), [0] * n,
                      np.asarray(dist, dtype=np.float64).tolist()))
@@ -187,7 +190,11 @@ class Matcher:
         if k == 1:
             return tuple((m,) for m in first)
         has2 = idx2[:, 1] >= 0  # a single train row yields length-1 inner tuples (cv2 behaviour)
-        second = iter(_dmatches(qi[has2], idx2[has2, 1], dist2[has2, 1]))
+        seconds = _dmatches(qi[has2], idx2[has2, 1], dist2[has2, 1])
+        fast = _objects.knn_tuples(first, seconds, has2)
+        if fast is not None:
+            return fast
+        second = iter(seconds)
         return tuple((m, next(second)) if h else (m,) for m, h in zip(first, has2.tolist()))
 
 
@@ -217,8 +224,12 @@ def extract_inliers_outliers(kp_left, kp_right, matches):
         return np.array([]), np.array([])
     pl = _keypoint_array(kp_left)
     pr = _keypoint_array(kp_right)
-    mq = np.fromiter((m.queryIdx for m in matches), dtype=np.int32, count=n)
-    mt = np.fromiter((m.trainIdx for m in matches), dtype=np.int32, count=n)
+    fast = _objects.dmatch_indices(matches)
+    if fast is not None:
+        mq, mt = fast
+    else:
+        mq = np.fromiter((m.queryIdx for m in matches), dtype=np.int32, count=n)
+        mt = np.fromiter((m.trainIdx for m in matches), dtype=np.int32, count=n)
     mask = stereo_filter_mask(pl, pr, mq, mt)
     return np.array(np.nonzero(mask)[0].tolist()), np.array(np.nonzero(~mask)[0].tolist())
 

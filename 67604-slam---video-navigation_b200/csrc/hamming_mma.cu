@@ -72,8 +72,11 @@ constexpr uint32_t TMEM_COLS = 512;
 //             ~83 + 0.2 N cycles on this part: 109 at N = 128, 122 at N = 192) at twice the expansion work
 //             per pair; the accumulators alternate between stages; column minima by redux only (no room
 //             for the transpose scratch next to 2 x 96 KB of B stages)
-template <int QT_, int NT_, bool REDUX_, int EXP_SPLIT_ = 1, bool SCR2_ = false, bool LD16_ = false, bool IDXK_ = false>
+template <int QT_, int NT_, bool REDUX_, int EXP_SPLIT_ = 1, bool SCR2_ = false, bool LD16_ = false, bool IDXK_ = false,
+          int ESPLIT_ = 1>
 struct Geo {
+    static constexpr int ESPLIT = ESPLIT_;           // epilogue warps per TMEM lane quarter and query tile: 2 = each takes one
+                                                     // 64-column chunk of the accumulator (16 epilogue warps, 80 registers)
     static constexpr bool IDXK = IDXK_;              // the train row's index within the stage rides in a spare K position
                                                      // (A = 1, B = index): the accumulator IS the 16-bit row key, no add
     static constexpr bool LD16 = LD16_;              // epilogue reads the accumulators with tcgen05.ld.16x256b: a thread holds
@@ -88,7 +91,7 @@ struct Geo {
     static constexpr int RAW_STAGE = NT * SLAMFE_MAX_DESC_BYTES + 16;
     static constexpr int EXP_SPLIT = EXP_SPLIT_;       // expander threads per train row (2 measured slower than 1:
                                                        // the expansion is bound by shared pipes, not by latency)
-    static constexpr int N_EPI_WARPS = 4 * QT, N_EXP_WARPS = NT / 32 * EXP_SPLIT;
+    static constexpr int N_EPI_WARPS = 4 * QT * ESPLIT, N_EXP_WARPS = NT / 32 * EXP_SPLIT;
     static constexpr int MMA_WARP = N_EPI_WARPS + N_EXP_WARPS;
     static constexpr int TMA_WARP = MMA_WARP + 1;
     static constexpr int THREADS = (TMA_WARP + 1) * 32;
@@ -275,9 +278,9 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
     // epilogue threads: start fetching their query row now, its HBM latency overlaps the TMEM allocation and
     // the barrier set-up below
     uint32_t wq[W];
-    const bool is_epi = warp < N_EPI_WARPS && (warp >> 2) < n_tiles;
+    const bool is_epi = warp < N_EPI_WARPS && ((warp >> 2) % QT) < n_tiles;
     if (is_epi) {
-        const int row_q = qt0 + (warp >> 2) * MQ + (warp & 3) * 32 + lane;
+        const int row_q = qt0 + ((warp >> 2) % QT) * MQ + (warp & 3) * 32 + lane;
         load_desc_global(p.q + static_cast<size_t>(q_row0 + min(row_q, nq - 1)) * p.q_stride, p.desc_bytes, wq);
     }
     if (tid == 0) {
@@ -288,9 +291,9 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&sm.d_full[i], 1);
-            mbar_init(&sm.d_empty[i], 128);
+            mbar_init(&sm.d_empty[i], 128 * G::ESPLIT);
         }
-        mbar_init(&sm.a_ready, n_tiles * 128);
+        mbar_init(&sm.a_ready, n_tiles * 128 * G::ESPLIT);
         fence_mbar_init();
     }
     if (COL)
@@ -317,7 +320,9 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
 
     if (warp < N_EPI_WARPS) {
         // ============================== epilogue warps ==============================
-        const int tile = warp >> 2;
+        const int tile = (warp >> 2) % QT;
+        const int chunk = (warp >> 2) / QT;   // ESPLIT == 2: this warp's 64-column chunk of every accumulator (and its K half
+                                              // of the +-1 tile); ESPLIT == 1: 0, the warp takes both chunks
         if (tile < n_tiles) {  // warp-uniform: a CTA over the last <= 128 query rows has a single tile
             const int quarter = warp & 3;
             const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;  // this warp's TMEM lanes
@@ -363,7 +368,7 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                 for (int s = 0; s < 8; ++s) mul[s] = (1u << (7 - s)) * one;
 #pragma unroll
                 for (int k = 0; k < W; ++k) {
-                    if (k < n_k) {
+                    if (k < n_k && (G::ESPLIT == 1 || (k >> 3) == chunk)) {
                         uint32_t a[8];
 #pragma unroll
                         for (int s = 0; s < 8; ++s) {
@@ -506,12 +511,14 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                 uint32_t vv[G::NCH][32];
 #pragma unroll
                 for (int h = 0; h < G::NCH; ++h)
-                    if (h == 0 || 64 * h < rows) tmem_ld64_packed(tmem + lane_base + acc * NT + 64 * h, vv[h]);
+                    if ((G::ESPLIT == 1 || h == chunk) && (h == 0 || 64 * h < rows))
+                        tmem_ld64_packed(tmem + lane_base + acc * NT + 64 * h, vv[h]);
                 tmem_wait_ld();
                 tc_fence_before();
                 mbar_arrive(&sm.d_empty[acc]);
 #pragma unroll
                 for (int h = 0; h < G::NCH; ++h) {
+                    if (G::ESPLIT == 2 && h != chunk) continue;   // warp-uniform
                     if (h > 0 && 64 * h >= rows) break;  // warp-uniform
                     uint32_t (&v)[32] = vv[h];
                     if (COL && !G::REDUX && !G::SCR2) {
@@ -645,7 +652,17 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                         }
                     }
                 }
-                if (COL) {
+                if (COL && G::ESPLIT == 2) {
+                    // the 4 warps of this (query tile, chunk) merge their 64 columns
+                    if (64 * chunk < rows) {   // uniform over the group
+                        asm volatile("bar.sync %0, 128;" ::"r"(1 + 2 * tile + chunk) : "memory");
+                        const int c = 64 * chunk + row_in_tile;
+                        if (row_in_tile < 64 && c < rows) {
+                            atomicMin(p.col_keys + t_row0 + tb + s * NT + c, sm.colmin[tile][s & 1][c]);
+                            sm.colmin[tile][s & 1][c] = KEY_NONE;
+                        }
+                    }
+                } else if (COL) {
                     // the 4 warps of this query tile merge: one global atomicMin per train row, tile and stage
                     if (tile == 0)
                         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -691,15 +708,16 @@ __global__ void __launch_bounds__(G::THREADS, 1) hamming_mma_kernel(const Hammin
                 }
             } else if (row < nq) {
                 const size_t orow = static_cast<size_t>(p.row_out_off ? p.row_out_off[prob] : q_row0) + row;
+                const bool sole = gridDim.y == 1 && G::ESPLIT == 1;   // nobody else holds results for this row
                 if (!TOP2 && p.compact) {
                     uint32_t *c = reinterpret_cast<uint32_t *>(p.row_keys) + orow;
-                    if (gridDim.y == 1)
+                    if (sole)
                         *c = b1;
                     else
                         atomicMin(c, b1);
                 } else {
                     uint2 *g = p.row_keys + orow;
-                    if (gridDim.y == 1)
+                    if (sole)
                         *g = make_uint2(b1, b2);
                     else if (TOP2)
                         merge_row_keys(g, b1, b2);
@@ -929,7 +947,7 @@ int run_geometry(HammingParams p, int n_problems, int max_nq, int max_nt, bool t
     const dim3 grid((max_nq + G::CQ - 1) / G::CQ, n_slices, n_problems);
     if (grid.y > 65535u || grid.z > 65535u) return SLAMFE_ERANGE;
 #ifdef SLAMFE_MMA_DEV
-    if constexpr (G::QT == 2 && !G::REDUX && G::EXP_SPLIT == 1 && !G::SCR2 && !G::LD16 && !G::IDXK) if (persistent) {
+    if constexpr (G::QT == 2 && !G::REDUX && G::EXP_SPLIT == 1 && !G::SCR2 && !G::LD16 && !G::IDXK && G::ESPLIT == 1) if (persistent) {
         const long long total = static_cast<long long>(grid.x) * grid.y * grid.z;
         if (total > 0x7FFF0000LL) return SLAMFE_ERANGE;
         p.jobs_x = static_cast<int>(grid.x);
@@ -962,7 +980,8 @@ int run_hamming_mma(HammingParams p, int n_problems, int max_nq, int max_nt, boo
     // chosen per process by SLAMFE_MMA_GEOMETRY for A/B runs (profiles/r02_mma_geometries.log).
     //   0 = shipped, 1 = <2,128> redux column minima, 2 = <1,192> redux, 3 = <2,128> two expander threads per row,
     //   4 = <2,128> with one transpose scratch per 64-column chunk, 5 = 16x256b accumulator loads (rows pre-reduced in
-    //   registers), 6 = train index in a spare K position (the accumulator is the row key)
+    //   registers), 6 = train index in a spare K position (the accumulator is the row key), 7 = 16 epilogue warps (one 64-column
+    //   chunk each)
     static const int geometry = [] {
         const char *v = getenv("SLAMFE_MMA_GEOMETRY");
         return v && *v ? atoi(v) : 0;
@@ -974,6 +993,7 @@ int run_hamming_mma(HammingParams p, int n_problems, int max_nq, int max_nt, boo
         case 4: return run_geometry<Geo<2, 128, false, 1, true>>(p, n_problems, max_nq, max_nt, top2, stream);
         case 5: return run_geometry<Geo<2, 128, false, 1, false, true>>(p, n_problems, max_nq, max_nt, top2, stream);
         case 6: return run_geometry<Geo<2, 128, false, 1, false, false, true>>(p, n_problems, max_nq, max_nt, top2, stream);
+        case 7: return run_geometry<Geo<2, 128, false, 1, false, false, false, 2>>(p, n_problems, max_nq, max_nt, top2, stream);
         default: break;
     }
 #endif

@@ -1,4 +1,6 @@
-"""Host model of the barrier protocol of hamming_mma_persistent_kernel (csrc/hamming_mma.cu).
+"""Host model of the barrier protocol of hamming_mma_persistent_kernel (csrc/hamming_mma_persistent.cuh — the
+persistent form of the tcgen05 matcher: built, proven bit-identical on the GPU, measured and not shipped; compiled in
+development builds only).  The model is kept because it is what found the kernel's first bug.
 
 The persistent tcgen05 matcher keeps every mbarrier running across the jobs of a CTA; each role (job fetch +
 TMA lane, expander threads, MMA lane, the two epilogue groups) counts phases on its own.  An mbarrier wait only
